@@ -1,0 +1,336 @@
+"""TEST INFRASTRUCTURE -- generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+The reference ships no tests, golden vectors or fixtures, and the
+``ue_trace_10k.npy`` it names is missing from the mount (.MISSING_LARGE_BLOBS:2).  These
+bundles are therefore produced by importing the reference's own modules through
+``oracle/ref_loader.py`` and recording what they compute on seeded inputs.  They pin
+``oracle/mobi_oracle.c`` (tests/test_oracle_golden.py) and travel to the GPU box, where
+/root/reference does not exist.
+
+Bundles
+  ref_trace_replay.npz  read_trace mode, 2001 step_test calls (BASELINE config 1 with a fixed action
+                        sequence): trace, actions, per-step decisions, SINR samples, rewards, state checksums.
+                        Fading = np.random.seed(FADE_SEED) global stream = RandomState(FADE_SEED).normal(0,2,(T+2,40,4)).
+  ref_group_replay.npz  group mode (the training path, env.step): every uniform and normal the reference drew
+                        (recorded through proxies), mobility state after construction, per-step outputs.
+  ref_mobility.npz      reference_point_group alone, 3000 ticks from RandomState(seed).rand stream: positions.
+  ref_bs_move.npz       BS_move + Decimal_to_Base_N over uniform and biased action sequences (lock-up included).
+  ref_dense_channel.npz LTEChannel(2048 UE, 32 BS) + BS_move driven directly for 3 steps (config 4 sizes).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader as rl  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TRACE_SEED = 20260101
+FADE_SEED = 12345
+ACT_SEED = 777
+
+
+def state_checksum(state):
+    """Exact integer checksum of a (nBS+1,G,G) count map: sum(state * w), w[p,x,y] = 1 + ((p*7919 + x*104729 + y*1299709) % 65521)."""
+    p, x, y = np.meshgrid(np.arange(state.shape[0]), np.arange(state.shape[1]), np.arange(state.shape[2]),
+                          indexing="ij")
+    w = 1 + ((p * 7919 + x * 104729 + y * 1299709) % 65521)
+    return float(np.sum(state * w))
+
+
+class _RandomProxy:
+    def __init__(self, log):
+        self._log = log
+
+    def normal(self, mean, sd, size=None):
+        v = np.random.normal(mean, sd, size)
+        self._log.append(np.atleast_1d(np.asarray(v, dtype=np.float64)).ravel().copy())
+        return v
+
+    def __getattr__(self, name):
+        return getattr(np.random, name)
+
+
+class _NpProxy:
+    """Stands in for the name `np` inside the reference's channel module so that every
+    np.random.normal draw (channel.py:240) is recorded; everything else delegates to numpy."""
+
+    def __init__(self, log):
+        self.random = _RandomProxy(log)
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+def gen_trace(T):
+    """A (T,40,2) trace 'generated from the group reference model' (README.md:31-32), recorded the way the
+    commented hooks do (mobile_env.py:192, main_test.py:69,114): env.ueLoc after each step."""
+    np.random.seed(TRACE_SEED)
+    env = rl.make_reference_env(4, 40, 100, "group")
+    out = np.zeros((T, 40, 2), dtype=np.int64)
+    with rl.quiet_stdout():
+        env.reset()
+        for t in range(T):
+            env.step(624)  # all BS stay; only UE movement matters
+            out[t] = env.ueLoc
+    return out
+
+
+def golden_trace_replay(T_steps=2001, T_trace=2100):
+    trace = gen_trace(T_trace)
+    assert trace.min() >= 0 and trace.max() <= 99
+    path = "/tmp/_uavenv_trace.npy"
+    np.save(path, trace)
+    actions = np.random.RandomState(ACT_SEED).randint(625, size=T_steps)
+    np.random.seed(FADE_SEED)
+    env = rl.make_reference_env(4, 40, 100, "read_trace", path)
+    ch = env.channel
+    ctor_cur = np.array(ch.current_BS)
+    with rl.quiet_stdout():
+        s0 = env.reset()
+    reset_cur = np.array(ch.current_BS)
+    reset_sinr = np.array(ch.current_BS_sinr)
+    cur = np.zeros((T_steps, 40), np.uint8)
+    n_out = np.zeros(T_steps, np.int32)
+    n_ho = np.zeros(T_steps, np.int32)
+    mean_sinr = np.zeros(T_steps)
+    reward = np.zeros(T_steps)
+    r_dissect = np.zeros((T_steps, 2))
+    bs_xy = np.zeros((T_steps, 4, 2), np.uint8)
+    digits = np.zeros((T_steps, 4), np.uint8)
+    chk = np.zeros(T_steps)
+    done = np.zeros(T_steps, np.uint8)
+    sinr_idx = np.array(sorted(set(list(range(100)) + list(range(0, T_steps, 50)) + [T_steps - 1])))
+    cur_sinr = np.zeros((len(sinr_idx), 40))
+    k = 0
+    with rl.quiet_stdout():
+        for t in range(T_steps):
+            before = np.array(ch.current_BS)
+            s, r, d, info = env.step_test(int(actions[t]))
+            after = np.array(ch.current_BS)
+            cur[t] = after
+            n_ho[t] = int(np.sum(before != after))  # derived: the reference drops fromBS/toBS (channel.py:165-167)
+            n_out[t] = int(round(info.outage_fraction * 40))
+            mean_sinr[t] = info.r_dissect[0] * 20
+            reward[t] = r
+            r_dissect[t] = info.r_dissect
+            bs_xy[t] = info.bs_loc[:, :2]
+            digits[t] = info.bs_actions
+            chk[t] = state_checksum(s)
+            done[t] = d
+            if t == sinr_idx[k]:
+                cur_sinr[k] = ch.current_BS_sinr
+                k += 1
+    fade_probe = np.random.RandomState(FADE_SEED).normal(0, 2, size=(3, 40, 4))
+    np.savez_compressed(
+        os.path.join(OUT, "ref_trace_replay.npz"),
+        trace=trace.astype(np.uint8), actions=actions.astype(np.int16), fade_seed=FADE_SEED,
+        fade_probe=fade_probe[:, :2, :], ctor_cur=ctor_cur.astype(np.uint8), reset_cur=reset_cur.astype(np.uint8),
+        reset_sinr=reset_sinr, reset_state_chk=state_checksum(s0),
+        cur=cur, n_out=n_out, n_ho=n_ho, mean_sinr=mean_sinr, reward=reward, r_dissect=r_dissect, bs_xy=bs_xy,
+        digits=digits, state_chk=chk, done=done, sinr_idx=sinr_idx, cur_sinr=cur_sinr,
+        trace_sha256=hashlib.sha256(trace.astype(np.int64).tobytes()).hexdigest(),
+    )
+    os.remove(path)
+    print("ref_trace_replay: %d steps, %d handovers, %d new outages" % (T_steps, n_ho.sum(), n_out.sum()))
+
+
+def golden_group_replay(n_steps=150, seed=424242):
+    mods = rl.load_reference()
+    um, chm = mods["ue_mobility"], mods["channel"]
+    ulog, nlog = [], []
+    real_rand, real_np = um.rand, chm.np
+
+    def rec_rand(*shape):
+        v = real_rand(*shape)
+        ulog.append(np.asarray(v, dtype=np.float64).ravel().copy())
+        return v
+
+    um.rand = rec_rand
+    chm.np = _NpProxy(nlog)
+    try:
+        np.random.seed(seed)
+        env = rl.make_reference_env(4, 40, 100, "group")
+        n_u_ctor = len(ulog)      # init draws (8 calls) + 201 ticks
+        u_ctor = np.concatenate(ulog)
+        f_ctor = np.concatenate(nlog)
+        assert f_ctor.size == 160
+        ue0 = np.array(env.ueLoc)
+        ulog.clear(); nlog.clear()
+        with rl.quiet_stdout():
+            s0 = env.reset()
+        u_reset = np.concatenate(ulog)
+        f_reset = np.concatenate(nlog)
+        reset_cur = np.array(env.channel.current_BS)
+        actions = np.random.RandomState(ACT_SEED + 1).randint(625, size=n_steps)
+        u_steps, u_len, f_steps = [], [], []
+        cur = np.zeros((n_steps, 40), np.uint8)
+        ue = np.zeros((n_steps, 40, 2), np.uint8)
+        cur_sinr = np.zeros((n_steps, 40))
+        n_out = np.zeros(n_steps, np.int32)
+        n_ho = np.zeros(n_steps, np.int32)
+        reward = np.zeros(n_steps)
+        chk = np.zeros(n_steps)
+        bs_xy = np.zeros((n_steps, 4, 2), np.uint8)
+        with rl.quiet_stdout():
+            for t in range(n_steps):
+                ulog.clear(); nlog.clear()
+                before = np.array(env.channel.current_BS)
+                s, r, d, info = env.step(int(actions[t]))
+                u = np.concatenate(ulog)
+                u_steps.append(u); u_len.append(u.size)
+                f_steps.append(np.concatenate(nlog))
+                cur[t] = env.channel.current_BS
+                ue[t] = env.ueLoc
+                cur_sinr[t] = env.channel.current_BS_sinr
+                n_ho[t] = int(np.sum(before != cur[t]))
+                n_out[t] = int(round(-info[0][1] * 40))
+                reward[t] = r
+                chk[t] = state_checksum(s)
+                bs_xy[t] = env.bsLoc[:, :2]
+    finally:
+        um.rand = real_rand
+        chm.np = real_np
+    np.savez_compressed(
+        os.path.join(OUT, "ref_group_replay.npz"),
+        seed=seed, u_ctor=u_ctor, n_u_ctor_calls=n_u_ctor, f_ctor=f_ctor.reshape(40, 4), ue0=ue0.astype(np.uint8),
+        u_reset=u_reset, f_reset=f_reset.reshape(40, 4), reset_cur=reset_cur.astype(np.uint8),
+        reset_state_chk=state_checksum(s0), actions=actions.astype(np.int16),
+        u_steps=np.concatenate(u_steps), u_len=np.array(u_len, np.int32),
+        f_steps=np.stack(f_steps).reshape(n_steps, 40, 4), cur=cur, ue=ue, cur_sinr=cur_sinr, n_out=n_out, n_ho=n_ho,
+        reward=reward, state_chk=chk, bs_xy=bs_xy,
+    )
+    print("ref_group_replay: %d steps, %d uniforms in ctor, arrivals in steps: %d"
+          % (n_steps, u_ctor.size, sum(1 for n in u_len if n > 40)))
+
+
+def golden_mobility(n_ticks=3000, seed=99):
+    mods = rl.load_reference()
+    um = mods["ue_mobility"]
+    np.random.seed(seed)
+    gen = um.reference_point_group([10, 10, 10, 10], dimensions=(100, 100), velocity=(0, 1), aggregation=0.8)
+    keep = np.arange(0, n_ticks, 25)
+    pos = np.zeros((len(keep), 40, 2))
+    cell_chk = np.zeros(n_ticks, np.int64)
+    k = 0
+    for t in range(n_ticks):
+        p = next(gen)
+        c = p.astype(int)
+        cell_chk[t] = int(np.sum(c[:, 0] * (np.arange(40) + 1) + c[:, 1] * (np.arange(40) + 41) * 101))
+        if k < len(keep) and t == keep[k]:
+            pos[k] = p
+            k += 1
+    # how many uniforms the reference consumed: draw one more and locate it in a flat stream
+    nxt = np.random.rand()
+    flat = np.random.RandomState(seed).rand(n_ticks * 60 + 1000)
+    n_used = int(np.flatnonzero(flat == nxt)[0])
+    np.savez_compressed(os.path.join(OUT, "ref_mobility.npz"), seed=seed, n_ticks=n_ticks, keep=keep, pos=pos,
+                        cell_chk=cell_chk, n_uniforms=n_used)
+    print("ref_mobility: %d ticks, %d uniforms" % (n_ticks, n_used))
+
+
+def golden_bs_move(n=4000):
+    mods = rl.load_reference()
+    um = mods["ue_mobility"]
+    init = np.array([[25, 25, 10], [25, 75, 10], [75, 25, 10], [75, 75, 10]])
+    runs = {}
+    rs = np.random.RandomState(5)
+    # uniform actions; actions biased toward the centre (provokes the permanent lock); wall-huggers
+    seqs = {
+        "uniform": rs.randint(625, size=n),
+        "biased": np.array([int(d[0] * 125 + d[1] * 25 + d[2] * 5 + d[3]) for d in
+                            np.stack([rs.choice(5, n, p=[.5, .1, .2, .1, .1]), rs.choice(5, n, p=[.5, .1, .1, .2, .1]),
+                                      rs.choice(5, n, p=[.1, .5, .2, .1, .1]), rs.choice(5, n, p=[.1, .5, .1, .2, .1])],
+                                     axis=1)]),
+        "walls": np.array([int(d[0] * 125 + d[1] * 25 + d[2] * 5 + d[3]) for d in
+                           np.stack([rs.choice(5, n, p=[.05, .6, .05, .25, .05]), rs.choice(5, n, p=[.05, .6, .25, .05, .05]),
+                                     rs.choice(5, n, p=[.6, .05, .05, .25, .05]), rs.choice(5, n, p=[.6, .05, .25, .05, .05])],
+                                    axis=1)]),
+    }
+    for name, acts in seqs.items():
+        loc = init.copy()
+        out = np.zeros((n, 4, 2), np.uint8)
+        dig = np.zeros((n, 4), np.uint8)
+        with rl.quiet_stdout():
+            for t in range(n):
+                loc, d = um.BS_move(loc, [1, 100, 1, 100], int(acts[t]), 2, 4, 5)
+                out[t] = loc[:, :2]
+                dig[t] = d
+        runs[name + "_actions"] = acts.astype(np.int16)
+        runs[name + "_loc"] = out
+        runs[name + "_digits"] = dig
+        print("ref_bs_move[%s]: final %s" % (name, out[-1].tolist()))
+    np.savez_compressed(os.path.join(OUT, "ref_bs_move.npz"), init=init[:, :2].astype(np.uint8), **runs)
+
+
+def golden_dense_channel(n_ue=2048, n_bs=32, n_steps=3, seed=31337):
+    """Config-4 sizes.  The env shell cannot build nBS != 4 (mobile_env.py:49-50,76), so LTEChannel and
+    BS_move -- both size-generic (channel.py:250-251, ue_mobility.py:204) -- are driven directly."""
+    mods = rl.load_reference()
+    um, chm = mods["ue_mobility"], mods["channel"]
+    rs = np.random.RandomState(seed)
+    G = 100
+    side = 6
+    pts = [(int(G * (2 * i + 1) / (2 * side)), int(G * (2 * j + 1) / (2 * side))) for i in range(side) for j in range(side)]
+    bs = np.array([[x, y, 10] for x, y in pts[:n_bs]])
+    ue_steps = rs.randint(0, G, size=(n_steps + 1, n_ue, 2))
+    digit_steps = rs.randint(0, 5, size=(n_steps, n_bs))
+    np.random.seed(seed + 1)   # fading stream = RandomState(seed+1).normal(0,2,(n_steps+1, n_ue, n_bs))
+    ch = chm.LTEChannel(n_ue, n_bs, [1, G, 1, G], ue_steps[0], bs)
+    ctor_cur = np.array(ch.current_BS)
+    ctor_sinr = np.array(ch.current_BS_sinr)
+    cur = np.zeros((n_steps, n_ue), np.uint8)
+    cur_sinr = np.zeros((n_steps, n_ue))
+    mean_sinr = np.zeros(n_steps)
+    n_out = np.zeros(n_steps, np.int32)
+    bs_out = np.zeros((n_steps, n_bs, 2), np.uint8)
+    chk = np.zeros(n_steps)
+    loc = bs.copy()
+    for t in range(n_steps):
+        # joint action overflows int64 for nBS=32 (mobile_env.py:104): apply the digits with one BS_move call per
+        # BS is NOT equivalent (lock test reads all BS), so build the arbitrary-precision joint action instead
+        action = 0
+        for d in digit_steps[t]:
+            action = action * 5 + int(d)
+        with rl.quiet_stdout():
+            loc, dig = um.BS_move(loc, [1, G, 1, G], action, 2, 4, 5)
+        assert np.array_equal(dig.astype(int), digit_steps[t])
+        amap, ms, no = ch.UpdateDroneNet(ue_steps[t + 1], loc)
+        cur[t] = ch.current_BS
+        cur_sinr[t] = ch.current_BS_sinr
+        mean_sinr[t] = ms
+        n_out[t] = no
+        bs_out[t] = loc[:, :2]
+        chk[t] = float(np.sum(amap * (1 + (np.arange(amap.size).reshape(amap.shape) % 8191))))
+        print("  dense step", t, "mean", ms, "nout", no)
+    np.savez_compressed(os.path.join(OUT, "ref_dense_channel.npz"), seed=seed, init_bs=bs[:, :2].astype(np.uint8),
+                        ue=ue_steps.astype(np.uint8), digits=digit_steps.astype(np.uint8), ctor_cur=ctor_cur.astype(np.uint8),
+                        ctor_sinr=ctor_sinr, cur=cur, cur_sinr=cur_sinr, mean_sinr=mean_sinr, n_out=n_out, bs_xy=bs_out,
+                        amap_chk=chk)
+    print("ref_dense_channel: done")
+
+
+if __name__ == "__main__":
+    if not rl.reference_available():
+        sys.exit("reference sources not found; run this in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["trace", "group", "mobility", "bs", "dense"]
+    if "bs" in which:
+        golden_bs_move()
+    if "mobility" in which:
+        golden_mobility()
+    if "group" in which:
+        golden_group_replay()
+    if "trace" in which:
+        golden_trace_replay()
+    if "dense" in which:
+        golden_dense_channel()
