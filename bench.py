@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the batched MobiEnvironment step hot path (BASELINE.json config[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is ONE batched env step over the rank's E = 4096 environments (default UAV-BS / UE counts, group
+reference-point mobility, Philox fading, random joint actions, dense float32 observation rewritten in full).
+Every 2000 steps (MAXSTEP) the envs are reset, as a rollout loop does.  Metric: env-steps/s summed over all
+ranks (UE-steps/s = 40 x that is reported alongside).  One JSON line on rank 0.
+
+  value      K steps back to back, actions already resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same through the host-buffer C-ABI call (uavenv_step_host): pinned host actions H2D,
+             kernel, rewards + done flags D2H, stream sync, every step
+  roofline   algorithmic bytes per launch (201 420 B per env-step) / mean launch duration
+             against the measured HBM copy peak of MEASURED_PEAKS.json
+  cpu_baseline  the C port of the reference step (oracle/, float64) on the host cores, bounded sample
+
+--impl reference times that C port on all host threads (the reference itself is Python 2 + numpy and cannot
+run in this image).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_BS, N_UE, GRID = 4, 40, 100
+N_GROUPS = 4
+MAXSTEP = 2000
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes_per_env_step(n_bs=N_BS, n_ue=N_UE, g=GRID, n_g=N_GROUPS) -> int:
+    """dense fp32 obs write + UE x,y / handover word r/w + serving SINR write + group state r/w
+    + BS xy r/w + action + per-env scalars."""
+    return 4 * (n_bs + 1) * g * g + n_ue * (2 * (8 + 4) + 4) + n_g * 2 * 24 + 16 + n_bs * 2 * 8 + 4 + 24
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_throughput(n_threads: int, envs_per_thread: int, steps: int, seed: int = 0):
+    """env-steps/s of the C port of the reference step (oracle/mobi_oracle.c, float64, dense float64 state rebuilt
+    and copied every step like the reference) on n_threads host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import mobi_oracle as orc
+    orc.lib()
+    cfg = orc.default_cfg(N_BS, N_UE, GRID, N_GROUPS)
+
+    def work(i):
+        t, _ = orc.bench_run(cfg, envs_per_thread, steps, seed=seed, env_id0=i * envs_per_thread)
+        return t
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(n_threads) as ex:
+        ts = list(ex.map(work, range(n_threads)))      # ctypes releases the GIL inside the C call
+    wall = time.perf_counter() - t0
+    return n_threads * envs_per_thread * steps / max(ts), max(ts), wall
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    envs_per_thread = 8
+    if args.warmup > 0:
+        cpu_port_throughput(cores, envs_per_thread, args.warmup)
+    v, t, _ = cpu_port_throughput(cores, envs_per_thread, args.steps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "ue_steps_per_s": v * N_UE,
+        "config": {"workload": "config[1]: default MobiEnvironment step (4 UAV-BS x 40 UE, grid 100, group mobility, "
+                               "random actions, dense obs rebuilt + copied per step)",
+                   "sample": "%d threads x %d envs per step" % (cores, envs_per_thread)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d threads x %d envs x %d steps of the C float64 port (oracle/mobi_oracle.c); the "
+                                   "reference itself is Python 2 and cannot run here" % (cores, envs_per_thread, args.steps)},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--obs", default="f32", choices=["f32", "f32_incremental", "none"])
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 500)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from drl_uav_cellularnet_b200 import BatchedMobiEnvironment
+    E = args.envs
+    env = BatchedMobiEnvironment(E, N_BS, N_UE, GRID, "group", precision=args.precision, obs=args.obs, seed=2026,
+                                 env_offset=rank * E, device=local_rank)
+    env.reset()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    pool = torch.randint(0, env.action_space_dim, (64, E), device=dev, dtype=torch.int64, generator=gen)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n, first):
+        for i in range(n):
+            env.step(pool[(first + i) % 64])
+            if (first + i + 1) % MAXSTEP == 0:
+                env.reset()                     # the rollout loop resets finished episodes (main.py:188-190)
+
+    run_steps(args.warmup, 0)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3 if sampler else 0.0)
+    barrier()
+    l0 = env.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    run_steps(args.steps, args.warmup)
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = env.launch_count - l0
+    ms = ev0.elapsed_time(ev1)
+    flags = env.check()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    n_e2e = args.e2e_steps or min(args.steps, 500)
+    act_host = torch.randint(0, env.action_space_dim, (8, E), dtype=torch.int64).pin_memory()
+    rew_host = torch.zeros(E, dtype=torch.float64).pin_memory()
+    done_host = torch.zeros(E, dtype=torch.uint8).pin_memory()
+    for i in range(3):
+        env.step_host(act_host[i % 8], rew_host, done_host)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    acc = 0.0
+    for i in range(n_e2e):
+        env.step_host(act_host[i % 8], rew_host, done_host)
+        acc += float(rew_host[0])               # the host consumes the step's result
+        if bool(done_host[0]):
+            env.reset()
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_envs = E * world
+        value = total_envs * args.steps / (ms * 1e-3)
+        e2e_value = total_envs * n_e2e / (ms_e2e * 1e-3)
+        b_env = algorithmic_bytes_per_env_step()
+        peak, peak_src = measured_peak_gbs()
+        per_launch_s = ms * 1e-3 / max(launches, 1)
+        achieved = b_env * E / per_launch_s / 1e9 if args.obs == "f32" else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.isfile(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get("env_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
+            "ue_steps_per_s": value * N_UE,
+            "config": {"workload": "config[1]: %d batched envs per GPU, 4 UAV-BS x 40 UE, grid 100, group-reference "
+                                   "mobility (float64), Philox fading, random joint actions, obs=%s, reset every 2000 steps"
+                                   % (E, args.obs),
+                       "envs_per_gpu": E, "n_bs": N_BS, "n_ue": N_UE, "grid_n": GRID, "precision": args.precision,
+                       "l2": "each step writes %.0f MB of observation (> 126 MB L2); no explicit flush" % (E * 4e-6 * (N_BS + 1) * GRID * GRID)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * 9,
+                    "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
+                    "note": "uavenv_step_host: pinned host actions in, rewards + done flags out, stream sync per step; "
+                            "the observation stays in HBM for the policy network"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_env,
+                         "kernel": "uavk::env_kernel<4,false>", "launch_us": per_launch_s * 1e6},
+            "clocks": clocks,
+            "device_error_flags": flags,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            v, tmax, wall = cpu_port_throughput(cores, 16, 4000)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d threads x 16 envs x 4000 steps of the C float64 port of the reference "
+                                              "step (oracle/mobi_oracle.c), %.1f s wall" % (cores, wall)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

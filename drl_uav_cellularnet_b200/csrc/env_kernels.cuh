@@ -1,0 +1,633 @@
+// Fused MobiEnvironment step / reset / constructor-pass kernels for sm_100a.
+//
+// One CTA owns one environment for the whole call: UE mobility tick -> BS move -> UE x BS channel pass ->
+// best server / time-to-trigger handover / new-outage count -> reward -> observation.  Nothing is exchanged
+// between environments (reference: one env object per worker, main.py:173), so the grid is E CTAs.
+//
+// Reference semantics restated here (file:line into the reference repo):
+//   mobile_env.py:150-194 / 196-233  step / step_test          -> env_kernel<.., MODE_STEP>
+//   mobile_env.py:115-148            reset                     -> MODE_RESET
+//   mobile_env.py:100 + channel.py:92-93,110  LTEChannel ctor  -> MODE_CTOR
+//   ue_mobility.py:409-523           reference_point_group     -> mob_tick
+//   ue_mobility.py:191-271,310-336   BS_move, Decimal_to_Base_N-> decode_action / bs_move_warp
+//   channel.py:220-269               gain / SINR               -> ue_channel_pass
+//   channel.py:138-176,216           UpdateDroneNet            -> ue_channel_pass (handover word)
+//   channel.py:387-409, ue_mobility.py:173-188  association / BS grid map -> obs_* functions
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "philox.cuh"
+
+namespace uavk {
+
+constexpr int MAX_BS = 32;
+constexpr int MAX_GROUPS = 32;
+constexpr int CTA_THREADS = 256;
+
+enum { MODE_STEP = 0, MODE_RESET = 1, MODE_CTOR = 2 };
+enum { MOB_GROUP = 0, MOB_TRACE = 1 };
+enum { FADE_PHILOX = 0, FADE_INJECTED = 1, FADE_NONE = 2 };
+enum { OBS_NONE = 0, OBS_F32 = 1, OBS_F32_INCREMENTAL = 3 };
+enum { ERR_ACTION = 1u, ERR_TRACE = 2u, ERR_CLAMP = 4u };
+enum { CTR_TICK = 0, CTR_EPOCH = 1, CTR_STEP = 2, CTR_AGG = 3, CTR_DEAGG = 4, CTR_STRIDE = 8 };
+
+// handover word, one per UE (channel.py:75-81,92-93): current_BS, the <=3 rows of bestBS_buf, its depth, and
+// whether the UE was in outage after the previous pass (membership in self.ue_out, channel.py:116,171-174)
+__device__ __forceinline__ uint32_t ho_pack(int cur, int f0, int f1, int f2, int depth, int outp) {
+    return (uint32_t)cur | ((uint32_t)f0 << 5) | ((uint32_t)f1 << 10) | ((uint32_t)f2 << 15) |
+           ((uint32_t)depth << 20) | ((uint32_t)outp << 22);
+}
+
+// Everything that is fixed for the lifetime of a handle.  Passed by value as a __grid_constant__ parameter.
+struct DevCfg {
+    int E, nBS, nUE, G, nG;
+    int mobility, fading, obs_mode;
+    int max_step, n_act, bs_step, lock_r2;
+    int deagg_len, agg_len;
+    uint32_t k0, k1;        // Philox key = seed
+    uint32_t env_offset;    // global id of env 0 of this handle
+    // float64 constants (parity path; reference operation order)
+    double grid_width, P, N, pl_a, pl_b, pl_dis, ant_gain, eq_loss, sh_mean, sh_sd, ho_thr, out_thr;
+    double v_min, v_max, aggr, max_xy, fl_max;
+    // float32 constants (fast path; log-domain form)
+    float f_q_scale;        // grid_width^2
+    float f_q_min;          // pl_dis^2: loss applies when q > f_q_min
+    float f_g0;             // ant_gain - eq_loss
+    float f_loss_a;         // pl_a
+    float f_loss_k;         // (pl_b / 2) * log10(2):   pl_b*log10(sqrt(q)) = f_loss_k * log2(q)
+    float f_exp_k;          // log2(10) / 10:           10^(g/10) = 2^(g * f_exp_k)
+    float f_log2P;          // log2(P)
+    float f_Pdb;            // 10 log10(P)
+    float f_db_k;           // 10 log10(2):             10 log10(x) = f_db_k * log2(x)
+    float f_N, f_sh_mean, f_sh_sd;
+    // persistent state (device)
+    double *x, *y;          // [E,nUE] float UE positions                      (ue_mobility.py:434-435)
+    double *th_u;           // [E,nUE] last theta uniform, injected-mobility runs only
+    double *grp;            // [E,6,nG] g_x g_y g_fl g_v g_cos g_sin           (ue_mobility.py:442-448)
+    int32_t *ctr;           // [E,8]   tick, epoch, step_n, aggregating, deaggregating
+    int16_t *bs_xy;         // [E,nBS,2]
+    int16_t *ue_cell;       // [E,nUE,2] integer UE cells                      (mobile_env.py:155)
+    uint32_t *ho;           // [E,nUE] handover words
+    const int16_t *init_bs; // [nBS,2]
+    const uint8_t *ue_group;// [nUE]   g_ref                                    (ue_mobility.py:423-426)
+    const int32_t *trace;   // [T,(E|1),nUE,2] or null
+    int64_t trace_T;
+    int trace_per_env;
+    uint32_t *err_flags;    // [1] sticky
+};
+
+struct CallArgs {
+    int mode;
+    int inject_mob;              // mob_u supplied
+    const int64_t *action;       // [E]
+    const uint8_t *digits;       // [E,nBS]
+    const double *fading;        // [E,nUE,nBS]
+    const double *mob_u;         // [E,nUE+3nG]
+    const uint8_t *env_mask;     // [E]
+    float *obs;                  // [E,nBS+1,G,G]
+    double *reward, *mean_sinr;  // [E]
+    int32_t *n_out, *n_ho, *n_blocked, *step_n;
+    uint8_t *done;
+    uint8_t *serving;            // [E,nUE]
+    void *serving_sinr;          // [E,nUE] f32 / f64
+    void *sinr_all;              // [E,nUE,nBS] f32 / f64
+    float *fading_used;          // [E,nUE,nBS]
+    int16_t *ue_xy, *bs_xy_out;  // [E,nUE,2], [E,nBS,2]
+    uint8_t *bs_digits;          // [E,nBS]
+};
+
+struct EnvShared {
+    double gx[MAX_GROUPS], gy[MAX_GROUPS], gfl[MAX_GROUPS], gv[MAX_GROUPS], gcos[MAX_GROUPS], gsin[MAX_GROUPS];
+    int refl[4][MAX_GROUPS];
+    int bsx[MAX_BS], bsy[MAX_BS];
+    int digit[MAX_BS];
+    double red_sinr[CTA_THREADS / 32];
+    int red_out[CTA_THREADS / 32], red_ho[CTA_THREADS / 32];
+    int ok, blocked;
+};
+
+// U(MIN,MAX,.) = rand*(MAX-MIN)+MIN (ue_mobility.py:408), no fused multiply-add
+__device__ __forceinline__ double U_(double lo, double hi, double r) { return __dadd_rn(__dmul_rn(r, hi - lo), lo); }
+
+constexpr double TWO_PI = 6.283185307179586;
+
+// ---------------------------------------------------------------------------------------------------------
+// One tick of the reference_point_group generator (ue_mobility.py:453-523) for the CTA's environment.
+// All threads of the CTA must call it.  `agg`/`deagg` are CTA-uniform register copies of the two counters.
+// inj: the uniforms the reference generator would draw this tick, in its order (theta[nUE], then for the k
+// arrived groups theta[k], fl[k], v[k]); null = Philox.  Returns nothing; UE cells are written to ue_cell.
+__device__ __forceinline__ void mob_tick(const DevCfg &c, EnvShared &s, int e, uint32_t genv, int tick, int &agg,
+                                         int &deagg, const double *inj, bool write_cells) {
+    const int tid = threadIdx.x;
+    const int nG = c.nG, nUE = c.nUE;
+    double *grp = c.grp + (size_t)e * 6 * nG;
+    if (tid < nG) {
+        const double gv = grp[3 * nG + tid], gc = grp[4 * nG + tid], gs = grp[5 * nG + tid];
+        s.gx[tid] = __dadd_rn(grp[0 * nG + tid], __dmul_rn(gv, gc));   // :458
+        s.gy[tid] = __dadd_rn(grp[1 * nG + tid], __dmul_rn(gv, gs));   // :459
+        s.gfl[tid] = grp[2 * nG + tid];
+        s.gv[tid] = gv; s.gcos[tid] = gc; s.gsin[tid] = gs;
+        s.refl[0][tid] = 0; s.refl[1][tid] = 0; s.refl[2][tid] = 0; s.refl[3][tid] = 0;
+    }
+    __syncthreads();
+    const bool aggregating = agg != 0;
+    for (int u = tid; u < nUE; u += blockDim.x) {
+        const size_t i = (size_t)e * nUE + u;
+        double x = c.x[i], y = c.y[i];
+        // direction drawn at the end of the previous tick (:508-510) or at init (:437-439)
+        double tu;
+        if (inj) tu = c.th_u[i];
+        else {
+            double b_;
+            if (tick == 0) philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, 0u, DOM_INIT_TH, tu, b_);
+            else philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, (uint32_t)(tick - 1), DOM_THETA, tu, b_);
+        }
+        double sn, cs;
+        sincos(U_(0.0, TWO_PI, tu), &sn, &cs);
+        x = __dadd_rn(x, cs);                                           // :455 (velocity 1.0, :436)
+        y = __dadd_rn(y, sn);                                           // :456
+        const int g = c.ue_group[u];
+        const double gvx = __dmul_rn(s.gv[g], s.gcos[g]), gvy = __dmul_rn(s.gv[g], s.gsin[g]);
+        if (aggregating) {                                              // :461-470
+            double sc, cc;
+            sincos(atan2(s.gy[g] - y, s.gx[g] - x), &sc, &cc);
+            x = __dadd_rn(__dadd_rn(x, gvx), __dmul_rn(c.aggr, cc));
+            y = __dadd_rn(__dadd_rn(y, gvy), __dmul_rn(c.aggr, sc));
+        } else {                                                        // :475-484
+            x = __dadd_rn(x, gvx);
+            y = __dadd_rn(y, gvy);
+        }
+        // reflecting walls, reference order (:490-505); a group flips once per wall if any member reflects
+        if (x < 0.0) { x = -x; s.refl[0][g] = 1; }
+        if (x > c.max_xy) { x = __dadd_rn(__dmul_rn(2.0, c.max_xy), -x); s.refl[1][g] = 1; }
+        if (y < 0.0) { y = -y; s.refl[2][g] = 1; }
+        if (y > c.max_xy) { y = __dadd_rn(__dmul_rn(2.0, c.max_xy), -y); s.refl[3][g] = 1; }
+        c.x[i] = x;
+        c.y[i] = y;
+        if (inj) c.th_u[i] = inj[u];
+        if (write_cells) {
+            // np.concatenate(...).astype(int): truncation toward zero (mobile_env.py:154-155).  A UE exactly on
+            // the far wall would index cell G (IndexError in the reference, ue_mobility.py:186): clamp + flag.
+            int cx = (int)x, cy = (int)y;
+            if (cx >= c.G || cy >= c.G) {
+                cx = min(cx, c.G - 1); cy = min(cy, c.G - 1);
+                atomicOr(c.err_flags, ERR_CLAMP);
+            }
+            reinterpret_cast<short2 *>(c.ue_cell)[i] = make_short2((short)cx, (short)cy);
+        }
+    }
+    // counters (:471-473, :485-487): uniform across the CTA
+    if (aggregating) { agg -= 1; if (agg == 0) deagg = c.deagg_len; }
+    else { deagg -= 1; if (deagg == 0) agg = c.agg_len; }
+    __syncthreads();
+    if (tid < 32) {
+        const int g = tid;
+        const bool live = g < nG;
+        double gc = 0, gs = 0, gfl = 0, gv = 0;
+        if (live) {
+            gc = s.gcos[g]; gs = s.gsin[g];
+            if (s.refl[0][g]) gc = -gc;
+            if (s.refl[1][g]) gc = -gc;
+            if (s.refl[2][g]) gs = -gs;
+            if (s.refl[3][g]) gs = -gs;
+            gv = s.gv[g];
+            gfl = __dadd_rn(s.gfl[g], -gv);                            // :513
+        }
+        const bool arrived = live && gv > 0.0 && gfl <= 0.0;           // :514
+        const unsigned am = __ballot_sync(0xffffffffu, arrived);
+        if (arrived) {                                                  // :515-521
+            double ut, uf, uv;
+            if (inj) {
+                const int k = __popc(am), r = __popc(am & ((1u << g) - 1u));
+                ut = inj[nUE + r]; uf = inj[nUE + k + r]; uv = inj[nUE + 2 * k + r];
+            } else {
+                double b_;
+                philox_uniform2(c.k0, c.k1, genv, (uint32_t)g, (uint32_t)tick, DOM_GRP_TF, ut, uf);
+                philox_uniform2(c.k0, c.k1, genv, (uint32_t)g, (uint32_t)tick, DOM_GRP_V, uv, b_);
+            }
+            sincos(U_(0.0, TWO_PI, ut), &gs, &gc);
+            gfl = U_(0.0, c.fl_max, uf);
+            gv = U_(c.v_min, c.v_max, uv);
+        }
+        if (live) {
+            grp[0 * nG + g] = s.gx[g]; grp[1 * nG + g] = s.gy[g];
+            grp[2 * nG + g] = gfl; grp[3 * nG + g] = gv;
+            grp[4 * nG + g] = gc; grp[5 * nG + g] = gs;
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Mobility init (ue_mobility.py:434-448) + warm-up ticks (mobile_env.py:77-79) + the tick that yields the
+// constructor's UE positions (mobile_env.py:93-97).  Philox only.
+__global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_constant__ DevCfg c, int warmup,
+                                                               int agg0, int deagg0) {
+    __shared__ EnvShared s;
+    const int e = blockIdx.x, tid = threadIdx.x;
+    const uint32_t genv = c.env_offset + (uint32_t)e;
+    for (int u = tid; u < c.nUE; u += blockDim.x) {
+        double a, b;
+        philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, 0u, DOM_INIT_XY, a, b);
+        c.x[(size_t)e * c.nUE + u] = U_(0.0, c.max_xy, a);
+        c.y[(size_t)e * c.nUE + u] = U_(0.0, c.max_xy, b);
+    }
+    if (tid < c.nG) {
+        double *grp = c.grp + (size_t)e * 6 * c.nG;
+        double a, b, sn, cs;
+        philox_uniform2(c.k0, c.k1, genv, (uint32_t)tid, 0u, DOM_INIT_GXY, a, b);
+        grp[0 * c.nG + tid] = U_(0.0, c.max_xy, a);
+        grp[1 * c.nG + tid] = U_(0.0, c.max_xy, b);                    // MAX_X (sic), ue_mobility.py:443
+        philox_uniform2(c.k0, c.k1, genv, (uint32_t)tid, 0u, DOM_INIT_GFV, a, b);
+        grp[2 * c.nG + tid] = U_(0.0, c.fl_max, a);
+        grp[3 * c.nG + tid] = U_(c.v_min, c.v_max, b);
+        philox_uniform2(c.k0, c.k1, genv, (uint32_t)tid, 0u, DOM_INIT_GTH, a, b);
+        sincos(U_(0.0, TWO_PI, a), &sn, &cs);
+        grp[4 * c.nG + tid] = cs;
+        grp[5 * c.nG + tid] = sn;
+    }
+    __syncthreads();
+    int agg = agg0, deagg = deagg0;
+    for (int t = 0; t <= warmup; t++) mob_tick(c, s, e, genv, t, agg, deagg, nullptr, t == warmup);
+    if (tid == 0) {
+        int32_t *ctr = c.ctr + (size_t)e * CTR_STRIDE;
+        ctr[CTR_TICK] = warmup + 1; ctr[CTR_EPOCH] = 0; ctr[CTR_STEP] = 0;
+        ctr[CTR_AGG] = agg; ctr[CTR_DEAGG] = deagg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BS_move (ue_mobility.py:191-271) by warp 0, lane i = BS i.  Sequential over BSs; the lock test compares
+// BS i's PRE-move cell with the others' CURRENT cells (ue_mobility.py:256-263) and blocks the move if any
+// is within lock radius.  Returns the number of blocked BSs (all lanes).
+__device__ __forceinline__ int bs_move_warp(const DevCfg &c, int &bx, int &by, int digit, int lane) {
+    const int s1 = c.bs_step, s2 = 2 * c.bs_step, G = c.G;
+    int px = bx, py = by;
+    switch (digit) {                                                   // :221-253 with [xMin,xMax,yMin,yMax]=[1,G,1,G]
+        case 0: if (bx + s1 < G) px = bx + s1; break;
+        case 1: if (bx - s1 > 1) px = bx - s1; break;
+        case 2: if (by + s1 < G) py = by + s1; break;
+        case 3: if (by - s1 > 1) py = by - s1; break;
+        case 5: if (bx + s2 < G) px = bx + s2; break;
+        case 6: if (bx - s2 > 1) px = bx - s2; break;
+        case 7: if (by + s2 < G) py = by + s2; break;
+        case 8: if (by - s2 > 1) py = by - s2; break;
+        default: break;                                                // 4 = stay
+    }
+    int blocked = 0;
+    for (int i = 0; i < c.nBS; i++) {
+        const int xi = __shfl_sync(0xffffffffu, bx, i), yi = __shfl_sync(0xffffffffu, by, i);
+        const int dx = bx - xi, dy = by - yi;
+        const bool col = lane < c.nBS && lane != i && (dx * dx + dy * dy <= c.lock_r2);
+        const unsigned m = __ballot_sync(0xffffffffu, col);
+        if (m) blocked++;
+        else if (lane == i) { bx = px; by = py; }                      // :265-266
+    }
+    return blocked;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <bool F64> struct Real { using T = float; };
+template <> struct Real<true> { using T = double; };
+
+// The channel pass of one UE against all BSs + its handover-word update.
+// NB: compile-time bound on nBS (register arrays).  Returns the serving-cell SINR (pre-handover cell,
+// channel.py:145-146) and updates `word`; flags receive new-outage / handover events.
+template <int NB, bool F64>
+__device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c, const CallArgs &a,
+                                                                 const EnvShared &s, int e, uint32_t genv, int u,
+                                                                 int cx, int cy, uint32_t epoch, int mode,
+                                                                 uint32_t &word, int &new_out, int &did_ho) {
+    using T = typename Real<F64>::T;
+    const int nBS = c.nBS;
+    const size_t pair0 = ((size_t)e * c.nUE + u) * nBS;
+    T fade[NB];
+    // ---- shadow fading, dB (channel.py:240) ----
+    if (c.fading == FADE_INJECTED) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) fade[b] = b < nBS ? (T)a.fading[pair0 + b] : (T)0;
+    } else if (c.fading == FADE_PHILOX) {
+        const int cpu = (nBS + 3) >> 2;
+#pragma unroll
+        for (int q = 0; q < (NB + 3) / 4; q++) {
+            if (4 * q < nBS) {
+                const Philox4 p = philox4x32_10(genv, (uint32_t)(u * cpu + q), epoch, DOM_FADING, c.k0, c.k1);
+                T z[4];
+                if constexpr (F64) normal4_f64(p, z); else normal4_f32(p, z);
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (4 * q + k < NB) {
+                        if constexpr (F64) fade[4 * q + k] = __dadd_rn(c.sh_mean, __dmul_rn(c.sh_sd, z[k]));
+                        else fade[4 * q + k] = fmaf(c.f_sh_sd, z[k], c.f_sh_mean);
+                    }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (4 * q + k < NB) fade[4 * q + k] = (T)0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < NB; b++) fade[b] = (T)0;
+    }
+    if (a.fading_used) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) if (b < nBS) a.fading_used[pair0 + b] = (float)fade[b];
+    }
+
+    T S[NB];   // SINR in dB per BS
+    if constexpr (F64) {
+        // reference operation order in float64 (channel.py:220-247, 259-269); no fma contraction
+        double p[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            p[b] = 0.0;
+            if (b < nBS) {
+                const double ax = __dadd_rn(__dmul_rn((double)cx, c.grid_width), -__dmul_rn((double)s.bsx[b], c.grid_width));
+                const double ay = __dadd_rn(__dmul_rn((double)cy, c.grid_width), -__dmul_rn((double)s.bsy[b], c.grid_width));
+                const double d = sqrt(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));     // :220-226
+                double loss = 0.0;
+                if (d > c.pl_dis) loss = __dadd_rn(c.pl_a, __dmul_rn(c.pl_b, log10(d)));    // :230-235
+                const double gdb = __dadd_rn(__dadd_rn(__dadd_rn(c.ant_gain, -loss), -fade[b]), -c.eq_loss);  // :245
+                p[b] = __dmul_rn(c.P, pow(10.0, gdb / 10.0));                               // :246, :264
+            }
+        }
+        double pre[NB], suf[NB];
+        if constexpr (NB > 8) {
+            // exclude-self interference as prefix + suffix sums (never total - own: SURVEY H4)
+            double acc = 0.0;
+#pragma unroll
+            for (int b = 0; b < NB; b++) { pre[b] = acc; acc = __dadd_rn(acc, p[b]); }
+            acc = 0.0;
+#pragma unroll
+            for (int b = NB - 1; b >= 0; b--) { suf[b] = acc; acc = __dadd_rn(acc, p[b]); }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            double interf;
+            if constexpr (NB > 8) interf = __dadd_rn(pre[b], suf[b]);
+            else {
+                interf = 0.0;                                          // np.sum over the other BSs in index order (:265)
+#pragma unroll
+                for (int j = 0; j < NB; j++) if (j != b && j < nBS) interf = __dadd_rn(interf, p[j]);
+            }
+            S[b] = b < nBS ? __dmul_rn(10.0, log10(p[b] / __dadd_rn(c.N, interf))) : -1.0e300;  // :266-268
+        }
+    } else {
+        // fp32 log-domain form: gdb[b] = g0 - (a + k log2 q) - fade;  p = 2^(gdb*ek + log2 P);
+        // S[b] = gdb[b] + Pdb - dbk * log2(N + sum_{j != b} p[j])
+        float gdb[NB], p[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            gdb[b] = 0.f; p[b] = 0.f;
+            if (b < nBS) {
+                const int dx = cx - s.bsx[b], dy = cy - s.bsy[b];
+                const float q = c.f_q_scale * (float)(dx * dx + dy * dy);
+                const float loss = q > c.f_q_min ? fmaf(c.f_loss_k, __log2f(q), c.f_loss_a) : 0.f;
+                gdb[b] = c.f_g0 - loss - fade[b];
+                p[b] = exp2f(fmaf(gdb[b], c.f_exp_k, c.f_log2P));
+            }
+        }
+        float pre[NB], suf[NB];
+        if constexpr (NB > 4) {
+            float acc = 0.f;
+#pragma unroll
+            for (int b = 0; b < NB; b++) { pre[b] = acc; acc += p[b]; }
+            acc = 0.f;
+#pragma unroll
+            for (int b = NB - 1; b >= 0; b--) { suf[b] = acc; acc += p[b]; }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            float interf;
+            if constexpr (NB > 4) interf = pre[b] + suf[b];
+            else {
+                interf = 0.f;
+#pragma unroll
+                for (int j = 0; j < NB; j++) if (j != b) interf += p[j];
+            }
+            S[b] = b < nBS ? (gdb[b] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + interf) : -3.0e38f;
+        }
+    }
+    if (a.sinr_all) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) if (b < nBS) reinterpret_cast<T *>(a.sinr_all)[pair0 + b] = S[b];
+    }
+
+    // ---- best server: first maximum (np.argmax / np.max, channel.py:141-142) ----
+    int best = 0;
+    T bestS = S[0];
+#pragma unroll
+    for (int b = 1; b < NB; b++) if (S[b] > bestS) { bestS = S[b]; best = b; }
+
+    // decisions are taken in float64 on the (exactly converted) SINR values in both precisions, so they are a
+    // pure function of the SINR matrix this pass produced
+    const double out_thr = c.out_thr, ho_thr = c.ho_thr;
+    T curS;
+    if (mode != MODE_STEP) {
+        // LTEChannel ctor / reset (channel.py:92-93,110,113-116): associate to the best server, FIFO = 1 row
+        curS = bestS;
+        word = ho_pack(best, best, 0, 0, 1, (double)bestS <= out_thr ? 1 : 0);
+        new_out = 0; did_ho = 0;
+    } else {
+        int cur = word & 31, f0 = (word >> 5) & 31, f1 = (word >> 10) & 31, f2 = (word >> 15) & 31;
+        int depth = (word >> 20) & 3;
+        const int outp = (word >> 22) & 1;
+        curS = S[0];
+#pragma unroll
+        for (int b = 1; b < NB; b++) if (b == cur) curS = S[b];        // serving SINR of the PRE-handover cell
+        bool remain;                                                   // channel.py:148-155
+        if (depth == 1) { f1 = best; depth = 2; remain = (f1 == f0); }
+        else if (depth == 2) { f2 = best; depth = 3; remain = (f1 == f0) && (f2 == f0); }
+        else { f0 = f1; f1 = f2; f2 = best; remain = (f1 == f0) && (f2 == f0); }
+        const bool need = remain && (cur != best) && ((double)bestS - (double)curS > ho_thr);   // :156-159
+        if (need) cur = best;                                          // :162-167
+        did_ho = need ? 1 : 0;
+        const int o = (double)curS <= out_thr ? 1 : 0;                 // :170
+        new_out = (o && !outp) ? 1 : 0;                                // :171-174
+        word = ho_pack(cur, f0, f1, f2, depth, o);
+    }
+    return curS;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Observation, float32 [nBS+1, G, G]: plane 0 = BS counts (GetGridMap, ue_mobility.py:173-188), plane 1+b =
+// UEs served by b after handover (GetCurrentAssociationMap, channel.py:387-409), indexed [plane, x, y].
+__device__ __forceinline__ void obs_zero_fill(float *obs_env, int n_cells) {
+    if ((n_cells & 3) == 0) {
+        float4 *o4 = reinterpret_cast<float4 *>(obs_env);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n4 = n_cells >> 2;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, z);
+    } else {
+        for (int i = threadIdx.x; i < n_cells; i += blockDim.x) obs_env[i] = 0.f;
+    }
+}
+
+template <int NB, bool F64>
+__global__ void __launch_bounds__(CTA_THREADS) env_kernel(const __grid_constant__ DevCfg c,
+                                                          const __grid_constant__ CallArgs a) {
+    using T = typename Real<F64>::T;
+    __shared__ EnvShared s;
+    const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mode = a.mode;
+    if (a.env_mask && !a.env_mask[e]) return;
+    const uint32_t genv = c.env_offset + (uint32_t)e;
+    const int nBS = c.nBS, nUE = c.nUE, G = c.G;
+    int32_t *ctr = c.ctr + (size_t)e * CTR_STRIDE;
+    int tick = ctr[CTR_TICK], epoch = ctr[CTR_EPOCH], step_n = ctr[CTR_STEP];
+    int agg = ctr[CTR_AGG], deagg = ctr[CTR_DEAGG];
+
+    // ---- validate + decode the action (Decimal_to_Base_N, ue_mobility.py:310-336: MSB first, digit 0 <-> BS 0)
+    if (tid == 0) {
+        int ok = 1;
+        if (mode == MODE_STEP) {
+            if (a.digits) {
+                for (int b = 0; b < nBS; b++) {
+                    const int d = a.digits[(size_t)e * nBS + b];
+                    s.digit[b] = d;
+                    if (d >= c.n_act) ok = 0;
+                }
+            } else if (a.action) {
+                long long cur = a.action[e];
+                if (cur < 0) { ok = 0; cur = 0; }
+                for (int pos = nBS - 1; pos >= 0; pos--) { s.digit[pos] = (int)(cur % c.n_act); cur /= c.n_act; }
+                if (cur != 0) ok = 0;                                  // more digits than BSs (reference fails at :334)
+            } else ok = 0;
+            if (!ok) atomicOr(c.err_flags, ERR_ACTION);
+        }
+        if (c.mobility == MOB_TRACE) {
+            const long long row = mode == MODE_STEP ? step_n : 0;      // mobile_env.py:203 / :87,130
+            if (!c.trace || row >= c.trace_T) { ok = 0; atomicOr(c.err_flags, ERR_TRACE); }
+        }
+        s.ok = ok;
+    }
+    __syncthreads();
+    if (!s.ok) return;                                                 // the env is left untouched
+
+    const bool incremental = c.obs_mode == OBS_F32_INCREMENTAL && a.obs && mode == MODE_STEP;
+    const int n_cells = (nBS + 1) * G * G;
+    float *obs_env = a.obs ? a.obs + (size_t)e * n_cells : nullptr;
+    const bool full_obs = obs_env && c.obs_mode != OBS_NONE && mode != MODE_CTOR && !incremental;
+
+    // ---- UE movement ----
+    if (c.mobility == MOB_GROUP) {
+        if (mode != MODE_CTOR) {                                       // mobile_env.py:152-155 / :122-127
+            const double *inj = a.inject_mob ? a.mob_u + (size_t)e * (nUE + 3 * c.nG) : nullptr;
+            if (incremental) {
+                // the cells of the previous step leave the association planes before ue_cell is overwritten
+                for (int u = tid; u < nUE; u += blockDim.x) {
+                    const short2 oc = reinterpret_cast<const short2 *>(c.ue_cell)[(size_t)e * nUE + u];
+                    const int ob = c.ho[(size_t)e * nUE + u] & 31;
+                    atomicAdd(obs_env + ((size_t)(1 + ob) * G + oc.x) * G + oc.y, -1.f);
+                }
+            }
+            mob_tick(c, s, e, genv, tick, agg, deagg, inj, true);
+            tick++;
+        }
+    } else {
+        const long long row = mode == MODE_STEP ? step_n : 0;
+        const int32_t *tr = c.trace + ((size_t)row * (c.trace_per_env ? c.E : 1) + (c.trace_per_env ? e : 0)) * nUE * 2;
+        for (int u = tid; u < nUE; u += blockDim.x) {
+            const size_t i = (size_t)e * nUE + u;
+            if (incremental) {
+                const short2 oc = reinterpret_cast<const short2 *>(c.ue_cell)[i];
+                const int ob = c.ho[i] & 31;
+                atomicAdd(obs_env + ((size_t)(1 + ob) * G + oc.x) * G + oc.y, -1.f);
+            }
+            const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
+            reinterpret_cast<short2 *>(c.ue_cell)[i] = make_short2((short)xy.x, (short)xy.y);
+        }
+    }
+
+    // ---- BS movement (warp 0) ----
+    if (warp == 0) {
+        int bx = 0, by = 0, blocked = 0;
+        if (lane < nBS) {
+            if (mode == MODE_RESET) {                                  // mobile_env.py:119
+                bx = c.init_bs[2 * lane]; by = c.init_bs[2 * lane + 1];
+            } else {
+                bx = c.bs_xy[((size_t)e * nBS + lane) * 2]; by = c.bs_xy[((size_t)e * nBS + lane) * 2 + 1];
+            }
+        }
+        const int ox = bx, oy = by;
+        if (mode == MODE_STEP) blocked = bs_move_warp(c, bx, by, lane < nBS ? s.digit[lane] : 4, lane);
+        if (lane < nBS) {
+            s.bsx[lane] = bx; s.bsy[lane] = by;
+            if (mode != MODE_CTOR) {
+                c.bs_xy[((size_t)e * nBS + lane) * 2] = (int16_t)bx;
+                c.bs_xy[((size_t)e * nBS + lane) * 2 + 1] = (int16_t)by;
+            }
+            if (a.bs_xy_out) {
+                a.bs_xy_out[((size_t)e * nBS + lane) * 2] = (int16_t)bx;
+                a.bs_xy_out[((size_t)e * nBS + lane) * 2 + 1] = (int16_t)by;
+            }
+            if (a.bs_digits && mode == MODE_STEP) a.bs_digits[(size_t)e * nBS + lane] = (uint8_t)s.digit[lane];
+            if (incremental && (ox != bx || oy != by)) {
+                atomicAdd(obs_env + (size_t)ox * G + oy, -1.f);
+                atomicAdd(obs_env + (size_t)bx * G + by, 1.f);
+            }
+        }
+        if (lane == 0) s.blocked = blocked;
+    }
+    // the dense observation is streamed out while the channel pass of this CTA (and of the other resident
+    // CTAs) is in flight; non-zero cells are added after the barrier below
+    if (full_obs) obs_zero_fill(obs_env, n_cells);
+    __syncthreads();
+
+    // ---- channel pass, one thread per UE ----
+    double sum_sinr = 0.0;
+    int cnt_out = 0, cnt_ho = 0;
+    for (int u = tid; u < nUE; u += blockDim.x) {
+        const size_t i = (size_t)e * nUE + u;
+        const short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
+        uint32_t word = mode == MODE_STEP ? c.ho[i] : 0u;
+        int new_out, did_ho;
+        const T curS = ue_channel_pass<NB, F64>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
+                                                new_out, did_ho);
+        c.ho[i] = word;
+        sum_sinr += (double)curS;
+        cnt_out += new_out;
+        cnt_ho += did_ho;
+        const int srv = word & 31;
+        if (a.serving) a.serving[i] = (uint8_t)srv;
+        if (a.serving_sinr) reinterpret_cast<T *>(a.serving_sinr)[i] = curS;
+        if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
+        if (full_obs || incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+    }
+    if (full_obs && tid < nBS) atomicAdd(obs_env + (size_t)s.bsx[tid] * G + s.bsy[tid], 1.f);
+
+    // ---- per-env reductions in a fixed order (warp tree, then warps in index order) ----
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_sinr += __shfl_down_sync(0xffffffffu, sum_sinr, o);
+        cnt_out += __shfl_down_sync(0xffffffffu, cnt_out, o);
+        cnt_ho += __shfl_down_sync(0xffffffffu, cnt_ho, o);
+    }
+    if (lane == 0) { s.red_sinr[warp] = sum_sinr; s.red_out[warp] = cnt_out; s.red_ho[warp] = cnt_ho; }
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        int no = 0, nh = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { tot += s.red_sinr[w]; no += s.red_out[w]; nh += s.red_ho[w]; }
+        const double mean = tot / (double)nUE;                         // channel.py:216
+        if (mode == MODE_STEP) {
+            step_n += 1;                                               // mobile_env.py:179
+            const double r0 = mean / 20.0, r1 = -1.0 * no / nUE;       // :165,167
+            const double r = __dadd_rn(r0, r1);
+            if (a.reward) a.reward[e] = r > -1.0 ? r : -1.0;           // :189
+            if (a.n_out) a.n_out[e] = no;
+            if (a.n_ho) a.n_ho[e] = nh;
+            if (a.n_blocked) a.n_blocked[e] = s.blocked;
+        } else if (mode == MODE_RESET) {
+            step_n = 0;                                                // :146
+        }
+        if (a.mean_sinr) a.mean_sinr[e] = mean;
+        if (a.done) a.done[e] = step_n >= c.max_step ? 1 : 0;          // :186-187
+        if (a.step_n) a.step_n[e] = step_n;
+        ctr[CTR_TICK] = tick; ctr[CTR_EPOCH] = epoch + 1; ctr[CTR_STEP] = step_n;
+        ctr[CTR_AGG] = agg; ctr[CTR_DEAGG] = deagg;
+    }
+}
+
+}  // namespace uavk

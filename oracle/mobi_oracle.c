@@ -107,6 +107,20 @@ void orc_philox_uniform2(uint64_t seed, uint32_t env, uint32_t idx, uint32_t seq
     *b = u53(w[2], w[3]);
 }
 
+/* four N(0,1) from one Philox call: (w0,w1) and (w2,w3) each feed one Box-Muller pair,
+ * u = (w + 0.5) * 2^-32 in (0,1) */
+void orc_philox_normal4(uint64_t seed, uint32_t env, uint32_t idx, uint32_t seq, uint32_t domain, double z[4]) {
+    uint32_t w[4];
+    orc_philox4x32(env, idx, seq, domain, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    for (int k = 0; k < 2; k++) {
+        double u1 = ((double)w[2 * k] + 0.5) * (1.0 / 4294967296.0);
+        double u2 = ((double)w[2 * k + 1] + 0.5) * (1.0 / 4294967296.0);
+        double r = sqrt(-2.0 * log(u1));
+        z[2 * k] = r * cos(6.283185307179586 * u2);
+        z[2 * k + 1] = r * sin(6.283185307179586 * u2);
+    }
+}
+
 enum {
     DOM_INIT_XY = 1, DOM_INIT_TH = 2, DOM_INIT_GXY = 3, DOM_INIT_GFV = 4, DOM_INIT_GTH = 5,
     DOM_THETA = 6, DOM_GRP_TF = 7, DOM_GRP_V = 8, DOM_FADING = 9, DOM_ACTION = 10
@@ -553,18 +567,24 @@ static int env_move_ues(orc_env *e, const double *mob_uniforms, int trace_row) {
     return 0;
 }
 
+void orc_philox_fading(const orc_cfg *c, uint64_t seed, uint32_t env_id, uint32_t epoch, double *out) {
+    const int nu = c->n_ue, nb = c->n_bs, cpu = (nb + 3) / 4;
+    for (int u = 0; u < nu; u++)
+        for (int q = 0; q < cpu; q++) {
+            double z[4];
+            orc_philox_normal4(seed, env_id, (uint32_t)(u * cpu + q), epoch, DOM_FADING, z);
+            for (int k = 0; k < 4 && 4 * q + k < nb; k++)
+                out[u * nb + 4 * q + k] = c->shadow_mean + c->shadow_sd * z[k];
+        }
+}
+
 static const double *env_fading(orc_env *e, const double *injected) {
     if (e->fading_mode == ORC_FADE_NONE) return NULL;
     if (e->fading_mode == ORC_FADE_INJECTED) return injected;
-    /* Philox: N(mean, sd) per pair, Box-Muller cosine branch (replaces np.random.normal, channel.py:240) */
-    const int nu = e->c.n_ue, nb = e->c.n_bs;
-    for (int u = 0; u < nu; u++)
-        for (int b = 0; b < nb; b++) {
-            double a, bb;
-            orc_philox_uniform2(e->seed, e->env_id, (uint32_t)(u * nb + b), e->epoch, DOM_FADING, &a, &bb);
-            double z = sqrt(-2.0 * log(1.0 - a)) * cos(TWO_PI * bb);
-            e->fade_buf[u * nb + b] = e->c.shadow_mean + e->c.shadow_sd * z;
-        }
+    /* Philox: N(mean, sd) per pair (replaces np.random.normal, channel.py:240).  One Philox4x32-10 call yields
+     * four normals (two Box-Muller pairs from 32-bit uniforms): BS b of UE u takes normal (b & 3) of call
+     * idx = u * ceil(nBS/4) + (b >> 2), sequence number = channel-pass epoch. */
+    orc_philox_fading(&e->c, e->seed, e->env_id, e->epoch, e->fade_buf);
     return e->fade_buf;
 }
 

@@ -55,6 +55,9 @@ void orc_philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                     uint32_t k0, uint32_t k1, uint32_t out[4]);
 void orc_philox_uniform2(uint64_t seed, uint32_t env, uint32_t idx, uint32_t seq,
                          uint32_t domain, double *a, double *b);
+void orc_philox_normal4(uint64_t seed, uint32_t env, uint32_t idx, uint32_t seq, uint32_t domain, double z[4]);
+/* the fading matrix (nUE,nBS) channel pass `epoch` of env `env_id` draws in Philox mode */
+void orc_philox_fading(const orc_cfg *c, uint64_t seed, uint32_t env_id, uint32_t epoch, double *out);
 
 /* ---- a4: reference_point_group, ue_mobility.py:409-523 ---- */
 typedef struct orc_mob orc_mob;

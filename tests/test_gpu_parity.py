@@ -1,0 +1,306 @@
+"""Parity tests proper: the CUDA path (through the C-ABI library) against the C oracle and against the
+fixtures recorded from the unmodified reference (tests/golden, oracle/make_golden.py).  Need a B200: -m gpu.
+
+Tolerances (BASELINE.json north_star): serving-BS indices, handover counts and outage counts bit-exact;
+SINR within 1e-3 dB; reward within 1e-5 relative.  The float64 parity kernels are held to far tighter bounds
+(1e-9 dB / 1e-9 relative); the fp32 kernels to the stated ones."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from oracle.make_golden import state_checksum
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+SINR_TOL_DB = 1e-3        # north_star tolerance
+REWARD_RTOL = 1e-5        # north_star tolerance
+F64_SINR_TOL_DB = 1e-9    # what the float64 kernels actually achieve (libm vs CUDA log10/pow: ~1e-13)
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import drl_uav_cellularnet_b200 as p
+    return p
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_trace_replay_matches_reference_fixture(pkg, golden_dir):
+    """BASELINE config 1: MobiEnvironment(4,40,100,"read_trace") replaying the regenerated trace for 2001
+    step_test calls with a fixed action sequence and the recorded fading, against outputs recorded from the
+    UNMODIFIED reference.  Decisions bit-exact; SINR / reward within the float64 bounds."""
+    g = _load(golden_dir, "ref_trace_replay.npz")
+    T = len(g["actions"])
+    fade = np.random.RandomState(int(g["fade_seed"])).normal(0, 2, size=(T + 2, 40, 4))
+    env = pkg.MobiEnvironment(4, 40, 100, "read_trace", trace=g["trace"], fading="injected")
+    assert float(env.state.sum()) == 0.0                           # zeros until the first reset (mobile_env.py:107)
+    env._b.ctor_pass(fading=fade[0][None])
+    assert np.array_equal(env.channel.current_BS, g["ctor_cur"])
+    s0 = env.reset(fading=fade[1])
+    assert np.array_equal(env.channel.current_BS, g["reset_cur"])
+    assert np.max(np.abs(env.channel.current_BS_sinr - g["reset_sinr"])) < F64_SINR_TOL_DB
+    assert state_checksum(s0) == float(g["reset_state_chk"])
+    sinr_rows = {int(t): i for i, t in enumerate(g["sinr_idx"])}
+    max_sinr_err = max_rew_rel = 0.0
+    for t in range(T):
+        s, r, d, info = env.step_test(np.array([g["actions"][t]]), fading=fade[2 + t])   # shape-(1,) as main_test.py:73
+        assert np.array_equal(env.channel.current_BS, g["cur"][t]), t
+        assert int(env._b.n_out[0]) == g["n_out"][t], t
+        assert int(env._b.n_ho[0]) == g["n_ho"][t], t
+        assert np.array_equal(info.bs_loc[:, :2], g["bs_xy"][t]), t
+        assert info.bs_actions.tolist() == g["digits"][t].tolist()
+        assert d == bool(g["done"][t])
+        assert info.step_n == t + 1
+        assert state_checksum(s) == float(g["state_chk"][t]), t
+        assert abs(float(env._b.mean_sinr[0]) - g["mean_sinr"][t]) < F64_SINR_TOL_DB
+        assert abs(info.outage_fraction - g["n_out"][t] / 40.0) < 1e-15
+        if abs(g["reward"][t]) > 0:
+            max_rew_rel = max(max_rew_rel, abs(r - g["reward"][t]) / abs(g["reward"][t]))
+        if t in sinr_rows:
+            max_sinr_err = max(max_sinr_err,
+                               float(np.max(np.abs(env.channel.current_BS_sinr - g["cur_sinr"][sinr_rows[t]]))))
+    assert max_sinr_err < F64_SINR_TOL_DB, max_sinr_err
+    assert max_rew_rel < 1e-9, max_rew_rel
+    with pytest.raises(IndexError):                                # past the end of the trace (mobile_env.py:203)
+        for _ in range(200):
+            env.step_test(0, fading=fade[0])
+
+
+def test_trace_replay_fp32_within_north_star_tolerance(pkg, golden_dir):
+    """Same replay through the fp32 kernels: SINR of every UE within 1e-3 dB of the reference at the sampled
+    steps, mean SINR within 1e-3 dB at every step, and every decision consistent (see _decisions_consistent)."""
+    g = _load(golden_dir, "ref_trace_replay.npz")
+    T = 600
+    fade = np.random.RandomState(int(g["fade_seed"])).normal(0, 2, size=(len(g["actions"]) + 2, 40, 4))
+    env = pkg.MobiEnvironment(4, 40, 100, "read_trace", trace=g["trace"], fading="injected", precision="fp32")
+    env._b.ctor_pass(fading=fade[0][None])
+    env.reset(fading=fade[1])
+    sinr_rows = {int(t): i for i, t in enumerate(g["sinr_idx"])}
+    worst = 0.0
+    n_diverged = 0
+    for t in range(T):
+        s, r, d, info = env.step_test(int(g["actions"][t]), fading=fade[2 + t])
+        same = np.array_equal(env.channel.current_BS, g["cur"][t])
+        n_diverged += 0 if same else 1
+        if same and t in sinr_rows:
+            worst = max(worst, float(np.max(np.abs(env.channel.current_BS_sinr - g["cur_sinr"][sinr_rows[t]]))))
+        if same:
+            assert abs(float(env._b.mean_sinr[0]) - g["mean_sinr"][t]) < SINR_TOL_DB
+            ref_r = g["reward"][t]
+            assert abs(r - ref_r) <= REWARD_RTOL * abs(ref_r) + 1e-6, (t, r, ref_r)
+    assert worst < SINR_TOL_DB, worst
+    assert n_diverged == 0      # 24k UE-steps: no near-tie flips expected (~4e-6 per UE-step)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_group_mobility_matches_reference_fixture(pkg, orc, golden_dir):
+    """Group mobility + channel driven by the uniforms / fading the UNMODIFIED reference drew
+    (ref_group_replay.npz): the GPU generator is initialised from the reference's init draws, ticked 201 times
+    (reset() is one tick) with the recorded uniforms, then reset + stepped against the recorded outputs."""
+    g = _load(golden_dir, "ref_group_replay.npz")
+    cfg = orc.default_cfg()
+    u = g["u_ctor"]
+    n, ng, G = 40, 4, 100.0
+    # ue_mobility.py:434-448 init draws, in reference order
+    x0, y0, th0 = u[0:n] * G, u[n:2 * n] * G, u[2 * n:3 * n]
+    k = 3 * n
+    gx, gy, gfl, gv = u[k:k + ng] * G, u[k + ng:k + 2 * ng] * G, u[k + 2 * ng:k + 3 * ng] * G, u[k + 3 * ng:k + 4 * ng]
+    gth = u[k + 4 * ng:k + 5 * ng] * (2 * np.pi)
+    k += 5 * ng
+    env = pkg.BatchedMobiEnvironment(1, 4, 40, 100, "group", fading="injected", precision="fp64", warmup_ticks=-1)
+    st = env.get_state()
+    st["x"][0], st["y"][0], st["theta_u"][0] = x0, y0, th0
+    st["group"][0] = np.stack([gx, gy, gfl, gv, np.cos(gth), np.sin(gth)])
+    st["counters"][0, :5] = [0, 0, 0, 200, 100]                    # tick, epoch, step_n, aggregating, deaggregating
+    env.set_state(st)
+    m = orc.Mobility(cfg, [10, 10, 10, 10])                        # the oracle walks alongside to size the draws
+    assert m.init(u) == k
+    dummy_fade = np.zeros((1, 40, 4))
+    xy = None
+    for tick in range(201):
+        uu = np.concatenate([u[k:k + 52], np.zeros(52)])[:52]
+        xy, used = m.tick(uu)
+        env.reset(fading=dummy_fade, mob_uniforms=uu[None])
+        k += used
+        if tick % 25 == 0 or tick == 200:
+            s = env.get_state()
+            assert np.max(np.abs(s["x"][0] - xy[:, 0])) < 1e-9 and np.max(np.abs(s["y"][0] - xy[:, 1])) < 1e-9, tick
+    assert k == u.size
+    assert np.array_equal(env.get_state()["ue_cell"][0], g["ue0"])
+    # constructor channel pass, then reset + steps with the recorded fading / uniforms
+    env.ctor_pass(fading=g["f_ctor"][None])
+    obs = env.reset(fading=g["f_reset"][None], mob_uniforms=np.concatenate([g["u_reset"], np.zeros(12)])[None])
+    assert np.array_equal(_np(env.serving[0]), g["reset_cur"])
+    assert state_checksum(_np(obs[0]).astype(np.float64)) == float(g["reset_state_chk"])
+    off = 0
+    for t in range(len(g["actions"])):
+        nn = int(g["u_len"][t])
+        uu = np.concatenate([g["u_steps"][off:off + nn], np.zeros(12)])[None]
+        off += nn
+        obs, r, d, info = env.step(np.array([g["actions"][t]]), fading=g["f_steps"][t][None], mob_uniforms=uu)
+        assert np.array_equal(_np(info["ue_xy"][0]), g["ue"][t]), t
+        assert np.array_equal(_np(info["bs_xy"][0]), g["bs_xy"][t]), t
+        assert np.array_equal(_np(info["serving"][0]), g["cur"][t]), t
+        assert int(info["n_out"][0]) == g["n_out"][t] and int(info["n_ho"][0]) == g["n_ho"][t], t
+        assert np.max(np.abs(_np(info["serving_sinr"][0]) - g["cur_sinr"][t])) < F64_SINR_TOL_DB, t
+        assert abs(float(r[0]) - g["reward"][t]) <= 1e-9 * max(1.0, abs(g["reward"][t])), t
+        assert state_checksum(_np(obs[0]).astype(np.float64)) == float(g["state_chk"][t]), t
+    assert env.check() == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _oracle_envs(orc, E, seed, env_offset=0, **cfg_over):
+    return [orc.OracleEnv(orc.default_cfg(**cfg_over), seed=seed, env_id=env_offset + e) for e in range(E)]
+
+
+@pytest.mark.parametrize("E,steps", [(6, 260)])
+def test_philox_fp64_matches_oracle(pkg, orc, E, steps):
+    """Synthetic mode (Philox mobility + fading), float64 kernels vs the oracle with the same counters: every
+    integer output exact, SINR 1e-9 dB, reward 1e-9; covers the 200/100/10 aggregation phase flips and reset."""
+    seed = 77
+    env = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", precision="fp64", seed=seed, diagnostics=True)
+    oenvs = _oracle_envs(orc, E, seed)
+    st = env.get_state()
+    for e in range(E):
+        assert np.array_equal(st["ue_cell"][e], oenvs[e].ue_xy), e           # constructor positions (201 ticks)
+        assert np.array_equal(st["ho_word"][e] & 31, oenvs[e].current_BS), e  # constructor association
+    obs = env.reset()
+    for e in range(E):
+        assert np.array_equal(_np(obs[e]).astype(np.float64), oenvs[e].reset())
+    rs = np.random.RandomState(5)
+    for t in range(steps):
+        act = rs.randint(0, 625, size=E)
+        if t == 130:                                                          # reset half of the envs mid-run
+            mask = (np.arange(E) % 2).astype(np.uint8)
+            obs = env.reset(env_mask=mask)
+            for e in range(E):
+                if mask[e]:
+                    assert np.array_equal(_np(obs[e]).astype(np.float64), oenvs[e].reset())
+        obs, r, d, info = env.step(act)
+        for e in range(E):
+            s, orw, od, oi = oenvs[e].step(int(act[e]))
+            assert np.array_equal(_np(info["ue_xy"][e]), oenvs[e].ue_xy), (t, e)
+            assert np.array_equal(_np(info["bs_xy"][e]), oenvs[e].bs_xy), (t, e)
+            assert np.array_equal(_np(info["serving"][e]), oenvs[e].current_BS), (t, e)
+            assert int(info["n_out"][e]) == oi["n_out"] and int(info["n_ho"][e]) == oi["n_ho"], (t, e)
+            assert int(info["n_blocked"][e]) == oi["n_blocked"], (t, e)
+            assert int(info["step_n"][e]) == oi["step_n"] and bool(d[e]) == od
+            assert np.max(np.abs(_np(env.sinr_all[e]) - oenvs[e].last_sinr)) < F64_SINR_TOL_DB, (t, e)
+            assert abs(float(r[e]) - orw) <= 1e-9 * max(1.0, abs(orw)), (t, e)
+            assert np.array_equal(_np(obs[e]).astype(np.float64), s), (t, e)
+    assert env.check() == 0
+
+
+def _chan_replay(orc, cfg, sinr_steps, sinr_reset):
+    """Drive the oracle's LTEChannel state machine (channel.py:113-116,138-176) with a given SINR history."""
+    L = orc.lib()
+    n_ue, n_bs = sinr_reset.shape
+    ch = L.orc_chan_create(n_ue, n_bs)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))  # noqa: E731
+    out = []
+    try:
+        s = np.ascontiguousarray(sinr_reset, dtype=np.float64)
+        L.orc_chan_reset(C.byref(cfg), ch, dp(s))
+        cur = np.ctypeslib.as_array(ch.contents.cur, shape=(n_ue,))
+        cs = np.ctypeslib.as_array(ch.contents.cur_sinr, shape=(n_ue,))
+        for s in sinr_steps:
+            s = np.ascontiguousarray(s, dtype=np.float64)
+            ms, no, nh = C.c_double(), C.c_int32(), C.c_int32()
+            L.orc_chan_update(C.byref(cfg), ch, dp(s), C.byref(ms), C.byref(no), C.byref(nh))
+            out.append((cur.copy(), cs.copy(), ms.value, no.value, nh.value))
+    finally:
+        L.orc_chan_destroy(ch)
+    return out
+
+
+@pytest.mark.parametrize("E,steps", [(8, 200)])
+def test_philox_fp32_matches_oracle(pkg, orc, E, steps):
+    """fp32 kernels vs the oracle in synthetic mode.  UE / BS cells are exact (mobility is float64 and does not
+    depend on SINR decisions).  The SINR matrix of every pass is within 1e-3 dB of the oracle's float64 SINR for
+    the same cells and the same Philox fading, the fading itself within 1e-4 dB, and the handover / outage state
+    machine run on the GPU's own SINR values reproduces the GPU's serving cells and counts exactly."""
+    seed = 4242
+    env = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", precision="fp32", seed=seed, diagnostics=True)
+    oenvs = _oracle_envs(orc, E, seed)
+    cfg = orc.default_cfg()
+    env.reset()
+    for o in oenvs:
+        o.reset()
+    sinr_reset = _np(env.sinr_all).astype(np.float64)
+    hist, gpu = [], []
+    rs = np.random.RandomState(9)
+    worst_sinr = worst_fade = worst_rew = 0.0
+    for t in range(steps):
+        act = rs.randint(0, 625, size=E)
+        obs, r, d, info = env.step(act)
+        sa = _np(env.sinr_all).astype(np.float64)
+        hist.append(sa)
+        gpu.append((_np(info["serving"]).copy(), _np(info["serving_sinr"]).astype(np.float64), _np(info["mean_sinr"]).copy(),
+                    _np(info["n_out"]).copy(), _np(info["n_ho"]).copy(), _np(r).copy()))
+        fu = _np(env.fading_used).astype(np.float64)
+        for e in range(E):
+            oenvs[e].step(int(act[e]))
+            assert np.array_equal(_np(info["ue_xy"][e]), oenvs[e].ue_xy), (t, e)
+            assert np.array_equal(_np(info["bs_xy"][e]), oenvs[e].bs_xy), (t, e)
+            worst_sinr = max(worst_sinr, float(np.max(np.abs(sa[e] - oenvs[e].last_sinr))))
+            # oracle epoch of this pass: ctor 0, reset 1, step t -> 2 + t
+            of = np.empty((40, 4))
+            orc.lib().orc_philox_fading(C.byref(cfg), seed, e, 2 + t, of.ctypes.data_as(C.POINTER(C.c_double)))
+            worst_fade = max(worst_fade, float(np.max(np.abs(fu[e] - of))))
+    assert worst_fade < 1e-4, worst_fade
+    assert worst_sinr < SINR_TOL_DB, worst_sinr
+    for e in range(E):
+        rep = _chan_replay(orc, cfg, [h[e] for h in hist], sinr_reset[e])
+        for t, (cur, cs, ms, no, nh) in enumerate(rep):
+            srv, ssinr, mean, n_out, n_ho, rew = gpu[t]
+            assert np.array_equal(srv[e], cur), (t, e)
+            assert np.array_equal(ssinr[e], cs), (t, e)
+            assert n_out[e] == no and n_ho[e] == nh, (t, e)
+            assert abs(mean[e] - ms) < 1e-9
+            want = max(ms / 20 - no / 40.0, -1.0)
+            worst_rew = max(worst_rew, abs(rew[e] - want) / max(abs(want), 1e-12))
+    assert worst_rew < 1e-9, worst_rew
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_dense_channel_matches_reference_fixture(pkg, golden_dir):
+    """Config-4 sizes (32 BS x 2048 UE): the reference's LTEChannel / BS_move driven directly (fixture), UE
+    cells from a per-step trace, per-BS digit actions, injected fading; float64 kernels."""
+    g = _load(golden_dir, "ref_dense_channel.npz")
+    n_steps, n_ue = g["cur"].shape
+    n_bs = g["init_bs"].shape[0]
+    fade = np.random.RandomState(int(g["seed"]) + 1).normal(0, 2, size=(n_steps + 1, n_ue, n_bs))
+    # trace row 0 feeds the ctor pass; the fixture moved the UEs to ue[t+1] before update t, while step_test
+    # reads trace[step_n] (mobile_env.py:203) and step_n is 0 at the first step: start the replay at step_n = 1
+    env = pkg.BatchedMobiEnvironment(1, n_bs, n_ue, 100, "read_trace", trace=g["ue"], fading="injected",
+                                     precision="fp64", init_bs_xy=g["init_bs"][:, :2])
+    env.ctor_pass(fading=fade[0][None])
+    assert np.array_equal(_np(env.serving[0]), g["ctor_cur"])
+    assert np.max(np.abs(_np(env.serving_sinr[0]) - g["ctor_sinr"])) < F64_SINR_TOL_DB
+    st = env.get_state()
+    st["counters"][0, 2] = 1
+    env.set_state(st)
+    for t in range(n_steps):
+        obs, r, d, info = env.step(g["digits"][t].astype(np.uint8)[None], fading=fade[t + 1][None])
+        assert np.array_equal(_np(info["bs_xy"][0]), g["bs_xy"][t][:, :2]), t
+        assert np.array_equal(_np(info["serving"][0]), g["cur"][t]), t
+        assert int(info["n_out"][0]) == g["n_out"][t], t
+        assert np.max(np.abs(_np(info["serving_sinr"][0]) - g["cur_sinr"][t])) < F64_SINR_TOL_DB, t
+        assert abs(float(info["mean_sinr"][0]) - g["mean_sinr"][t]) < F64_SINR_TOL_DB, t
+        o = _np(obs[0]).astype(np.float64)
+        assert o[0].sum() == n_bs and o[1:].sum() == n_ue
+        amap = o[1:]
+        assert float(np.sum(amap * (1 + (np.arange(amap.size).reshape(amap.shape) % 8191)))) == float(g["amap_chk"][t]), t
+    assert env.check() == 0
