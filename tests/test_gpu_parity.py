@@ -36,6 +36,13 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+def _pad(u, n=52):
+    """one tick's uniforms padded to the fixed [nUE + 3*nG] injection row"""
+    out = np.zeros(n)
+    out[:min(len(u), n)] = u[:n]
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 def test_trace_replay_matches_reference_fixture(pkg, golden_dir):
     """BASELINE config 1: MobiEnvironment(4,40,100,"read_trace") replaying the regenerated trace for 2001
@@ -130,7 +137,7 @@ def test_group_mobility_matches_reference_fixture(pkg, orc, golden_dir):
     dummy_fade = np.zeros((1, 40, 4))
     xy = None
     for tick in range(201):
-        uu = np.concatenate([u[k:k + 52], np.zeros(52)])[:52]
+        uu = _pad(u[k:k + 52])
         xy, used = m.tick(uu)
         env.reset(fading=dummy_fade, mob_uniforms=uu[None])
         k += used
@@ -141,13 +148,13 @@ def test_group_mobility_matches_reference_fixture(pkg, orc, golden_dir):
     assert np.array_equal(env.get_state()["ue_cell"][0], g["ue0"])
     # constructor channel pass, then reset + steps with the recorded fading / uniforms
     env.ctor_pass(fading=g["f_ctor"][None])
-    obs = env.reset(fading=g["f_reset"][None], mob_uniforms=np.concatenate([g["u_reset"], np.zeros(12)])[None])
+    obs = env.reset(fading=g["f_reset"][None], mob_uniforms=_pad(g["u_reset"])[None])
     assert np.array_equal(_np(env.serving[0]), g["reset_cur"])
     assert state_checksum(_np(obs[0]).astype(np.float64)) == float(g["reset_state_chk"])
     off = 0
     for t in range(len(g["actions"])):
         nn = int(g["u_len"][t])
-        uu = np.concatenate([g["u_steps"][off:off + nn], np.zeros(12)])[None]
+        uu = _pad(g["u_steps"][off:off + nn])[None]
         off += nn
         obs, r, d, info = env.step(np.array([g["actions"][t]]), fading=g["f_steps"][t][None], mob_uniforms=uu)
         assert np.array_equal(_np(info["ue_xy"][0]), g["ue"][t]), t
