@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(PKG, "libuavenv.so")
+# UAVENV_SO selects another build of the same library (tuning variants made by build.build(defines=..., out=...))
+SO = os.environ.get("UAVENV_SO") or os.path.join(PKG, "libuavenv.so")
 
 MAX_BS = 32
 MAX_GROUPS = 32
@@ -55,7 +56,7 @@ SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
-    "uavenv_launch_count", "uavenv_version",
+    "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill",
 ]
 
 _lib = None
@@ -92,5 +93,6 @@ def lib():
     L.uavenv_launch_count.argtypes = [vp]
     L.uavenv_launch_count.restype = C.c_int64
     L.uavenv_version.restype = C.c_char_p
+    L.uavenv_diag_fill.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp]
     _lib = L
     return L

@@ -39,17 +39,20 @@ def up_to_date() -> bool:
     return all(os.path.getmtime(d) <= t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and up_to_date():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = SO) -> str:
+    """defines / out: tuning variants (e.g. defines=["UAVENV_NT_SMALL=256"], out=".../variants/x.so") selected at run
+    time with the UAVENV_SO environment variable; the default build takes neither."""
+    if not force and out == SO and up_to_date():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + \
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return SO
+    return out
 
 
 if __name__ == "__main__":

@@ -8,7 +8,7 @@
 //   mobile_env.py:150-194 / 196-233  step / step_test          -> env_kernel<.., MODE_STEP>
 //   mobile_env.py:115-148            reset                     -> MODE_RESET
 //   mobile_env.py:100 + channel.py:92-93,110  LTEChannel ctor  -> MODE_CTOR
-//   ue_mobility.py:409-523           reference_point_group     -> mob_tick
+//   ue_mobility.py:409-523           reference_point_group     -> mob_group_load / mob_ue_move / mob_group_finish
 //   ue_mobility.py:191-271,310-336   BS_move, Decimal_to_Base_N-> decode_action / bs_move_warp
 //   channel.py:220-269               gain / SINR               -> ue_channel_pass
 //   channel.py:138-176,216           UpdateDroneNet            -> ue_channel_pass (handover word)
@@ -113,110 +113,113 @@ __device__ __forceinline__ double U_(double lo, double hi, double r) { return __
 constexpr double TWO_PI = 6.283185307179586;
 
 // ---------------------------------------------------------------------------------------------------------
-// One tick of the reference_point_group generator (ue_mobility.py:453-523) for the CTA's environment.
-// All threads of the CTA must call it.  `agg`/`deagg` are CTA-uniform register copies of the two counters.
+// One tick of the reference_point_group generator (ue_mobility.py:453-523), split in three so that the step
+// kernel can fuse the per-UE part with the channel pass of the same thread:
+//   mob_group_load   (nG lanes of one warp)  group centres advance, state -> shared memory      :458-459
+//   mob_ue_move      (one thread per UE)     random walk + group drift + aggregation + walls    :455-456,461-505
+//   mob_group_finish (one warp)              wall flips, flight length, arrivals, state -> HBM  :493-521
+// A CTA barrier separates each part from the next.
+__device__ __forceinline__ void mob_group_load(const DevCfg &c, EnvShared &s, int e, int g) {
+    const int nG = c.nG;
+    const double *grp = c.grp + (size_t)e * 6 * nG;
+    const double gv = grp[3 * nG + g], gc = grp[4 * nG + g], gs = grp[5 * nG + g];
+    s.gx[g] = __dadd_rn(grp[0 * nG + g], __dmul_rn(gv, gc));          // :458
+    s.gy[g] = __dadd_rn(grp[1 * nG + g], __dmul_rn(gv, gs));          // :459
+    s.gfl[g] = grp[2 * nG + g];
+    s.gv[g] = gv; s.gcos[g] = gc; s.gsin[g] = gs;
+    s.refl[0][g] = 0; s.refl[1][g] = 0; s.refl[2][g] = 0; s.refl[3][g] = 0;
+}
+
 // inj: the uniforms the reference generator would draw this tick, in its order (theta[nUE], then for the k
-// arrived groups theta[k], fl[k], v[k]); null = Philox.  Returns nothing; UE cells are written to ue_cell.
-__device__ __forceinline__ void mob_tick(const DevCfg &c, EnvShared &s, int e, uint32_t genv, int tick, int &agg,
-                                         int &deagg, const double *inj, bool write_cells) {
-    const int tid = threadIdx.x;
-    const int nG = c.nG, nUE = c.nUE;
-    double *grp = c.grp + (size_t)e * 6 * nG;
-    if (tid < nG) {
-        const double gv = grp[3 * nG + tid], gc = grp[4 * nG + tid], gs = grp[5 * nG + tid];
-        s.gx[tid] = __dadd_rn(grp[0 * nG + tid], __dmul_rn(gv, gc));   // :458
-        s.gy[tid] = __dadd_rn(grp[1 * nG + tid], __dmul_rn(gv, gs));   // :459
-        s.gfl[tid] = grp[2 * nG + tid];
-        s.gv[tid] = gv; s.gcos[tid] = gc; s.gsin[tid] = gs;
-        s.refl[0][tid] = 0; s.refl[1][tid] = 0; s.refl[2][tid] = 0; s.refl[3][tid] = 0;
+// arrived groups theta[k], fl[k], v[k]); null = Philox.  Returns the UE's integer cell.
+__device__ __forceinline__ short2 mob_ue_move(const DevCfg &c, EnvShared &s, int e, uint32_t genv, int tick,
+                                              bool aggregating, const double *inj, int u) {
+    const size_t i = (size_t)e * c.nUE + u;
+    double x = c.x[i], y = c.y[i];
+    // direction drawn at the end of the previous tick (:508-510) or at init (:437-439)
+    double tu;
+    if (inj) tu = c.th_u[i];
+    else {
+        double b_;
+        if (tick == 0) philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, 0u, DOM_INIT_TH, tu, b_);
+        else philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, (uint32_t)(tick - 1), DOM_THETA, tu, b_);
     }
-    __syncthreads();
-    const bool aggregating = agg != 0;
-    for (int u = tid; u < nUE; u += blockDim.x) {
-        const size_t i = (size_t)e * nUE + u;
-        double x = c.x[i], y = c.y[i];
-        // direction drawn at the end of the previous tick (:508-510) or at init (:437-439)
-        double tu;
-        if (inj) tu = c.th_u[i];
-        else {
-            double b_;
-            if (tick == 0) philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, 0u, DOM_INIT_TH, tu, b_);
-            else philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, (uint32_t)(tick - 1), DOM_THETA, tu, b_);
-        }
-        double sn, cs;
-        sincos(U_(0.0, TWO_PI, tu), &sn, &cs);
-        x = __dadd_rn(x, cs);                                           // :455 (velocity 1.0, :436)
-        y = __dadd_rn(y, sn);                                           // :456
-        const int g = c.ue_group[u];
-        const double gvx = __dmul_rn(s.gv[g], s.gcos[g]), gvy = __dmul_rn(s.gv[g], s.gsin[g]);
-        if (aggregating) {                                              // :461-470
-            double sc, cc;
-            sincos(atan2(s.gy[g] - y, s.gx[g] - x), &sc, &cc);
-            x = __dadd_rn(__dadd_rn(x, gvx), __dmul_rn(c.aggr, cc));
-            y = __dadd_rn(__dadd_rn(y, gvy), __dmul_rn(c.aggr, sc));
-        } else {                                                        // :475-484
-            x = __dadd_rn(x, gvx);
-            y = __dadd_rn(y, gvy);
-        }
-        // reflecting walls, reference order (:490-505); a group flips once per wall if any member reflects
-        if (x < 0.0) { x = -x; s.refl[0][g] = 1; }
-        if (x > c.max_xy) { x = __dadd_rn(__dmul_rn(2.0, c.max_xy), -x); s.refl[1][g] = 1; }
-        if (y < 0.0) { y = -y; s.refl[2][g] = 1; }
-        if (y > c.max_xy) { y = __dadd_rn(__dmul_rn(2.0, c.max_xy), -y); s.refl[3][g] = 1; }
-        c.x[i] = x;
-        c.y[i] = y;
-        if (inj) c.th_u[i] = inj[u];
-        if (write_cells) {
-            // np.concatenate(...).astype(int): truncation toward zero (mobile_env.py:154-155).  A UE exactly on
-            // the far wall would index cell G (IndexError in the reference, ue_mobility.py:186): clamp + flag.
-            int cx = (int)x, cy = (int)y;
-            if (cx >= c.G || cy >= c.G) {
-                cx = min(cx, c.G - 1); cy = min(cy, c.G - 1);
-                atomicOr(c.err_flags, ERR_CLAMP);
-            }
-            reinterpret_cast<short2 *>(c.ue_cell)[i] = make_short2((short)cx, (short)cy);
-        }
+    double sn, cs;
+    sincos(U_(0.0, TWO_PI, tu), &sn, &cs);
+    x = __dadd_rn(x, cs);                                               // :455 (velocity 1.0, :436)
+    y = __dadd_rn(y, sn);                                               // :456
+    const int g = c.ue_group[u];
+    const double gvx = __dmul_rn(s.gv[g], s.gcos[g]), gvy = __dmul_rn(s.gv[g], s.gsin[g]);
+    if (aggregating) {                                                  // :461-470
+        double sc, cc;
+        sincos(atan2(s.gy[g] - y, s.gx[g] - x), &sc, &cc);
+        x = __dadd_rn(__dadd_rn(x, gvx), __dmul_rn(c.aggr, cc));
+        y = __dadd_rn(__dadd_rn(y, gvy), __dmul_rn(c.aggr, sc));
+    } else {                                                            // :475-484
+        x = __dadd_rn(x, gvx);
+        y = __dadd_rn(y, gvy);
     }
-    // counters (:471-473, :485-487): uniform across the CTA
-    if (aggregating) { agg -= 1; if (agg == 0) deagg = c.deagg_len; }
+    // reflecting walls, reference order (:490-505); a group flips once per wall if any member reflects
+    if (x < 0.0) { x = -x; s.refl[0][g] = 1; }
+    if (x > c.max_xy) { x = __dadd_rn(__dmul_rn(2.0, c.max_xy), -x); s.refl[1][g] = 1; }
+    if (y < 0.0) { y = -y; s.refl[2][g] = 1; }
+    if (y > c.max_xy) { y = __dadd_rn(__dmul_rn(2.0, c.max_xy), -y); s.refl[3][g] = 1; }
+    c.x[i] = x;
+    c.y[i] = y;
+    if (inj) c.th_u[i] = inj[u];
+    // np.concatenate(...).astype(int): truncation toward zero (mobile_env.py:154-155).  A UE exactly on the far
+    // wall would index cell G (IndexError in the reference, ue_mobility.py:186): clamp + flag.
+    int cx = (int)x, cy = (int)y;
+    if (cx >= c.G || cy >= c.G) {
+        cx = min(cx, c.G - 1); cy = min(cy, c.G - 1);
+        atomicOr(c.err_flags, ERR_CLAMP);
+    }
+    return make_short2((short)cx, (short)cy);
+}
+
+// the phase counters (:471-473, :485-487); CTA-uniform register copies
+__device__ __forceinline__ void mob_phase_advance(const DevCfg &c, int &agg, int &deagg) {
+    if (agg != 0) { agg -= 1; if (agg == 0) deagg = c.deagg_len; }
     else { deagg -= 1; if (deagg == 0) agg = c.agg_len; }
-    __syncthreads();
-    if (tid < 32) {
-        const int g = tid;
-        const bool live = g < nG;
-        double gc = 0, gs = 0, gfl = 0, gv = 0;
-        if (live) {
-            gc = s.gcos[g]; gs = s.gsin[g];
-            if (s.refl[0][g]) gc = -gc;
-            if (s.refl[1][g]) gc = -gc;
-            if (s.refl[2][g]) gs = -gs;
-            if (s.refl[3][g]) gs = -gs;
-            gv = s.gv[g];
-            gfl = __dadd_rn(s.gfl[g], -gv);                            // :513
-        }
-        const bool arrived = live && gv > 0.0 && gfl <= 0.0;           // :514
-        const unsigned am = __ballot_sync(0xffffffffu, arrived);
-        if (arrived) {                                                  // :515-521
-            double ut, uf, uv;
-            if (inj) {
-                const int k = __popc(am), r = __popc(am & ((1u << g) - 1u));
-                ut = inj[nUE + r]; uf = inj[nUE + k + r]; uv = inj[nUE + 2 * k + r];
-            } else {
-                double b_;
-                philox_uniform2(c.k0, c.k1, genv, (uint32_t)g, (uint32_t)tick, DOM_GRP_TF, ut, uf);
-                philox_uniform2(c.k0, c.k1, genv, (uint32_t)g, (uint32_t)tick, DOM_GRP_V, uv, b_);
-            }
-            sincos(U_(0.0, TWO_PI, ut), &gs, &gc);
-            gfl = U_(0.0, c.fl_max, uf);
-            gv = U_(c.v_min, c.v_max, uv);
-        }
-        if (live) {
-            grp[0 * nG + g] = s.gx[g]; grp[1 * nG + g] = s.gy[g];
-            grp[2 * nG + g] = gfl; grp[3 * nG + g] = gv;
-            grp[4 * nG + g] = gc; grp[5 * nG + g] = gs;
-        }
+}
+
+// all 32 lanes of one warp; lane = group
+__device__ __forceinline__ void mob_group_finish(const DevCfg &c, EnvShared &s, int e, uint32_t genv, int tick,
+                                                 const double *inj, int lane) {
+    const int nG = c.nG, nUE = c.nUE, g = lane;
+    double *grp = c.grp + (size_t)e * 6 * nG;
+    const bool live = g < nG;
+    double gc = 0, gs = 0, gfl = 0, gv = 0;
+    if (live) {
+        gc = s.gcos[g]; gs = s.gsin[g];
+        if (s.refl[0][g]) gc = -gc;
+        if (s.refl[1][g]) gc = -gc;
+        if (s.refl[2][g]) gs = -gs;
+        if (s.refl[3][g]) gs = -gs;
+        gv = s.gv[g];
+        gfl = __dadd_rn(s.gfl[g], -gv);                                // :513
     }
-    __syncthreads();
+    const bool arrived = live && gv > 0.0 && gfl <= 0.0;               // :514
+    const unsigned am = __ballot_sync(0xffffffffu, arrived);
+    if (arrived) {                                                      // :515-521
+        double ut, uf, uv;
+        if (inj) {
+            const int k = __popc(am), r = __popc(am & ((1u << g) - 1u));
+            ut = inj[nUE + r]; uf = inj[nUE + k + r]; uv = inj[nUE + 2 * k + r];
+        } else {
+            double b_;
+            philox_uniform2(c.k0, c.k1, genv, (uint32_t)g, (uint32_t)tick, DOM_GRP_TF, ut, uf);
+            philox_uniform2(c.k0, c.k1, genv, (uint32_t)g, (uint32_t)tick, DOM_GRP_V, uv, b_);
+        }
+        sincos(U_(0.0, TWO_PI, ut), &gs, &gc);
+        gfl = U_(0.0, c.fl_max, uf);
+        gv = U_(c.v_min, c.v_max, uv);
+    }
+    if (live) {
+        grp[0 * nG + g] = s.gx[g]; grp[1 * nG + g] = s.gy[g];
+        grp[2 * nG + g] = gfl; grp[3 * nG + g] = gv;
+        grp[4 * nG + g] = gc; grp[5 * nG + g] = gs;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -249,7 +252,18 @@ __global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_cons
     }
     __syncthreads();
     int agg = agg0, deagg = deagg0;
-    for (int t = 0; t <= warmup; t++) mob_tick(c, s, e, genv, t, agg, deagg, nullptr, t == warmup);
+    for (int t = 0; t <= warmup; t++) {
+        if (tid < c.nG) mob_group_load(c, s, e, tid);
+        __syncthreads();
+        for (int u = tid; u < c.nUE; u += blockDim.x) {
+            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u);
+            if (t == warmup) reinterpret_cast<short2 *>(c.ue_cell)[(size_t)e * c.nUE + u] = cell;
+        }
+        mob_phase_advance(c, agg, deagg);
+        __syncthreads();
+        if (tid < 32) mob_group_finish(c, s, e, genv, t, nullptr, tid);
+        __syncthreads();
+    }
     if (tid == 0) {
         int32_t *ctr = c.ctr + (size_t)e * CTR_STRIDE;
         ctr[CTR_TICK] = warmup + 1; ctr[CTR_EPOCH] = 0; ctr[CTR_STEP] = 0;
@@ -258,7 +272,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// BS_move (ue_mobility.py:191-271) by warp 0, lane i = BS i.  Sequential over BSs; the lock test compares
+// BS_move (ue_mobility.py:191-271) by one warp, lane i = BS i.  Sequential over BSs; the lock test compares
 // BS i's PRE-move cell with the others' CURRENT cells (ue_mobility.py:256-263) and blocks the move if any
 // is within lock radius.  Returns the number of blocked BSs (all lanes).
 __device__ __forceinline__ int bs_move_warp(const DevCfg &c, int &bx, int &by, int digit, int lane) {
@@ -453,22 +467,54 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 // ---------------------------------------------------------------------------------------------------------
 // Observation, float32 [nBS+1, G, G]: plane 0 = BS counts (GetGridMap, ue_mobility.py:173-188), plane 1+b =
 // UEs served by b after handover (GetCurrentAssociationMap, channel.py:387-409), indexed [plane, x, y].
-__device__ __forceinline__ void obs_zero_fill(float *obs_env, int n_cells) {
-    if ((n_cells & 3) == 0) {
-        float4 *o4 = reinterpret_cast<float4 *>(obs_env);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int n4 = n_cells >> 2;
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(o4 + i, z);
-    } else {
-        for (int i = threadIdx.x; i < n_cells; i += blockDim.x) obs_env[i] = 0.f;
-    }
+//
+// The dense observation is >99 % zeros (<= nBS + nUE non-zero cells of (nBS+1) G^2) and is 99 % of the bytes a
+// step moves.  It is streamed out by the TMA engine: one warp issues cp.async.bulk shared->global
+// copies of a zeroed shared-memory tile (SASS: UBLKCP) right after the action has been validated, the copies
+// drain while all warps run mobility and the channel pass, and the few non-zero cells are added with
+// float atomics (RED) once the bulk group has completed.
+#ifndef UAVENV_ZERO_TILE
+#define UAVENV_ZERO_TILE 16384
+#endif
+constexpr int ZERO_TILE_BYTES = UAVENV_ZERO_TILE;
+
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// fallback for observations whose per-env size / base is not 16-byte aligned (odd G): plain streaming stores
+__device__ __forceinline__ void obs_zero_fill_lsu(float *obs_env, int n_cells) {
+    for (int i = threadIdx.x; i < n_cells; i += blockDim.x) __stcs(obs_env + i, 0.f);
 }
 
-template <int NB, bool F64>
-__global__ void __launch_bounds__(CTA_THREADS) env_kernel(const __grid_constant__ DevCfg c,
-                                                          const __grid_constant__ CallArgs a) {
+// CTA size: NT_SMALL threads when every UE of an env gets its own thread with two warps to spare, else CTA_THREADS
+#ifndef UAVENV_NT_SMALL
+#define UAVENV_NT_SMALL 128
+#endif
+#ifndef UAVENV_MINB_SMALL
+#define UAVENV_MINB_SMALL 8
+#endif
+constexpr int NT_SMALL = UAVENV_NT_SMALL;
+constexpr int min_blocks(int nb, bool f64, int nt) {
+    return (f64 || nb > 8) ? 1 : (nt == CTA_THREADS ? 4 : UAVENV_MINB_SMALL);
+}
+
+// warp roles inside the CTA of NT/32 warps (every warp also takes part in the per-UE loop):
+//   last warp: bulk stores of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
+template <int NB, bool F64, int NT>
+__global__ void __launch_bounds__(NT, min_blocks(NB, F64, NT))
+env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a) {
     using T = typename Real<F64>::T;
+    constexpr int NW = NT / 32;
+    constexpr int WARP_TMA = NW - 1, WARP_GRP = NW >= 2 ? NW - 2 : 0, WARP_BS = NW >= 3 ? NW - 3 : 0;
+    static_assert(NW >= 1 && NW <= CTA_THREADS / 32, "CTA size");
     __shared__ EnvShared s;
+    __shared__ __align__(128) float zero_tile[ZERO_TILE_BYTES / 4];
     const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = a.mode;
     if (a.env_mask && !a.env_mask[e]) return;
@@ -478,113 +524,122 @@ __global__ void __launch_bounds__(CTA_THREADS) env_kernel(const __grid_constant_
     int tick = ctr[CTR_TICK], epoch = ctr[CTR_EPOCH], step_n = ctr[CTR_STEP];
     int agg = ctr[CTR_AGG], deagg = ctr[CTR_DEAGG];
 
-    // ---- validate + decode the action (Decimal_to_Base_N, ue_mobility.py:310-336: MSB first, digit 0 <-> BS 0)
-    if (tid == 0) {
-        int ok = 1;
+    const int n_cells = (nBS + 1) * G * G;
+    float *obs_env = (a.obs && c.obs_mode != OBS_NONE) ? a.obs + (size_t)e * n_cells : nullptr;
+    const bool incremental = c.obs_mode == OBS_F32_INCREMENTAL && obs_env && mode == MODE_STEP;
+    const bool full_obs = obs_env && mode != MODE_CTOR && !incremental;
+    const bool bulk_ok = full_obs && (n_cells & 3) == 0 && (reinterpret_cast<uintptr_t>(obs_env) & 15) == 0;
+    const bool group_tick = c.mobility == MOB_GROUP && mode != MODE_CTOR;   // mobile_env.py:152-155 / :122-127
+    const double *inj = (group_tick && a.inject_mob) ? a.mob_u + (size_t)e * (nUE + 3 * c.nG) : nullptr;
+
+    // ---- phase 0 (no barrier yet): zero tile | action + BS move (one warp) | group state (one warp) ----
+    if (bulk_ok) {
+        float4 *z4 = reinterpret_cast<float4 *>(zero_tile);
+        for (int i = tid; i < ZERO_TILE_BYTES / 16; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async_smem();          // generic-proxy writes of the tile -> visible to the async proxy
+    }
+    if (warp == WARP_BS) {
+        // validate + decode the action (Decimal_to_Base_N, ue_mobility.py:310-336: MSB first, digit 0 <-> BS 0)
+        int ok = 1, digit = 4;
         if (mode == MODE_STEP) {
             if (a.digits) {
-                for (int b = 0; b < nBS; b++) {
-                    const int d = a.digits[(size_t)e * nBS + b];
-                    s.digit[b] = d;
-                    if (d >= c.n_act) ok = 0;
-                }
+                if (lane < nBS) { digit = a.digits[(size_t)e * nBS + lane]; ok = digit < c.n_act; }
             } else if (a.action) {
                 long long cur = a.action[e];
                 if (cur < 0) { ok = 0; cur = 0; }
-                for (int pos = nBS - 1; pos >= 0; pos--) { s.digit[pos] = (int)(cur % c.n_act); cur /= c.n_act; }
-                if (cur != 0) ok = 0;                                  // more digits than BSs (reference fails at :334)
+                // lane b takes digit b = (action / n_act^(nBS-1-b)) mod n_act; more digits than BSs is an error
+                // (the reference fails at ue_mobility.py:334)
+                long long rem = cur;
+                int mine = 0;
+                for (int pos = nBS - 1; pos >= 0; pos--) {
+                    const int d = (int)(rem % c.n_act);
+                    rem /= c.n_act;
+                    if (pos == lane) mine = d;
+                }
+                if (rem != 0) ok = 0;
+                if (lane < nBS) digit = mine;
             } else ok = 0;
-            if (!ok) atomicOr(c.err_flags, ERR_ACTION);
         }
+        ok = __all_sync(0xffffffffu, ok);
+        if (!ok && lane == 0) atomicOr(c.err_flags, ERR_ACTION);
         if (c.mobility == MOB_TRACE) {
             const long long row = mode == MODE_STEP ? step_n : 0;      // mobile_env.py:203 / :87,130
-            if (!c.trace || row >= c.trace_T) { ok = 0; atomicOr(c.err_flags, ERR_TRACE); }
+            if (!c.trace || row >= c.trace_T) {
+                ok = 0;
+                if (lane == 0) atomicOr(c.err_flags, ERR_TRACE);
+            }
         }
-        s.ok = ok;
-    }
-    __syncthreads();
-    if (!s.ok) return;                                                 // the env is left untouched
-
-    const bool incremental = c.obs_mode == OBS_F32_INCREMENTAL && a.obs && mode == MODE_STEP;
-    const int n_cells = (nBS + 1) * G * G;
-    float *obs_env = a.obs ? a.obs + (size_t)e * n_cells : nullptr;
-    const bool full_obs = obs_env && c.obs_mode != OBS_NONE && mode != MODE_CTOR && !incremental;
-
-    // ---- UE movement ----
-    if (c.mobility == MOB_GROUP) {
-        if (mode != MODE_CTOR) {                                       // mobile_env.py:152-155 / :122-127
-            const double *inj = a.inject_mob ? a.mob_u + (size_t)e * (nUE + 3 * c.nG) : nullptr;
-            if (incremental) {
-                // the cells of the previous step leave the association planes before ue_cell is overwritten
-                for (int u = tid; u < nUE; u += blockDim.x) {
-                    const short2 oc = reinterpret_cast<const short2 *>(c.ue_cell)[(size_t)e * nUE + u];
-                    const int ob = c.ho[(size_t)e * nUE + u] & 31;
-                    atomicAdd(obs_env + ((size_t)(1 + ob) * G + oc.x) * G + oc.y, -1.f);
+        if (ok) {
+            // BS movement (mobile_env.py:157; reset: back to the initial layout, :119)
+            int bx = 0, by = 0, blocked = 0;
+            if (lane < nBS) {
+                if (mode == MODE_RESET) { bx = c.init_bs[2 * lane]; by = c.init_bs[2 * lane + 1]; }
+                else {
+                    const short2 b2 = reinterpret_cast<const short2 *>(c.bs_xy)[(size_t)e * nBS + lane];
+                    bx = b2.x; by = b2.y;
                 }
             }
-            mob_tick(c, s, e, genv, tick, agg, deagg, inj, true);
-            tick++;
+            const int ox = bx, oy = by;
+            if (mode == MODE_STEP) blocked = bs_move_warp(c, bx, by, digit, lane);
+            if (lane < nBS) {
+                s.bsx[lane] = bx; s.bsy[lane] = by;
+                const short2 nb = make_short2((short)bx, (short)by);
+                if (mode != MODE_CTOR) reinterpret_cast<short2 *>(c.bs_xy)[(size_t)e * nBS + lane] = nb;
+                if (a.bs_xy_out) reinterpret_cast<short2 *>(a.bs_xy_out)[(size_t)e * nBS + lane] = nb;
+                if (a.bs_digits && mode == MODE_STEP) a.bs_digits[(size_t)e * nBS + lane] = (uint8_t)digit;
+                if (incremental && (ox != bx || oy != by)) {
+                    atomicAdd(obs_env + (size_t)ox * G + oy, -1.f);
+                    atomicAdd(obs_env + (size_t)bx * G + by, 1.f);
+                }
+            }
+            if (lane == 0) s.blocked = blocked;
         }
-    } else {
+        if (lane == 0) s.ok = ok;
+    }
+    if (warp == WARP_GRP && group_tick && lane < c.nG) mob_group_load(c, s, e, lane);
+    __syncthreads();                                                   // barrier 1
+    if (!s.ok) return;                                                 // the env is left untouched
+
+    // ---- the dense observation starts streaming out now ----
+    if (bulk_ok) {
+        if (warp == WARP_TMA) {
+            const uint32_t total = (uint32_t)n_cells * 4u;
+            char *dst = reinterpret_cast<char *>(obs_env);
+            for (uint32_t off = (uint32_t)lane * ZERO_TILE_BYTES; off < total; off += 32u * ZERO_TILE_BYTES)
+                bulk_store(dst + off, zero_tile, min((uint32_t)ZERO_TILE_BYTES, total - off));
+            bulk_commit();
+        }
+    } else if (full_obs) {
+        obs_zero_fill_lsu(obs_env, n_cells);
+    }
+
+    // ---- per-UE: movement + channel pass + handover word, one thread per UE ----
+    const bool aggregating = agg != 0;
+    const int32_t *tr = nullptr;
+    if (c.mobility == MOB_TRACE) {
         const long long row = mode == MODE_STEP ? step_n : 0;
-        const int32_t *tr = c.trace + ((size_t)row * (c.trace_per_env ? c.E : 1) + (c.trace_per_env ? e : 0)) * nUE * 2;
-        for (int u = tid; u < nUE; u += blockDim.x) {
-            const size_t i = (size_t)e * nUE + u;
-            if (incremental) {
-                const short2 oc = reinterpret_cast<const short2 *>(c.ue_cell)[i];
-                const int ob = c.ho[i] & 31;
-                atomicAdd(obs_env + ((size_t)(1 + ob) * G + oc.x) * G + oc.y, -1.f);
-            }
-            const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
-            reinterpret_cast<short2 *>(c.ue_cell)[i] = make_short2((short)xy.x, (short)xy.y);
-        }
+        tr = c.trace + ((size_t)row * (c.trace_per_env ? c.E : 1) + (c.trace_per_env ? e : 0)) * nUE * 2;
     }
-
-    // ---- BS movement (warp 0) ----
-    if (warp == 0) {
-        int bx = 0, by = 0, blocked = 0;
-        if (lane < nBS) {
-            if (mode == MODE_RESET) {                                  // mobile_env.py:119
-                bx = c.init_bs[2 * lane]; by = c.init_bs[2 * lane + 1];
-            } else {
-                bx = c.bs_xy[((size_t)e * nBS + lane) * 2]; by = c.bs_xy[((size_t)e * nBS + lane) * 2 + 1];
-            }
-        }
-        const int ox = bx, oy = by;
-        if (mode == MODE_STEP) blocked = bs_move_warp(c, bx, by, lane < nBS ? s.digit[lane] : 4, lane);
-        if (lane < nBS) {
-            s.bsx[lane] = bx; s.bsy[lane] = by;
-            if (mode != MODE_CTOR) {
-                c.bs_xy[((size_t)e * nBS + lane) * 2] = (int16_t)bx;
-                c.bs_xy[((size_t)e * nBS + lane) * 2 + 1] = (int16_t)by;
-            }
-            if (a.bs_xy_out) {
-                a.bs_xy_out[((size_t)e * nBS + lane) * 2] = (int16_t)bx;
-                a.bs_xy_out[((size_t)e * nBS + lane) * 2 + 1] = (int16_t)by;
-            }
-            if (a.bs_digits && mode == MODE_STEP) a.bs_digits[(size_t)e * nBS + lane] = (uint8_t)s.digit[lane];
-            if (incremental && (ox != bx || oy != by)) {
-                atomicAdd(obs_env + (size_t)ox * G + oy, -1.f);
-                atomicAdd(obs_env + (size_t)bx * G + by, 1.f);
-            }
-        }
-        if (lane == 0) s.blocked = blocked;
-    }
-    // the dense observation is streamed out while the channel pass of this CTA (and of the other resident
-    // CTAs) is in flight; non-zero cells are added after the barrier below
-    if (full_obs) obs_zero_fill(obs_env, n_cells);
-    __syncthreads();
-
-    // ---- channel pass, one thread per UE ----
     double sum_sinr = 0.0;
     int cnt_out = 0, cnt_ho = 0;
-    for (int u = tid; u < nUE; u += blockDim.x) {
+    for (int u = tid; u < nUE; u += NT) {
         const size_t i = (size_t)e * nUE + u;
-        const short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
-        uint32_t word = mode == MODE_STEP ? c.ho[i] : 0u;
+        short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
+        uint32_t word = c.ho[i];
+        if (incremental) {
+            // the cell of the previous step leaves its association plane
+            atomicAdd(obs_env + ((size_t)(1 + (word & 31)) * G + cell.x) * G + cell.y, -1.f);
+        }
+        if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u);
+        else if (tr) {
+            const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
+            cell = make_short2((short)xy.x, (short)xy.y);
+        }
+        if (mode != MODE_STEP) word = 0u;
         int new_out, did_ho;
         const T curS = ue_channel_pass<NB, F64>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
                                                 new_out, did_ho);
+        if (mode != MODE_CTOR || c.mobility == MOB_TRACE) reinterpret_cast<short2 *>(c.ue_cell)[i] = cell;
         c.ho[i] = word;
         sum_sinr += (double)curS;
         cnt_out += new_out;
@@ -593,9 +648,9 @@ __global__ void __launch_bounds__(CTA_THREADS) env_kernel(const __grid_constant_
         if (a.serving) a.serving[i] = (uint8_t)srv;
         if (a.serving_sinr) reinterpret_cast<T *>(a.serving_sinr)[i] = curS;
         if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
-        if (full_obs || incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+        if (incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
     }
-    if (full_obs && tid < nBS) atomicAdd(obs_env + (size_t)s.bsx[tid] * G + s.bsy[tid], 1.f);
+    if (group_tick) { mob_phase_advance(c, agg, deagg); tick++; }
 
     // ---- per-env reductions in a fixed order (warp tree, then warps in index order) ----
 #pragma unroll
@@ -605,11 +660,24 @@ __global__ void __launch_bounds__(CTA_THREADS) env_kernel(const __grid_constant_
         cnt_ho += __shfl_down_sync(0xffffffffu, cnt_ho, o);
     }
     if (lane == 0) { s.red_sinr[warp] = sum_sinr; s.red_out[warp] = cnt_out; s.red_ho[warp] = cnt_ho; }
-    __syncthreads();
+    if (bulk_ok && warp == WARP_TMA) bulk_wait_all();                  // the zeros have landed
+    __syncthreads();                                                   // barrier 2
+
+    if (warp == WARP_GRP && group_tick) mob_group_finish(c, s, e, genv, tick - 1, inj, lane);
+    if (full_obs) {
+        // non-zero cells: UEs on the plane of their (post-handover) serving BS, BSs on plane 0
+        for (int u = tid; u < nUE; u += NT) {
+            const size_t i = (size_t)e * nUE + u;
+            const short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
+            const int srv = c.ho[i] & 31;
+            atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+        }
+        if (tid < nBS) atomicAdd(obs_env + (size_t)s.bsx[tid] * G + s.bsy[tid], 1.f);
+    }
     if (tid == 0) {
         double tot = 0.0;
         int no = 0, nh = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { tot += s.red_sinr[w]; no += s.red_out[w]; nh += s.red_ho[w]; }
+        for (int w = 0; w < NW; w++) { tot += s.red_sinr[w]; no += s.red_out[w]; nh += s.red_ho[w]; }
         const double mean = tot / (double)nUE;                         // channel.py:216
         if (mode == MODE_STEP) {
             step_n += 1;                                               // mobile_env.py:179
@@ -627,6 +695,35 @@ __global__ void __launch_bounds__(CTA_THREADS) env_kernel(const __grid_constant_
         if (a.step_n) a.step_n[e] = step_n;
         ctr[CTR_TICK] = tick; ctr[CTR_EPOCH] = epoch + 1; ctr[CTR_STEP] = step_n;
         ctr[CTR_AGG] = agg; ctr[CTR_DEAGG] = deagg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Diagnostic: a pure zero-fill of `bytes` bytes with the two store mechanisms the step kernel can use, so the
+// write-only HBM ceiling of the box can be measured next to the step kernel (bench.py --write-ceiling).
+//   mode 0: st.global.cs.v4 from all threads;  mode 1: cp.async.bulk shared->global of a zero tile (UBLKCP)
+__global__ void __launch_bounds__(CTA_THREADS) fill_kernel(char *dst, unsigned long long bytes, unsigned long long per_cta,
+                                                           int mode) {
+    __shared__ __align__(128) float zero_tile[ZERO_TILE_BYTES / 4];
+    const unsigned long long lo = (unsigned long long)blockIdx.x * per_cta;
+    if (lo >= bytes) return;
+    const unsigned long long n = min(per_cta, bytes - lo);
+    if (mode == 0) {
+        float4 *d4 = reinterpret_cast<float4 *>(dst + lo);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (unsigned long long i = threadIdx.x; i < n / 16; i += CTA_THREADS) __stcs(d4 + i, z);
+    } else {
+        float4 *z4 = reinterpret_cast<float4 *>(zero_tile);
+        for (int i = threadIdx.x; i < ZERO_TILE_BYTES / 16; i += CTA_THREADS) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            for (unsigned long long off = (unsigned long long)threadIdx.x * ZERO_TILE_BYTES; off < n;
+                 off += 32ull * ZERO_TILE_BYTES)
+                bulk_store(dst + lo + off, zero_tile, (uint32_t)min((unsigned long long)ZERO_TILE_BYTES, n - off));
+            bulk_commit();
+            bulk_wait_all();
+        }
     }
 }
 

@@ -61,15 +61,23 @@ int use_device(uavenv_t *h) {
     return UAVENV_OK;
 }
 
+template <bool F64, int NT>
+cudaError_t launch_env_nt(const uavenv_t *h, const CallArgs &a, cudaStream_t st) {
+    const int nBS = h->d.nBS;
+    const dim3 grid(h->d.E), block(NT);
+    if (nBS <= 4) env_kernel<4, F64, NT><<<grid, block, 0, st>>>(h->d, a);
+    else if (nBS <= 8) env_kernel<8, F64, NT><<<grid, block, 0, st>>>(h->d, a);
+    else if (nBS <= 16) env_kernel<16, F64, NT><<<grid, block, 0, st>>>(h->d, a);
+    else env_kernel<32, F64, NT><<<grid, block, 0, st>>>(h->d, a);
+    return cudaGetLastError();
+}
+
+/* small environments (every UE its own thread, two warps to spare for the BS / group / TMA roles) run in
+ * NT_SMALL-thread CTAs so that more of them are resident per SM; larger ones in CTA_THREADS-thread CTAs */
 template <bool F64>
 cudaError_t launch_env(const uavenv_t *h, const CallArgs &a, cudaStream_t st) {
-    const int nBS = h->d.nBS;
-    const dim3 grid(h->d.E), block(CTA_THREADS);
-    if (nBS <= 4) env_kernel<4, F64><<<grid, block, 0, st>>>(h->d, a);
-    else if (nBS <= 8) env_kernel<8, F64><<<grid, block, 0, st>>>(h->d, a);
-    else if (nBS <= 16) env_kernel<16, F64><<<grid, block, 0, st>>>(h->d, a);
-    else env_kernel<32, F64><<<grid, block, 0, st>>>(h->d, a);
-    return cudaGetLastError();
+    if (NT_SMALL < CTA_THREADS && h->d.nUE <= NT_SMALL - 64) return launch_env_nt<F64, NT_SMALL>(h, a, st);
+    return launch_env_nt<F64, CTA_THREADS>(h, a, st);
 }
 
 int run_env(uavenv_t *h, int mode, const uavenv_in *in, const uavenv_out *out, void *stream) {
@@ -407,6 +415,17 @@ int uavenv_check(uavenv_t *h, uint32_t *flags_out, void *stream) {
     if (f & 1u) return fail(h, UAVENV_EACTION, "an action was outside [0, n_act^n_bs) (or a digit >= n_act); those envs were not stepped%s");
     if (f & 2u) return fail(h, UAVENV_ETRACE, "trace exhausted (step_n past the end of the trace); those envs were not stepped%s");
     return UAVENV_OK;
+}
+
+int uavenv_diag_fill(void *dst_dev, int64_t bytes, int64_t bytes_per_cta, int32_t mode, void *stream) {
+    if (!dst_dev || bytes < 16 || (bytes & 15) || bytes_per_cta < 16 || (bytes_per_cta & 15) || (mode != 0 && mode != 1) ||
+        ((uintptr_t)dst_dev & 15))
+        return UAVENV_EINVAL;
+    const int64_t grid = (bytes + bytes_per_cta - 1) / bytes_per_cta;
+    if (grid > 0x7fffffffLL) return UAVENV_EINVAL;
+    fill_kernel<<<(unsigned)grid, CTA_THREADS, 0, (cudaStream_t)stream>>>((char *)dst_dev, (unsigned long long)bytes,
+                                                                          (unsigned long long)bytes_per_cta, mode);
+    return cudaGetLastError() == cudaSuccess ? UAVENV_OK : UAVENV_ECUDA;
 }
 
 const uavenv_cfg *uavenv_get_cfg(const uavenv_t *h) { return h ? &h->cfg : nullptr; }

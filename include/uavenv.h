@@ -147,6 +147,12 @@ int uavenv_set_state(uavenv_t *h, const void *host_buf, int64_t bytes);
  * bit2 UE cell clamped from G to G-1).  Synchronises the stream. */
 int uavenv_check(uavenv_t *h, uint32_t *flags_out, void *stream);
 
+/* Diagnostic (no reference counterpart): zero-fill `bytes` bytes (multiple of 16, 16-byte aligned device pointer) with
+ * the store mechanism of the step kernel's observation stream -- mode 0: st.global.v4, mode 1: cp.async.bulk from a
+ * zeroed shared-memory tile -- one CTA per bytes_per_cta.  bench.py uses it to measure the box's write-only HBM
+ * ceiling beside the step kernel. */
+int uavenv_diag_fill(void *dst_dev, int64_t bytes, int64_t bytes_per_cta, int32_t mode, void *stream);
+
 const uavenv_cfg *uavenv_get_cfg(const uavenv_t *h);
 const char *uavenv_last_error(const uavenv_t *h);
 /* kernels launched by this handle so far (bench.py's gpu_launches) */
