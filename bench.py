@@ -272,8 +272,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_env,
-                         "kernel": "uavk::env_kernel<4,false>", "launch_us": per_launch_s * 1e6},
+                         "kernel": "uavk::env_kernel<4,false,256>", "launch_us": per_launch_s * 1e6},
             "clocks": clocks,
+            "launch_plan": env.launch_plan,
             "device_error_flags": flags,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -56,7 +56,7 @@ SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
-    "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill",
+    "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
 ]
 
 _lib = None
@@ -93,6 +93,9 @@ def lib():
     L.uavenv_launch_count.argtypes = [vp]
     L.uavenv_launch_count.restype = C.c_int64
     L.uavenv_version.restype = C.c_char_p
+    L.uavenv_launch_plan.argtypes = [vp, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32)]
+    L.uavenv_diag_fill_ring.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.uavenv_diag_fill_env.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.uavenv_diag_fill.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp]
     _lib = L
     return L

@@ -95,6 +95,7 @@ struct CallArgs {
     float *fading_used;          // [E,nUE,nBS]
     int16_t *ue_xy, *bs_xy_out;  // [E,nUE,2], [E,nBS,2]
     uint8_t *bs_digits;          // [E,nBS]
+    int tile_bytes;              // bytes of the zeroed shared-memory tile the TMA warp streams from (0: no TMA path)
 };
 
 struct EnvShared {
@@ -119,26 +120,35 @@ constexpr double TWO_PI = 6.283185307179586;
 //   mob_ue_move      (one thread per UE)     random walk + group drift + aggregation + walls    :455-456,461-505
 //   mob_group_finish (one warp)              wall flips, flight length, arrivals, state -> HBM  :493-521
 // A CTA barrier separates each part from the next.
-__device__ __forceinline__ void mob_group_load(const DevCfg &c, EnvShared &s, int e, int g) {
+struct GroupRow { double gx, gy, gfl, gv, gcos, gsin; };     // one group's state as stored (c.grp[e, :, g])
+
+__device__ __forceinline__ GroupRow group_row_load(const DevCfg &c, int e, int g) {
     const int nG = c.nG;
     const double *grp = c.grp + (size_t)e * 6 * nG;
-    const double gv = grp[3 * nG + g], gc = grp[4 * nG + g], gs = grp[5 * nG + g];
-    s.gx[g] = __dadd_rn(grp[0 * nG + g], __dmul_rn(gv, gc));          // :458
-    s.gy[g] = __dadd_rn(grp[1 * nG + g], __dmul_rn(gv, gs));          // :459
-    s.gfl[g] = grp[2 * nG + g];
-    s.gv[g] = gv; s.gcos[g] = gc; s.gsin[g] = gs;
+    GroupRow r;
+    r.gx = grp[0 * nG + g]; r.gy = grp[1 * nG + g]; r.gfl = grp[2 * nG + g];
+    r.gv = grp[3 * nG + g]; r.gcos = grp[4 * nG + g]; r.gsin = grp[5 * nG + g];
+    return r;
+}
+
+__device__ __forceinline__ void mob_group_load(EnvShared &s, const GroupRow &r, int g) {
+    s.gx[g] = __dadd_rn(r.gx, __dmul_rn(r.gv, r.gcos));               // :458
+    s.gy[g] = __dadd_rn(r.gy, __dmul_rn(r.gv, r.gsin));               // :459
+    s.gfl[g] = r.gfl;
+    s.gv[g] = r.gv; s.gcos[g] = r.gcos; s.gsin[g] = r.gsin;
     s.refl[0][g] = 0; s.refl[1][g] = 0; s.refl[2][g] = 0; s.refl[3][g] = 0;
 }
 
 // inj: the uniforms the reference generator would draw this tick, in its order (theta[nUE], then for the k
 // arrived groups theta[k], fl[k], v[k]); null = Philox.  Returns the UE's integer cell.
+// x, y (and thu, the injected direction uniform) are the UE's stored state, loaded by the caller.
 __device__ __forceinline__ short2 mob_ue_move(const DevCfg &c, EnvShared &s, int e, uint32_t genv, int tick,
-                                              bool aggregating, const double *inj, int u) {
+                                              bool aggregating, const double *inj, int u, double x, double y,
+                                              double thu) {
     const size_t i = (size_t)e * c.nUE + u;
-    double x = c.x[i], y = c.y[i];
     // direction drawn at the end of the previous tick (:508-510) or at init (:437-439)
     double tu;
-    if (inj) tu = c.th_u[i];
+    if (inj) tu = thu;
     else {
         double b_;
         if (tick == 0) philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, 0u, DOM_INIT_TH, tu, b_);
@@ -253,10 +263,11 @@ __global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_cons
     __syncthreads();
     int agg = agg0, deagg = deagg0;
     for (int t = 0; t <= warmup; t++) {
-        if (tid < c.nG) mob_group_load(c, s, e, tid);
+        if (tid < c.nG) mob_group_load(s, group_row_load(c, e, tid), tid);
         __syncthreads();
         for (int u = tid; u < c.nUE; u += blockDim.x) {
-            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u);
+            const size_t i = (size_t)e * c.nUE + u;
+            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u, c.x[i], c.y[i], 0.0);
             if (t == warmup) reinterpret_cast<short2 *>(c.ue_cell)[(size_t)e * c.nUE + u] = cell;
         }
         mob_phase_advance(c, agg, deagg);
@@ -469,52 +480,67 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 // UEs served by b after handover (GetCurrentAssociationMap, channel.py:387-409), indexed [plane, x, y].
 //
 // The dense observation is >99 % zeros (<= nBS + nUE non-zero cells of (nBS+1) G^2) and is 99 % of the bytes a
-// step moves.  It is streamed out by the TMA engine: one warp issues cp.async.bulk shared->global
-// copies of a zeroed shared-memory tile (SASS: UBLKCP) right after the action has been validated, the copies
-// drain while all warps run mobility and the channel pass, and the few non-zero cells are added with
-// float atomics (RED) once the bulk group has completed.
-#ifndef UAVENV_ZERO_TILE
-#define UAVENV_ZERO_TILE 16384
+// step moves.  The zeros are streamed by the TMA engine: right after the action has been validated one
+// warp issues cp.async.bulk shared->global copies (SASS: UBLKCP) of ONE constant zeroed shared-memory tile, the
+// copies drain while all warps run mobility and the channel pass, and once the bulk group has completed the env's
+// few counts are added with float REDs that hit the still L2-resident lines.  Tile size and CTAs per SM follow the
+// measurements in profiles/r1/NOTES.md: large copies (64 KB) amortise the TMA's per-copy cost, and few resident
+// CTAs keep the in-flight observations inside L2.
+#ifndef UAVENV_TILE_BYTES
+#define UAVENV_TILE_BYTES 73728
 #endif
-constexpr int ZERO_TILE_BYTES = UAVENV_ZERO_TILE;
+constexpr int TILE_BYTES = UAVENV_TILE_BYTES;      // largest bulk copy / zero tile (the launch plan may shrink it)
+constexpr int ZERO_TILE_BYTES = 16384;             // fill_kernel (diagnostic)
+static_assert((TILE_BYTES % 128) == 0, "tile");
 
 __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(__cvta_generic_to_global(gdst)),
                  "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes)
                  : "memory");
 }
+// same copy with an L2 eviction-priority hint (createpolicy): the observation is a write-once stream
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_store_hint(void *gdst, const void *ssrc, uint32_t bytes, uint64_t policy) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(__cvta_generic_to_global(gdst)),
+                 "r"((uint32_t)__cvta_generic_to_shared(ssrc)), "r"(bytes), "l"(policy)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// all but the most recent bulk group of this thread have completed (their writes are visible)
+__device__ __forceinline__ void bulk_wait_prev() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+// the source tiles of all bulk copies this thread committed have been read (they may be rewritten)
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 // fallback for observations whose per-env size / base is not 16-byte aligned (odd G): plain streaming stores
 __device__ __forceinline__ void obs_zero_fill_lsu(float *obs_env, int n_cells) {
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) __stcs(obs_env + i, 0.f);
 }
 
-// CTA size: NT_SMALL threads when every UE of an env gets its own thread with two warps to spare, else CTA_THREADS
-#ifndef UAVENV_NT_SMALL
-#define UAVENV_NT_SMALL 128
+// CTAs per SM the fp32 kernels are compiled for (register budget); the launch plan (uavenv.cu: plan_kernel) keeps
+// (resident CTAs) x (bytes of one env's observation) well inside the 126 MB L2 so that the REDs hit.
+#ifndef UAVENV_MINB
+#define UAVENV_MINB 3
 #endif
-#ifndef UAVENV_MINB_SMALL
-#define UAVENV_MINB_SMALL 8
-#endif
-constexpr int NT_SMALL = UAVENV_NT_SMALL;
-constexpr int min_blocks(int nb, bool f64, int nt) {
-    return (f64 || nb > 8) ? 1 : (nt == CTA_THREADS ? 4 : UAVENV_MINB_SMALL);
-}
+constexpr int min_blocks(int nb, bool f64) { return (f64 || nb > 8) ? 1 : UAVENV_MINB; }
 
-// warp roles inside the CTA of NT/32 warps (every warp also takes part in the per-UE loop):
-//   last warp: bulk stores of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
+// One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
+//   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
 template <int NB, bool F64, int NT>
-__global__ void __launch_bounds__(NT, min_blocks(NB, F64, NT))
+__global__ void __launch_bounds__(NT, min_blocks(NB, F64))
 env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a) {
     using T = typename Real<F64>::T;
     constexpr int NW = NT / 32;
     constexpr int WARP_TMA = NW - 1, WARP_GRP = NW >= 2 ? NW - 2 : 0, WARP_BS = NW >= 3 ? NW - 3 : 0;
     static_assert(NW >= 1 && NW <= CTA_THREADS / 32, "CTA size");
     __shared__ EnvShared s;
-    __shared__ __align__(128) float zero_tile[ZERO_TILE_BYTES / 4];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    float *zero_tile = reinterpret_cast<float *>(dyn_smem);
+    const uint32_t tile_bytes = (uint32_t)a.tile_bytes;   // 0: no TMA path for this launch
     const int e = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = a.mode;
     if (a.env_mask && !a.env_mask[e]) return;
@@ -528,15 +554,30 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     float *obs_env = (a.obs && c.obs_mode != OBS_NONE) ? a.obs + (size_t)e * n_cells : nullptr;
     const bool incremental = c.obs_mode == OBS_F32_INCREMENTAL && obs_env && mode == MODE_STEP;
     const bool full_obs = obs_env && mode != MODE_CTOR && !incremental;
-    const bool bulk_ok = full_obs && (n_cells & 3) == 0 && (reinterpret_cast<uintptr_t>(obs_env) & 15) == 0;
+    const bool bulk_ok = full_obs && tile_bytes != 0;     // host: whole float4s, aligned buffer, tile fits
     const bool group_tick = c.mobility == MOB_GROUP && mode != MODE_CTOR;   // mobile_env.py:152-155 / :122-127
     const double *inj = (group_tick && a.inject_mob) ? a.mob_u + (size_t)e * (nUE + 3 * c.nG) : nullptr;
 
-    // ---- phase 0 (no barrier yet): zero tile | action + BS move (one warp) | group state (one warp) ----
-    if (bulk_ok) {
+    // ---- phase 0 (no barrier yet): zero stream (one warp) | action + BS move (one warp) | group state (one warp) ----
+    if (bulk_ok && warp == WARP_TMA) {
+        // The observation's zeros start streaming before anything has been read from HBM: the warp zeroes the tile,
+        // publishes it to the async proxy and issues the env's bulk copies.  (An env whose action turns out to be
+        // invalid keeps its state but its observation is zeroed.)
         float4 *z4 = reinterpret_cast<float4 *>(zero_tile);
-        for (int i = tid; i < ZERO_TILE_BYTES / 16; i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = lane; i < (int)(tile_bytes / 16); i += 32) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async_smem();          // generic-proxy writes of the tile -> visible to the async proxy
+        __syncwarp();
+        const uint32_t total = (uint32_t)n_cells * 4u;
+        char *dst = reinterpret_cast<char *>(obs_env);
+#ifndef UAVENV_NO_L2_HINT
+        const uint64_t pol = l2_policy_evict_first();      // write-once stream: first in line for eviction
+        for (uint32_t off = (uint32_t)lane * tile_bytes; off < total; off += 32u * tile_bytes)
+            bulk_store_hint(dst + off, zero_tile, min(tile_bytes, total - off), pol);
+#else
+        for (uint32_t off = (uint32_t)lane * tile_bytes; off < total; off += 32u * tile_bytes)
+            bulk_store(dst + off, zero_tile, min(tile_bytes, total - off));
+#endif
+        bulk_commit();
     }
     if (warp == WARP_BS) {
         // validate + decode the action (Decimal_to_Base_N, ue_mobility.py:310-336: MSB first, digit 0 <-> BS 0)
@@ -596,22 +637,13 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         }
         if (lane == 0) s.ok = ok;
     }
-    if (warp == WARP_GRP && group_tick && lane < c.nG) mob_group_load(c, s, e, lane);
+    if (warp == WARP_GRP && group_tick && lane < c.nG) mob_group_load(s, group_row_load(c, e, lane), lane);
     __syncthreads();                                                   // barrier 1
-    if (!s.ok) return;                                                 // the env is left untouched
-
-    // ---- the dense observation starts streaming out now ----
-    if (bulk_ok) {
-        if (warp == WARP_TMA) {
-            const uint32_t total = (uint32_t)n_cells * 4u;
-            char *dst = reinterpret_cast<char *>(obs_env);
-            for (uint32_t off = (uint32_t)lane * ZERO_TILE_BYTES; off < total; off += 32u * ZERO_TILE_BYTES)
-                bulk_store(dst + off, zero_tile, min((uint32_t)ZERO_TILE_BYTES, total - off));
-            bulk_commit();
-        }
-    } else if (full_obs) {
-        obs_zero_fill_lsu(obs_env, n_cells);
+    if (!s.ok) {                                                       // the env's state is left untouched
+        if (bulk_ok && warp == WARP_TMA) bulk_wait_read_all();         // the tile must outlive the copies' reads
+        return;
     }
+    if (full_obs && !bulk_ok) obs_zero_fill_lsu(obs_env, n_cells);     // fallback: odd sizes / unaligned buffer
 
     // ---- per-UE: movement + channel pass + handover word, one thread per UE ----
     const bool aggregating = agg != 0;
@@ -630,7 +662,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             // the cell of the previous step leaves its association plane
             atomicAdd(obs_env + ((size_t)(1 + (word & 31)) * G + cell.x) * G + cell.y, -1.f);
         }
-        if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u);
+        if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, c.x[i], c.y[i], inj ? c.th_u[i] : 0.0);
         else if (tr) {
             const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
             cell = make_short2((short)xy.x, (short)xy.y);
@@ -725,6 +757,102 @@ __global__ void __launch_bounds__(CTA_THREADS) fill_kernel(char *dst, unsigned l
             bulk_wait_all();
         }
     }
+}
+
+// mode 2: the store-warp pattern of env_kernel in isolation -- persistent CTAs, one warp, a ring of `ring` tiles,
+// every tile re-armed (wait for its previous copy to be read, optional proxy fence) before the next bulk copy.
+// CTA j streams chunks j, j + gridDim.x, ... of per_cta bytes.  flags bit0: fence.proxy.async per tile;
+// bit1: all lanes of the warp issue (tile t by lane t % 32) instead of lane rb; bit2: rewrite a few floats of the
+// tile before every copy (clear + atomic add, as the step kernel does); bit3: a short dependent chain per chunk.
+__global__ void __launch_bounds__(128) fill_ring_kernel(char *dst, unsigned long long bytes, unsigned long long per_cta,
+                                                        int ring, int tile_bytes, int flags) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    float4 *z4 = reinterpret_cast<float4 *>(dyn_smem);
+    for (int i = threadIdx.x; i < ring * tile_bytes / 16; i += blockDim.x) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const unsigned long long n_chunks = (bytes + per_cta - 1) / per_cta;
+    int g = 0;
+    for (unsigned long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const unsigned long long lo = ch * per_cta, n = min(per_cta, bytes - lo);
+        const int nT = (int)((n + tile_bytes - 1) / tile_bytes);
+        for (int t = 0; t < nT; t++, g++) {
+            const int rb = g % ring;
+            const int issuer = (flags & 2) ? (g % 32) : rb;
+            if (g >= ring) {
+                // the lane that issued the previous copy from this tile waits for its read
+                const int prev_issuer = (flags & 2) ? ((g - ring) % 32) : rb;
+                if (lane == prev_issuer) bulk_wait_read_all();
+                __syncwarp();
+            }
+            if (flags & 4) {
+                // what the step kernel's store warp does per tile: clear the previous counts, add the new ones
+                float *buf = reinterpret_cast<float *>(dyn_smem + (size_t)rb * tile_bytes);
+                const int nf = tile_bytes / 4;
+                if (lane < 4 && g >= ring) buf[(unsigned)(lane * 977 + (g - ring) * 131) % (unsigned)nf] = 0.f;
+                __syncwarp();
+                if (lane < 4) atomicAdd(&buf[(unsigned)(lane * 977 + g * 131) % (unsigned)nf], 1.f);
+            }
+            if (flags & 1) fence_proxy_async_smem();
+            __syncwarp();
+            if (flags & 8) {
+                // emulate the per-env sort of the store warp: a dependent chain of shared-memory round trips
+                if (t == 0) {
+                    int v = lane;
+                    for (int r = 0; r < 12; r++) { v = __shfl_xor_sync(0xffffffffu, v, 1) + 1; }
+                    if (v == -1) bulk_commit();
+                }
+            }
+            if (lane == issuer) {
+                const unsigned long long off = (unsigned long long)t * tile_bytes;
+                bulk_store(dst + lo + off, dyn_smem + (size_t)rb * tile_bytes, (uint32_t)min((unsigned long long)tile_bytes, n - off));
+                bulk_commit();
+            }
+        }
+    }
+    bulk_wait_read_all();
+}
+
+// mode 3: the "zeros now, counts one chunk later" pattern -- persistent CTAs, one warp; per chunk the lanes issue the
+// chunk's tiles from ONE constant zero tile, commit, wait for the PREVIOUS chunk's group and (flags bit0) add
+// n_red float REDs into the previous chunk.  flags bit1: wait for the chunk's own group instead (no overlap).
+__global__ void __launch_bounds__(128) fill_env_kernel(char *dst, unsigned long long bytes, unsigned long long per_cta,
+                                                       int tile_bytes, int flags, int n_red) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    float4 *z4 = reinterpret_cast<float4 *>(dyn_smem);
+    for (int i = threadIdx.x; i < tile_bytes / 16; i += blockDim.x) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const unsigned long long n_chunks = (bytes + per_cta - 1) / per_cta;
+    float *prev = nullptr;
+    unsigned prev_n = 0;
+    for (unsigned long long ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+        const unsigned long long lo = ch * per_cta, n = min(per_cta, bytes - lo);
+        for (unsigned long long off = (unsigned long long)lane * tile_bytes; off < n; off += 32ull * tile_bytes)
+            bulk_store(dst + lo + off, dyn_smem, (uint32_t)min((unsigned long long)tile_bytes, n - off));
+        bulk_commit();
+        if (flags & 2) {
+            bulk_wait_all();
+            __syncwarp();
+            if (flags & 1)
+                for (int q = lane; q < n_red; q += 32)
+                    atomicAdd(reinterpret_cast<float *>(dst + lo) + (unsigned)(q * 1031 + 17) % (unsigned)(n / 4), 1.f);
+        } else {
+            if (prev) {
+                bulk_wait_prev();
+                __syncwarp();
+                if (flags & 1)
+                    for (int q = lane; q < n_red; q += 32) atomicAdd(prev + (unsigned)(q * 1031 + 17) % prev_n, 1.f);
+            }
+            prev = reinterpret_cast<float *>(dst + lo);
+            prev_n = (unsigned)(n / 4);
+        }
+    }
+    bulk_wait_all();
 }
 
 }  // namespace uavk

@@ -37,6 +37,11 @@ struct uavenv {
     void *h_action, *h_reward, *h_mean, *h_nout, *h_done;
     Field fields[F_COUNT];
     bool ctor_done;
+    // launch plan of the persistent step kernel
+    void *kernel;
+    int threads, grid, tile_bytes, ctas_per_sm;
+    size_t dyn_smem;
+    bool tiles_ok;
 };
 
 namespace {
@@ -61,23 +66,50 @@ int use_device(uavenv_t *h) {
     return UAVENV_OK;
 }
 
-template <bool F64, int NT>
-cudaError_t launch_env_nt(const uavenv_t *h, const CallArgs &a, cudaStream_t st) {
-    const int nBS = h->d.nBS;
-    const dim3 grid(h->d.E), block(NT);
-    if (nBS <= 4) env_kernel<4, F64, NT><<<grid, block, 0, st>>>(h->d, a);
-    else if (nBS <= 8) env_kernel<8, F64, NT><<<grid, block, 0, st>>>(h->d, a);
-    else if (nBS <= 16) env_kernel<16, F64, NT><<<grid, block, 0, st>>>(h->d, a);
-    else env_kernel<32, F64, NT><<<grid, block, 0, st>>>(h->d, a);
-    return cudaGetLastError();
+typedef void (*env_kernel_fn)(const DevCfg, const CallArgs);
+
+template <bool F64>
+env_kernel_fn pick_nb(int nBS) {
+    if (nBS <= 4) return env_kernel<4, F64, CTA_THREADS>;
+    if (nBS <= 8) return env_kernel<8, F64, CTA_THREADS>;
+    if (nBS <= 16) return env_kernel<16, F64, CTA_THREADS>;
+    return env_kernel<32, F64, CTA_THREADS>;
 }
 
-/* small environments (every UE its own thread, two warps to spare for the BS / group / TMA roles) run in
- * NT_SMALL-thread CTAs so that more of them are resident per SM; larger ones in CTA_THREADS-thread CTAs */
-template <bool F64>
-cudaError_t launch_env(const uavenv_t *h, const CallArgs &a, cudaStream_t st) {
-    if (NT_SMALL < CTA_THREADS && h->d.nUE <= NT_SMALL - 64) return launch_env_nt<F64, NT_SMALL>(h, a, st);
-    return launch_env_nt<F64, CTA_THREADS>(h, a, st);
+/* Launch plan of the step kernel (one CTA per env): the zero tile the TMA warp streams from and the CTAs per SM.
+ * Measured on B200 (profiles/r1/NOTES.md): 64 KB bulk copies amortise the TMA's per-copy cost (7.0 TB/s against
+ * 6.3 TB/s with 16 KB copies), and the observations of all resident CTAs must stay inside the 126 MB L2 or the
+ * count REDs that follow the zeros miss it (-10 %).  The tile is the dynamic shared memory of the kernel, so its
+ * size also sets the residency: 64 KB -> 3 CTAs per SM -> 444 x 200 KB = 89 MB in flight at the reference sizes. */
+int plan_kernel(uavenv_t *h) {
+    const bool f64 = h->cfg.precision == UAVENV_PREC_FP64_PARITY;
+    h->kernel = (void *)(f64 ? pick_nb<true>(h->d.nBS) : pick_nb<false>(h->d.nBS));
+    h->threads = CTA_THREADS;
+    const int64_t n_cells = (int64_t)(h->d.nBS + 1) * h->d.G * h->d.G;
+    int dev_smem = 0, n_sm = 0;
+    CU(h, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    CU(h, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+    cudaFuncAttributes fa;
+    CU(h, cudaFuncGetAttributes(&fa, (const void *)h->kernel));
+    /* the TMA path needs whole float4s per env and 32-bit byte offsets */
+    h->tiles_ok = h->cfg.obs_mode == UAVENV_OBS_F32 && (n_cells & 3) == 0 && n_cells * 4 < 0x7fffffffLL;
+    int64_t tile = TILE_BYTES;
+    if (const char *ev = getenv("UAVENV_TILE_BYTES")) { const long v = atol(ev); if (v >= 128 && v % 128 == 0) tile = v; }
+    {   /* equal copies: ceil(total / tile) of them, each rounded up to 128 B (reference sizes: 3 x 66 688 B) */
+        const int64_t total = n_cells * 4, n_ops = (total + tile - 1) / tile;
+        tile = ((total + n_ops - 1) / n_ops + 127) / 128 * 128;
+    }
+    if (tile + (int64_t)fa.sharedSizeBytes + 1024 > dev_smem) tile = (dev_smem - (int64_t)fa.sharedSizeBytes - 1024) / 128 * 128;
+    h->tile_bytes = h->tiles_ok ? (int)tile : 0;
+    h->dyn_smem = (size_t)h->tile_bytes;
+    if (h->dyn_smem) CU(h, cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+    int per_sm = 0;
+    CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)h->kernel, h->threads, h->dyn_smem));
+    if (per_sm < 1) return fail(h, UAVENV_ECUDA, "step kernel does not fit on an SM%s");
+    h->ctas_per_sm = per_sm;
+    h->grid = h->d.E;
+    (void)n_sm;
+    return UAVENV_OK;
 }
 
 int run_env(uavenv_t *h, int mode, const uavenv_in *in, const uavenv_out *out, void *stream) {
@@ -104,8 +136,10 @@ int run_env(uavenv_t *h, int mode, const uavenv_in *in, const uavenv_out *out, v
     if (h->cfg.mobility == UAVENV_MOB_TRACE && !h->trace) return fail(h, UAVENV_ETRACE, "trace mode but no trace set%s");
     if (h->cfg.obs_mode == UAVENV_OBS_NONE) a.obs = nullptr;
     h->d.trace = (const int32_t *)h->trace;
-    cudaError_t e = h->cfg.precision == UAVENV_PREC_FP64_PARITY ? launch_env<true>(h, a, (cudaStream_t)stream)
-                                                                : launch_env<false>(h, a, (cudaStream_t)stream);
+    /* the TMA warp streams the observation's zeros when the plan allows it and the buffer is float4-aligned */
+    a.tile_bytes = (h->tiles_ok && a.obs && mode != MODE_CTOR && ((uintptr_t)a.obs & 15) == 0) ? h->tile_bytes : 0;
+    ((env_kernel_fn)h->kernel)<<<h->grid, h->threads, h->dyn_smem, (cudaStream_t)stream>>>(h->d, a);
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, UAVENV_ECUDA, "env_kernel launch: %s", cudaGetErrorString(e));
     h->launches++;
     if (mode == MODE_CTOR) h->ctor_done = true;
@@ -281,6 +315,10 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
     d.trace = nullptr; d.trace_T = 0; d.trace_per_env = 0;
     d.err_flags = (uint32_t *)h->err_flags;
 
+    {
+        int rc = plan_kernel(h);
+        if (rc) return rc;
+    }
     if (cfg->mobility == UAVENV_MOB_GROUP) {
         if (cfg->warmup_ticks >= 0) {
             /* mobility init + warm-up + the constructor's positions (mobile_env.py:76-79,93-97) */
@@ -426,6 +464,41 @@ int uavenv_diag_fill(void *dst_dev, int64_t bytes, int64_t bytes_per_cta, int32_
     fill_kernel<<<(unsigned)grid, CTA_THREADS, 0, (cudaStream_t)stream>>>((char *)dst_dev, (unsigned long long)bytes,
                                                                           (unsigned long long)bytes_per_cta, mode);
     return cudaGetLastError() == cudaSuccess ? UAVENV_OK : UAVENV_ECUDA;
+}
+
+int uavenv_diag_fill_ring(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t ring,
+                          int32_t tile_bytes, int32_t flags, void *stream) {
+    if (!dst_dev || bytes < 16 || (bytes & 15) || bytes_per_chunk < 16 || (bytes_per_chunk & 15) || grid < 1 || ring < 1 ||
+        ring > 32 || tile_bytes < 128 || (tile_bytes & 127) || ((uintptr_t)dst_dev & 15))
+        return UAVENV_EINVAL;
+    const size_t dyn = (size_t)ring * tile_bytes;
+    if (dyn > 200 * 1024) return UAVENV_EINVAL;
+    if (cudaFuncSetAttribute((const void *)fill_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
+        return UAVENV_ECUDA;
+    fill_ring_kernel<<<grid, 128, dyn, (cudaStream_t)stream>>>((char *)dst_dev, (unsigned long long)bytes,
+                                                               (unsigned long long)bytes_per_chunk, ring, tile_bytes, flags);
+    return cudaGetLastError() == cudaSuccess ? UAVENV_OK : UAVENV_ECUDA;
+}
+
+int uavenv_diag_fill_env(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t tile_bytes,
+                         int32_t flags, int32_t n_red, void *stream) {
+    if (!dst_dev || bytes < 16 || (bytes & 15) || bytes_per_chunk < 16 || (bytes_per_chunk & 15) || grid < 1 ||
+        tile_bytes < 128 || (tile_bytes & 127) || tile_bytes > 200 * 1024 || n_red < 0 || ((uintptr_t)dst_dev & 15))
+        return UAVENV_EINVAL;
+    if (cudaFuncSetAttribute((const void *)fill_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_bytes) != cudaSuccess)
+        return UAVENV_ECUDA;
+    fill_env_kernel<<<grid, 128, tile_bytes, (cudaStream_t)stream>>>((char *)dst_dev, (unsigned long long)bytes,
+                                                                     (unsigned long long)bytes_per_chunk, tile_bytes, flags, n_red);
+    return cudaGetLastError() == cudaSuccess ? UAVENV_OK : UAVENV_ECUDA;
+}
+
+int uavenv_launch_plan(const uavenv_t *h, int32_t *grid, int32_t *threads, int32_t *tile_bytes, int32_t *ctas_per_sm) {
+    if (!h) return UAVENV_EINVAL;
+    if (grid) *grid = h->grid;
+    if (threads) *threads = h->threads;
+    if (tile_bytes) *tile_bytes = h->tile_bytes;
+    if (ctas_per_sm) *ctas_per_sm = h->ctas_per_sm;
+    return UAVENV_OK;
 }
 
 const uavenv_cfg *uavenv_get_cfg(const uavenv_t *h) { return h ? &h->cfg : nullptr; }

@@ -251,6 +251,13 @@ class BatchedMobiEnvironment:
         return int(f.value)
 
     @property
+    def launch_plan(self) -> dict:
+        """grid / threads of the step kernel, bytes of its TMA zero tile (0 = fallback path), resident CTAs per SM"""
+        g, t, z, o = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self._lib.uavenv_launch_plan(self._h, C.byref(g), C.byref(t), C.byref(z), C.byref(o))
+        return {"grid": g.value, "threads": t.value, "tile_bytes": z.value, "ctas_per_sm": o.value}
+
+    @property
     def launch_count(self) -> int:
         return int(self._lib.uavenv_launch_count(self._h))
 

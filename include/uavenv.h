@@ -147,11 +147,28 @@ int uavenv_set_state(uavenv_t *h, const void *host_buf, int64_t bytes);
  * bit2 UE cell clamped from G to G-1).  Synchronises the stream. */
 int uavenv_check(uavenv_t *h, uint32_t *flags_out, void *stream);
 
+/* Diagnostic: the launch plan of the step kernel -- CTAs (one per env), threads per CTA, bytes of the zeroed
+ * shared-memory tile the TMA warp streams the observation from (0: plain stores + atomics fallback for odd sizes)
+ * and resident CTAs per SM. */
+int uavenv_launch_plan(const uavenv_t *h, int32_t *grid, int32_t *threads, int32_t *tile_bytes, int32_t *ctas_per_sm);
+
 /* Diagnostic (no reference counterpart): zero-fill `bytes` bytes (multiple of 16, 16-byte aligned device pointer) with
  * the store mechanism of the step kernel's observation stream -- mode 0: st.global.v4, mode 1: cp.async.bulk from a
  * zeroed shared-memory tile -- one CTA per bytes_per_cta.  bench.py uses it to measure the box's write-only HBM
  * ceiling beside the step kernel. */
 int uavenv_diag_fill(void *dst_dev, int64_t bytes, int64_t bytes_per_cta, int32_t mode, void *stream);
+
+/* Diagnostic: the store-warp pattern of the step kernel in isolation -- `grid` persistent CTAs, one warp each, a ring
+ * of `ring` shared-memory tiles of tile_bytes, chunk c (bytes_per_chunk) handled by CTA c % grid.  flags bit0: proxy
+ * fence per tile, bit1: rotate the issuing lane. */
+int uavenv_diag_fill_ring(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t ring,
+                          int32_t tile_bytes, int32_t flags, void *stream);
+
+/* Diagnostic: the observation pattern of the step kernel's store warp in isolation -- per chunk: bulk copies of one
+ * constant zero tile, then (flags bit0) n_red float REDs into the chunk whose copies have completed (the previous one,
+ * or with flags bit1 the chunk itself). */
+int uavenv_diag_fill_env(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t tile_bytes,
+                         int32_t flags, int32_t n_red, void *stream);
 
 const uavenv_cfg *uavenv_get_cfg(const uavenv_t *h);
 const char *uavenv_last_error(const uavenv_t *h);
