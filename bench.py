@@ -36,6 +36,11 @@ if ROOT not in sys.path:
 N_BS, N_UE, GRID = 4, 40, 100
 N_GROUPS = 4
 MAXSTEP = 2000
+# --workload: config[1] is the headline (default); config[3] "dense" is the interference-reduction stress case
+WORKLOADS = {
+    "default": dict(n_bs=4, n_ue=40, n_groups=4, envs=4096, name="config[1]"),
+    "dense": dict(n_bs=32, n_ue=2048, n_groups=32, envs=1024, name="config[3] (dense)"),
+}
 METRIC = "env-steps/sec"
 UNIT = "env-steps/s"
 
@@ -106,9 +111,16 @@ def cpu_port_throughput(n_threads: int, envs_per_thread: int, steps: int, seed: 
     from oracle import mobi_oracle as orc
     orc.lib()
     cfg = orc.default_cfg(N_BS, N_UE, GRID, N_GROUPS)
+    init_bs = None
+    if N_BS != 4:                                   # the library's lattice layout for nBS != 4 (uavenv.cu)
+        side = 1
+        while side * side < N_BS:
+            side += 1
+        init_bs = [[max(2, (b // side + 1) * GRID // (side + 1)), max(2, (b % side + 1) * GRID // (side + 1))]
+                   for b in range(N_BS)]
 
     def work(i):
-        t, _ = orc.bench_run(cfg, envs_per_thread, steps, seed=seed, env_id0=i * envs_per_thread)
+        t, _ = orc.bench_run(cfg, envs_per_thread, steps, seed=seed, env_id0=i * envs_per_thread, init_bs_xy=init_bs)
         return t
 
     t0 = time.perf_counter()
@@ -149,7 +161,8 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="environments per GPU (0 = the workload's: 4096 / 1024)")
     ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
     ap.add_argument("--obs", default="f32", choices=["f32", "f32_incremental", "none"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 500)")
@@ -159,6 +172,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[args.workload]
+    global N_BS, N_UE, N_GROUPS
+    N_BS, N_UE, N_GROUPS = wl["n_bs"], wl["n_ue"], wl["n_groups"]
+    if not args.envs:
+        args.envs = wl["envs"]
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -166,27 +184,28 @@ def main():
         args.warmup = 3
 
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU port)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
     from drl_uav_cellularnet_b200 import BatchedMobiEnvironment
-    E = args.envs
+    from drl_uav_cellularnet_b200 import dist as udist
+    udist.init("nccl", dev)
+
+    E = args.envs                                   # weak scaling: every rank steps E envs, global ids rank*E ...
     env = BatchedMobiEnvironment(E, N_BS, N_UE, GRID, "group", precision=args.precision, obs=args.obs, seed=2026,
                                  env_offset=rank * E, device=local_rank)
     env.reset()
     gen = torch.Generator(device=dev)
     gen.manual_seed(1000 + rank)
-    pool = torch.randint(0, env.action_space_dim, (64, E), device=dev, dtype=torch.int64, generator=gen)
+    dense = args.workload == "dense"                # 5**32 overflows int64 (mobile_env.py:104): per-BS digits
+    if dense:
+        pool = torch.randint(0, 5, (64, E, N_BS), device=dev, dtype=torch.uint8, generator=gen)
+    else:
+        pool = torch.randint(0, env.action_space_dim, (64, E), device=dev, dtype=torch.int64, generator=gen)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        udist.barrier()
         torch.cuda.synchronize()
 
     def run_steps(n, first):
@@ -215,17 +234,34 @@ def main():
 
     # ---- end to end through the host-buffer C-ABI call ----
     n_e2e = args.e2e_steps or min(args.steps, 500)
-    act_host = torch.randint(0, env.action_space_dim, (8, E), dtype=torch.int64).pin_memory()
     rew_host = torch.zeros(E, dtype=torch.float64).pin_memory()
     done_host = torch.zeros(E, dtype=torch.uint8).pin_memory()
+    if dense:
+        # the host-buffer entry point takes joint int64 actions; the dense case stages per-BS digits itself
+        act_host = torch.randint(0, 5, (8, E, N_BS), dtype=torch.uint8).pin_memory()
+        act_dev = torch.empty((E, N_BS), dtype=torch.uint8, device=dev)
+
+        def e2e_step(i):
+            act_dev.copy_(act_host[i % 8], non_blocking=True)
+            env.step(act_dev)
+            rew_host.copy_(env.reward, non_blocking=True)
+            done_host.copy_(env.done_u8, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        h2d, d2h = E * N_BS, E * 9
+    else:
+        act_host = torch.randint(0, env.action_space_dim, (8, E), dtype=torch.int64).pin_memory()
+
+        def e2e_step(i):
+            env.step_host(act_host[i % 8], rew_host, done_host)
+        h2d, d2h = E * 8, E * 9
     for i in range(3):
-        env.step_host(act_host[i % 8], rew_host, done_host)
+        e2e_step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     acc = 0.0
     for i in range(n_e2e):
-        env.step_host(act_host[i % 8], rew_host, done_host)
+        e2e_step(i)
         acc += float(rew_host[0])               # the host consumes the step's result
         if bool(done_host[0]):
             env.reset()
@@ -233,22 +269,19 @@ def main():
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = udist.max_over_ranks([ms, ms_e2e], dev)
 
     if rank == 0:
         total_envs = E * world
         value = total_envs * args.steps / (ms * 1e-3)
         e2e_value = total_envs * n_e2e / (ms_e2e * 1e-3)
-        b_env = algorithmic_bytes_per_env_step()
+        b_env = algorithmic_bytes_per_env_step(N_BS, N_UE, GRID, N_GROUPS)
         peak, peak_src = measured_peak_gbs()
         per_launch_s = ms * 1e-3 / max(launches, 1)
         achieved = b_env * E / per_launch_s / 1e9 if args.obs == "f32" else None
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.isfile(tp):
+        if os.path.isfile(tp) and not dense:
             try:
                 with open(tp) as f:
                     traffic = json.load(f).get("env_kernel_dram_bytes_per_launch")
@@ -259,32 +292,39 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
             "ue_steps_per_s": value * N_UE,
-            "config": {"workload": "config[1]: %d batched envs per GPU, 4 UAV-BS x 40 UE, grid 100, group-reference "
-                                   "mobility (float64), Philox fading, random joint actions, obs=%s, reset every 2000 steps"
-                                   % (E, args.obs),
+            "config": {"workload": "%s: %d batched envs per GPU, %d UAV-BS x %d UE, grid 100, group-reference "
+                                   "mobility (float64), Philox fading, random %s actions, obs=%s, reset every 2000 steps"
+                                   % (wl["name"], E, N_BS, N_UE, "per-BS digit" if dense else "joint", args.obs),
                        "envs_per_gpu": E, "n_bs": N_BS, "n_ue": N_UE, "grid_n": GRID, "precision": args.precision,
-                       "l2": "each step writes %.0f MB of observation (> 126 MB L2); no explicit flush" % (E * 4e-6 * (N_BS + 1) * GRID * GRID)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * 8, "d2h_bytes_per_step": E * 9,
+                       "l2": "each step writes %.0f MB of observation (> 126 MB L2): inputs are never cache-resident "
+                             "between steps; no explicit flush" % (E * 4e-6 * (N_BS + 1) * GRID * GRID)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
-                    "note": "uavenv_step_host: pinned host actions in, rewards + done flags out, stream sync per step; "
-                            "the observation stays in HBM for the policy network"},
+                    "note": "uavenv_step_host: pinned host actions in (one async copy), kernel, rewards + done flags "
+                            "written by the kernel into the caller's pinned buffers, stream sync -- every step; the "
+                            "observation stays in HBM for the policy network"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_env,
-                         "kernel": "uavk::env_kernel<4,false,256>", "launch_us": per_launch_s * 1e6},
+                         "kernel": "uavk::env_kernel<%d,false,256>" % (4 if N_BS <= 4 else 8 if N_BS <= 8 else 16 if N_BS <= 16 else 32),
+                         "launch_us": per_launch_s * 1e6,
+                         "write_only_ceiling_gbs": 7030.0,
+                         "write_only_ceiling_note": "64 KB bulk-copy zero fill on this pool's B200, profiles/r1/NOTES.md"},
             "clocks": clocks,
             "launch_plan": env.launch_plan,
             "device_error_flags": flags,
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            v, tmax, wall = cpu_port_throughput(cores, 16, 4000)
+            ne, ns = (1, 40) if dense else (16, 40000)          # ~10-20 s of CPU work
+            v, tmax, wall = cpu_port_throughput(cores, ne, ns)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d threads x 16 envs x 4000 steps of the C float64 port of the reference "
-                                              "step (oracle/mobi_oracle.c), %.1f s wall" % (cores, wall)}
+                                    "sample": "%d threads x %d envs x %d steps of the C float64 port of the reference "
+                                              "step (oracle/mobi_oracle.c), %.1f s wall" % (cores, ne, ns, wall)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        import torch.distributed as dist
         dist.destroy_process_group()
 
 

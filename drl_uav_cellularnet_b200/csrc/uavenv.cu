@@ -372,6 +372,14 @@ int uavenv_step(uavenv_t *h, const uavenv_in *in, const uavenv_out *out, void *s
     return run_env(h, MODE_STEP, in, out, stream);
 }
 
+/* device alias of a pinned (page-locked, mapped) host buffer, or NULL for pageable memory */
+static void *pinned_alias(const void *p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
                      double *mean_sinr_host, int32_t *n_out_host, void *stream) {
     if (!h || !action_host) return fail(h, UAVENV_EINVAL, "step_host: action_host is NULL%s");
@@ -379,21 +387,28 @@ int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, dou
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->d.E;
+    /* Actions go to HBM with one async copy (the kernel's prologue must not wait on PCIe).  Results are written by
+     * the kernel straight into the caller's buffers when those are pinned (mapped) host memory -- posted PCIe
+     * writes, no device-to-host copies on the stream -- and through device staging + copies otherwise. */
     CU(h, cudaMemcpyAsync(h->h_action, action_host, E * 8, cudaMemcpyHostToDevice, st));
     uavenv_in in;
     memset(&in, 0, sizeof(in));
     in.action = (const int64_t *)h->h_action;
+    void *rw = pinned_alias(reward_host), *dn = pinned_alias(done_host), *ms = pinned_alias(mean_sinr_host),
+         *no = pinned_alias(n_out_host);
     uavenv_out out;
     memset(&out, 0, sizeof(out));
     out.obs = obs_dev;
-    out.reward = (double *)h->h_reward; out.mean_sinr = (double *)h->h_mean;
-    out.n_out = (int32_t *)h->h_nout; out.done = (uint8_t *)h->h_done;
+    out.reward = reward_host ? (double *)(rw ? rw : h->h_reward) : nullptr;
+    out.done = done_host ? (uint8_t *)(dn ? dn : h->h_done) : nullptr;
+    out.mean_sinr = mean_sinr_host ? (double *)(ms ? ms : h->h_mean) : nullptr;
+    out.n_out = n_out_host ? (int32_t *)(no ? no : h->h_nout) : nullptr;
     rc = run_env(h, MODE_STEP, &in, &out, stream);
     if (rc) return rc;
-    if (reward_host) CU(h, cudaMemcpyAsync(reward_host, h->h_reward, E * 8, cudaMemcpyDeviceToHost, st));
-    if (done_host) CU(h, cudaMemcpyAsync(done_host, h->h_done, E, cudaMemcpyDeviceToHost, st));
-    if (mean_sinr_host) CU(h, cudaMemcpyAsync(mean_sinr_host, h->h_mean, E * 8, cudaMemcpyDeviceToHost, st));
-    if (n_out_host) CU(h, cudaMemcpyAsync(n_out_host, h->h_nout, E * 4, cudaMemcpyDeviceToHost, st));
+    if (reward_host && !rw) CU(h, cudaMemcpyAsync(reward_host, h->h_reward, E * 8, cudaMemcpyDeviceToHost, st));
+    if (done_host && !dn) CU(h, cudaMemcpyAsync(done_host, h->h_done, E, cudaMemcpyDeviceToHost, st));
+    if (mean_sinr_host && !ms) CU(h, cudaMemcpyAsync(mean_sinr_host, h->h_mean, E * 8, cudaMemcpyDeviceToHost, st));
+    if (n_out_host && !no) CU(h, cudaMemcpyAsync(n_out_host, h->h_nout, E * 4, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     return UAVENV_OK;
 }

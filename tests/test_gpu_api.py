@@ -1,0 +1,260 @@
+"""GPU tests of the host-facing behaviour of the CUDA path (through the C-ABI library): the host-buffer entry
+point, sharding invariance, error behaviour, masked reset, state clone, the fallback observation paths, and
+size-independent properties at BASELINE.json's full sizes (config[1]: 4096 envs; config[3]: 32 BS x 2048 UE).
+Need a B200: -m gpu."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import drl_uav_cellularnet_b200 as p
+    return p
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def _actions(E, T, seed=3, n=625):
+    return np.random.RandomState(seed).randint(0, n, size=(T, E))
+
+
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_equals_device_step(pkg, pinned):
+    """uavenv_step_host (host actions in, host rewards / done / mean SINR / outage counts out; pinned buffers are
+    written by the kernel directly, pageable ones through staging copies) == uavenv_step on device tensors."""
+    E, T = 64, 12
+    a = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=11)
+    b = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=11)
+    a.reset()
+    b.reset()
+    mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    act_h = mk(torch.zeros(E, dtype=torch.int64))
+    rew_h, done_h = mk(torch.zeros(E, dtype=torch.float64)), mk(torch.zeros(E, dtype=torch.uint8))
+    mean_h, nout_h = mk(torch.zeros(E, dtype=torch.float64)), mk(torch.zeros(E, dtype=torch.int32))
+    acts = _actions(E, T)
+    for t in range(T):
+        act_h.copy_(torch.from_numpy(acts[t]))
+        obs_a = a.step_host(act_h, rew_h, done_h, mean_h, nout_h)
+        obs_b, r, d, info = b.step(acts[t])
+        torch.cuda.synchronize()
+        assert np.array_equal(rew_h.numpy(), _np(r)), t
+        assert np.array_equal(done_h.numpy().astype(bool), _np(d)), t
+        assert np.array_equal(mean_h.numpy(), _np(info["mean_sinr"])), t
+        assert np.array_equal(nout_h.numpy(), _np(info["n_out"])), t
+        assert torch.equal(obs_a, obs_b), t
+    assert a.check() == 0 and b.check() == 0
+
+
+def test_sharding_invariance(pkg):
+    """Environments are keyed by GLOBAL id: one handle with 12 envs == three handles with 4 envs at offsets
+    0 / 4 / 8 (how bench.py shards config[2] over ranks), for the fp32 and the fp64 kernels."""
+    E, T, seed = 12, 25, 2026
+    acts = _actions(E, T)
+    for prec in ("fp32", "fp64"):
+        full = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=seed, precision=prec)
+        parts = [pkg.BatchedMobiEnvironment(4, 4, 40, 100, "group", seed=seed, precision=prec, env_offset=4 * i)
+                 for i in range(3)]
+        o_full = full.reset()
+        o_parts = [p.reset() for p in parts]
+        assert torch.equal(o_full, torch.cat(o_parts))
+        for t in range(T):
+            o_full, r, d, info = full.step(acts[t])
+            outs = [p.step(acts[t][4 * i:4 * i + 4]) for i, p in enumerate(parts)]
+            assert torch.equal(o_full, torch.cat([o[0] for o in outs])), (prec, t)
+            assert torch.equal(r, torch.cat([o[1] for o in outs])), (prec, t)
+            for k in ("serving", "serving_sinr", "ue_xy", "bs_xy", "n_out", "n_ho", "mean_sinr"):
+                assert torch.equal(info[k], torch.cat([o[3][k] for o in outs])), (prec, t, k)
+
+
+def test_invalid_action_is_rejected_and_state_kept(pkg):
+    """An action >= 5**nBS (ValueError in the reference, ue_mobility.py:323-336) raises on check() and leaves the
+    state of that env untouched; the other envs of the batch are stepped."""
+    E = 4
+    env = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=5, precision="fp64")
+    ref = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=5, precision="fp64")
+    env.reset()
+    ref.reset()
+    before = env.get_state()
+    env.step(np.array([3, 625, 17, -1]))
+    with pytest.raises(ValueError):
+        env.check()
+    ref.step(np.array([3, 0, 17, 0]))
+    after, want = env.get_state(), ref.get_state()
+    for k in after:
+        assert np.array_equal(after[k][[1, 3]], before[k][[1, 3]]), k          # rejected envs: unchanged
+        assert np.array_equal(after[k][[0, 2]], want[k][[0, 2]]), k            # the others: stepped
+    assert env.check() == 0                                                    # flags are cleared by check()
+    single = pkg.MobiEnvironment(4, 40, 100)
+    single.reset()
+    with pytest.raises(ValueError):
+        single.step(625)
+    with pytest.raises(ValueError):
+        pkg.MobiEnvironment(4, 40, 100, "random_walk")                          # sys.exit at mobile_env.py:91
+
+
+def test_trace_exhaustion_raises_index_error(pkg):
+    """step_test past the end of the trace: IndexError as in the reference (mobile_env.py:203)."""
+    trace = np.random.RandomState(0).randint(0, 100, size=(3, 40, 2))
+    env = pkg.MobiEnvironment(4, 40, 100, "read_trace", trace=trace, fading="none")
+    env.reset()
+    for _ in range(3):
+        env.step_test(624)
+    with pytest.raises(IndexError):
+        env.step_test(624)
+
+
+def test_masked_reset_and_done(pkg):
+    """reset(env_mask) touches only the selected envs (main.py:188-190 resets a worker's env when done);
+    done is raised at step_n >= MAXSTEP (mobile_env.py:186-187) and step_n keeps counting."""
+    E = 6
+    env = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=9, max_step=5)
+    env.reset()
+    for t in range(5):
+        obs, r, d, info = env.step(np.full(E, 624))
+        assert bool(d.all()) == (t == 4)
+    before = env.get_state()
+    obs_before = env.obs.clone()
+    mask = np.array([1, 0, 0, 1, 0, 1], dtype=np.uint8)
+    env.reset(env_mask=mask)
+    after = env.get_state()
+    keep = mask == 0
+    for k in after:
+        assert np.array_equal(after[k][keep], before[k][keep]), k
+    assert torch.equal(env.obs[torch.from_numpy(keep)], obs_before[torch.from_numpy(keep)])
+    assert np.array_equal(after["counters"][:, 2], np.where(mask, 0, 5))       # step_n
+    init_bs = np.array([[25, 25], [25, 75], [75, 25], [75, 75]])               # mobile_env.py:49-50
+    assert np.array_equal(after["bs_xy"][mask == 1], np.broadcast_to(init_bs, (3, 4, 2)))
+
+
+def test_state_clone_what_if_step(pkg):
+    """copy.deepcopy(env) + look-ahead step_test(624) of gradient.py:14-17: get_state / set_state round trip."""
+    env = pkg.BatchedMobiEnvironment(3, 4, 40, 100, "group", seed=21, precision="fp64")
+    env.reset()
+    env.step(np.array([1, 2, 3]))
+    snap = env.get_state()
+    o1, r1, _, i1 = env.step(np.full(3, 624))
+    o1, r1, srv1 = o1.clone(), r1.clone(), i1["serving"].clone()
+    env.step(np.array([5, 6, 7]))
+    env.set_state(snap)
+    o2, r2, _, i2 = env.step(np.full(3, 624))
+    assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(srv1, i2["serving"])
+
+
+@pytest.mark.parametrize("nBS,nUE,G", [(4, 40, 25), (3, 17, 10), (4, 40, 100), (6, 100, 64)])
+def test_observation_paths_agree_with_oracle(pkg, nBS, nUE, G):
+    """The dense observation through every code path -- TMA zero stream + count REDs (whole float4s per env),
+    plain-store fallback (odd sizes), incremental updates -- against the oracle's state for the same env."""
+    from oracle import mobi_oracle as orc
+    seed, E, T = 31, 5, 30
+    gs = [nUE // 4 + (1 if g < nUE % 4 else 0) for g in range(4)]
+    kw = dict(seed=seed, precision="fp64", group_sizes=gs)
+    if nBS != 4:
+        kw["init_bs_xy"] = [[2 + (G - 4) * b // nBS, 2 + (G - 4) * ((b * 7) % nBS) // nBS] for b in range(nBS)]
+    full = pkg.BatchedMobiEnvironment(E, nBS, nUE, G, "group", obs="f32", **kw)
+    inc = pkg.BatchedMobiEnvironment(E, nBS, nUE, G, "group", obs="f32_incremental", **kw)
+    plan = full.launch_plan
+    assert (plan["tile_bytes"] > 0) == (((nBS + 1) * G * G) % 4 == 0), plan
+    cfg = orc.default_cfg(nBS, nUE, G, 4)
+    oenvs = [orc.OracleEnv(cfg, group_sizes=gs, init_bs_xy=kw.get("init_bs_xy"), seed=seed, env_id=e) for e in range(E)]
+    want = np.stack([o.reset() for o in oenvs])
+    assert np.array_equal(_np(full.reset()).astype(np.float64), want)
+    assert np.array_equal(_np(inc.reset()).astype(np.float64), want)
+    acts = np.random.RandomState(1).randint(0, 5, size=(T, E, nBS)).astype(np.uint8)
+    for t in range(T):
+        of, *_ = full.step(acts[t])
+        oi, *_ = inc.step(acts[t])
+        want = np.stack([oenvs[e].step(acts[t][e].astype(np.int32))[0] for e in range(E)])
+        assert np.array_equal(_np(of).astype(np.float64), want), t
+        assert np.array_equal(_np(oi).astype(np.float64), want), t
+    assert full.check() == 0 and inc.check() == 0
+
+
+def test_unaligned_observation_buffer_uses_fallback(pkg):
+    """A caller-provided observation buffer that is not 16-byte aligned cannot be a TMA destination: the same
+    call must fall back to plain stores and still produce the identical observation."""
+    import ctypes as C
+    from drl_uav_cellularnet_b200 import _native as N
+    E = 3
+    a = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=8)
+    b = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=8)
+    a.reset()
+    b.reset()
+    raw = torch.zeros(E * 50000 + 1, dtype=torch.float32, device=b.device)
+    shifted = raw[1:]                                                           # base + 4 bytes
+    assert shifted.data_ptr() % 16 == 4
+    b._out.obs = C.c_void_p(shifted.data_ptr())
+    act = np.array([7, 300, 624])
+    oa, *_ = a.step(act)
+    b.step(act)
+    torch.cuda.synchronize()
+    assert torch.equal(oa.reshape(-1), shifted)
+    assert N.OK == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_full_size_properties_config1(pkg):
+    """config[1] sizes (4096 envs, 4 x 40, grid 100), fp32 kernels, 40 steps + a reset: properties that do not need
+    the oracle -- BS plane sums to nBS and the association planes to nUE in every env, every count is where
+    (serving, ue_xy, bs_xy) say it is, rewards obey the clamp, incremental observations equal rebuilt ones, and
+    two handles with the same seed agree bit for bit (determinism across launches)."""
+    E, T = 4096, 40
+    a = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=123)
+    b = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=123, obs="f32_incremental")
+    a.reset()
+    b.reset()
+    acts = torch.from_numpy(_actions(E, T, seed=77)).cuda()
+    ar = torch.arange(E, device="cuda")
+    for t in range(T):
+        obs, r, d, info = a.step(acts[t])
+        obs_b, r_b, *_ = b.step(acts[t])
+        assert torch.equal(obs, obs_b), t
+        assert torch.equal(r, r_b), t
+        assert torch.all(obs[:, 0].sum(dim=(1, 2)) == 4) and torch.all(obs[:, 1:].sum(dim=(1, 2, 3)) == 40), t
+        rebuilt = torch.zeros_like(obs)
+        ue, srv, bs = info["ue_xy"].long(), info["serving"].long(), info["bs_xy"].long()
+        rebuilt.index_put_((ar[:, None].expand(E, 40), 1 + srv, ue[..., 0], ue[..., 1]),
+                           torch.ones((), device="cuda"), accumulate=True)
+        rebuilt.index_put_((ar[:, None].expand(E, 4), torch.zeros_like(bs[..., 0]), bs[..., 0], bs[..., 1]),
+                           torch.ones((), device="cuda"), accumulate=True)
+        assert torch.equal(obs, rebuilt), t
+        want = torch.clamp(info["mean_sinr"] / 20 - info["n_out"].double() / 40, min=-1.0)
+        assert torch.allclose(r, want, rtol=0, atol=1e-12), t
+        assert int(info["n_out"].max()) <= 40 and int(info["n_out"].min()) >= 0
+        if t == 20:
+            a.reset()
+            b.reset()
+    assert a.check() == 0 and b.check() == 0
+
+
+def test_full_size_properties_dense(pkg):
+    """config[3] sizes (32 UAV-BS x 2048 UE, 64 of the 1024 envs to keep the test short), fp32 kernels: plane sums,
+    exact count placement, serving BS = argmax of the SINR the kernel itself reports whenever a handover fired."""
+    E, nBS, nUE, T = 64, 32, 2048, 6
+    env = pkg.BatchedMobiEnvironment(E, nBS, nUE, 100, "group", seed=5, diagnostics=True)
+    env.reset()
+    rs = np.random.RandomState(2)
+    ar = torch.arange(E, device="cuda")
+    prev_srv = env.serving.clone()
+    for t in range(T):
+        digits = rs.randint(0, 5, size=(E, nBS)).astype(np.uint8)
+        obs, r, d, info = env.step(digits)
+        assert torch.all(obs[:, 0].sum(dim=(1, 2)) == nBS) and torch.all(obs[:, 1:].sum(dim=(1, 2, 3)) == nUE), t
+        ue, srv = info["ue_xy"].long(), info["serving"].long()
+        rebuilt = torch.zeros_like(obs[:, 1:])
+        rebuilt.index_put_((ar[:, None].expand(E, nUE), srv, ue[..., 0], ue[..., 1]), torch.ones((), device="cuda"),
+                           accumulate=True)
+        assert torch.equal(obs[:, 1:], rebuilt), t
+        changed = srv != prev_srv.long()
+        best = env.sinr_all.argmax(dim=2)
+        assert torch.equal(srv[changed], best[changed]), t                      # handovers go to the best server
+        assert int(info["n_ho"].sum()) == int(changed.sum()), t
+        prev_srv = info["serving"].clone()
+    assert env.check() == 0
