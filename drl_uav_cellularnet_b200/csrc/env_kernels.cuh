@@ -96,6 +96,7 @@ struct CallArgs {
     int16_t *ue_xy, *bs_xy_out;  // [E,nUE,2], [E,nBS,2]
     uint8_t *bs_digits;          // [E,nBS]
     int tile_bytes;              // bytes of the zeroed shared-memory tile the TMA warp streams from (0: no TMA path)
+    int cells_off;               // byte offset of the UE-cell staging area in dynamic shared memory (-1: use HBM)
 };
 
 struct EnvShared {
@@ -313,6 +314,37 @@ __device__ __forceinline__ int bs_move_warp(const DevCfg &c, int &bx, int &by, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// UpdateDroneNet's decisions for one UE (channel.py:145-176) from this pass's best server (index, SINR) and the
+// SINR of the UE's current cell.  Decisions are taken in float64 on the (exactly converted) SINR values in both
+// precisions, so they are a pure function of the SINR matrix the pass produced.  Updates the handover word and
+// returns the serving-cell SINR the reference stores in current_BS_sinr (PRE-handover cell, channel.py:145-146).
+template <typename T>
+__device__ __forceinline__ T ho_decide(const DevCfg &c, int mode, int best, T bestS, T curS, uint32_t &word,
+                                       int &new_out, int &did_ho) {
+    const double out_thr = c.out_thr, ho_thr = c.ho_thr;
+    if (mode != MODE_STEP) {
+        // LTEChannel ctor / reset (channel.py:92-93,110,113-116): associate to the best server, FIFO = 1 row
+        word = ho_pack(best, best, 0, 0, 1, (double)bestS <= out_thr ? 1 : 0);
+        new_out = 0; did_ho = 0;
+        return bestS;
+    }
+    int cur = word & 31, f0 = (word >> 5) & 31, f1 = (word >> 10) & 31, f2 = (word >> 15) & 31;
+    int depth = (word >> 20) & 3;
+    const int outp = (word >> 22) & 1;
+    bool remain;                                                       // channel.py:148-155
+    if (depth == 1) { f1 = best; depth = 2; remain = (f1 == f0); }
+    else if (depth == 2) { f2 = best; depth = 3; remain = (f1 == f0) && (f2 == f0); }
+    else { f0 = f1; f1 = f2; f2 = best; remain = (f1 == f0) && (f2 == f0); }
+    const bool need = remain && (cur != best) && ((double)bestS - (double)curS > ho_thr);   // :156-159
+    if (need) cur = best;                                              // :162-167
+    did_ho = need ? 1 : 0;
+    const int o = (double)curS <= out_thr ? 1 : 0;                     // :170
+    new_out = (o && !outp) ? 1 : 0;                                    // :171-174
+    word = ho_pack(cur, f0, f1, f2, depth, o);
+    return curS;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 template <bool F64> struct Real { using T = float; };
 template <> struct Real<true> { using T = double; };
 
@@ -444,35 +476,84 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
     T bestS = S[0];
 #pragma unroll
     for (int b = 1; b < NB; b++) if (S[b] > bestS) { bestS = S[b]; best = b; }
-
-    // decisions are taken in float64 on the (exactly converted) SINR values in both precisions, so they are a
-    // pure function of the SINR matrix this pass produced
-    const double out_thr = c.out_thr, ho_thr = c.ho_thr;
-    T curS;
-    if (mode != MODE_STEP) {
-        // LTEChannel ctor / reset (channel.py:92-93,110,113-116): associate to the best server, FIFO = 1 row
-        curS = bestS;
-        word = ho_pack(best, best, 0, 0, 1, (double)bestS <= out_thr ? 1 : 0);
-        new_out = 0; did_ho = 0;
-    } else {
-        int cur = word & 31, f0 = (word >> 5) & 31, f1 = (word >> 10) & 31, f2 = (word >> 15) & 31;
-        int depth = (word >> 20) & 3;
-        const int outp = (word >> 22) & 1;
-        curS = S[0];
+    const int cur = word & 31;
+    T curS = S[0];
 #pragma unroll
-        for (int b = 1; b < NB; b++) if (b == cur) curS = S[b];        // serving SINR of the PRE-handover cell
-        bool remain;                                                   // channel.py:148-155
-        if (depth == 1) { f1 = best; depth = 2; remain = (f1 == f0); }
-        else if (depth == 2) { f2 = best; depth = 3; remain = (f1 == f0) && (f2 == f0); }
-        else { f0 = f1; f1 = f2; f2 = best; remain = (f1 == f0) && (f2 == f0); }
-        const bool need = remain && (cur != best) && ((double)bestS - (double)curS > ho_thr);   // :156-159
-        if (need) cur = best;                                          // :162-167
-        did_ho = need ? 1 : 0;
-        const int o = (double)curS <= out_thr ? 1 : 0;                 // :170
-        new_out = (o && !outp) ? 1 : 0;                                // :171-174
-        word = ho_pack(cur, f0, f1, f2, depth, o);
+    for (int b = 1; b < NB; b++) if (b == cur) curS = S[b];            // serving SINR of the PRE-handover cell
+    return ho_decide<T>(c, mode, best, bestS, curS, word, new_out, did_ho);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 channel pass for more than 4 BSs: NB/4 adjacent lanes share one UE, each lane owns 4 BSs (one Philox call =
+// its 4 fading normals), so a warp runs 32/(NB/4) UEs at once with small register arrays.  The exclude-self
+// interference sum is (the other three of my four) + (the quad sums of the other lanes, gathered with shuffles) --
+// never total - own; the best server is a shuffle argmax with lowest-index tie break.  All lanes of a
+// group end up with the same decision; the caller lets lane q == 0 write it.  `u` must be clamped to a valid UE on
+// every lane (shuffles need the whole warp).
+template <int NB>
+__device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs &a, const EnvShared &s, int e,
+                                                 uint32_t genv, int u, int cx, int cy, uint32_t epoch, int mode,
+                                                 uint32_t &word, int &new_out, int &did_ho) {
+    constexpr int LPU = NB / 4;                                        // lanes per UE
+    static_assert(NB == 8 || NB == 16 || NB == 32, "quad mapping");
+    const int lane = threadIdx.x & 31, q = lane & (LPU - 1), gbase = lane & ~(LPU - 1);
+    const int nBS = c.nBS, cpu = (nBS + 3) >> 2, b0 = 4 * q;
+    const size_t pair0 = ((size_t)e * c.nUE + u) * nBS;
+    float fade[4] = {0.f, 0.f, 0.f, 0.f};
+    if (c.fading == FADE_INJECTED) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (b0 + k < nBS) fade[k] = (float)a.fading[pair0 + b0 + k];
+    } else if (c.fading == FADE_PHILOX && q < cpu) {
+        const Philox4 p = philox4x32_10(genv, (uint32_t)(u * cpu + q), epoch, DOM_FADING, c.k0, c.k1);
+        float z[4];
+        normal4_f32(p, z);
+#pragma unroll
+        for (int k = 0; k < 4; k++) fade[k] = fmaf(c.f_sh_sd, z[k], c.f_sh_mean);
     }
-    return curS;
+    float gdb[4], p[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        gdb[k] = 0.f; p[k] = 0.f;
+        const int b = b0 + k;
+        if (b < nBS) {
+            if (a.fading_used) a.fading_used[pair0 + b] = fade[k];
+            const int dx = cx - s.bsx[b], dy = cy - s.bsy[b];
+            const float qd = c.f_q_scale * (float)(dx * dx + dy * dy);
+            const float loss = qd > c.f_q_min ? fmaf(c.f_loss_k, __log2f(qd), c.f_loss_a) : 0.f;
+            gdb[k] = c.f_g0 - loss - fade[k];
+            p[k] = exp2f(fmaf(gdb[k], c.f_exp_k, c.f_log2P));
+        }
+    }
+    const float quad = (p[0] + p[1]) + (p[2] + p[3]);
+    float others = 0.f;                                                // quad sums of the other lanes of the group
+#pragma unroll
+    for (int r = 1; r < LPU; r++) others += __shfl_sync(0xffffffffu, quad, gbase | ((q + r) & (LPU - 1)));
+    float S[4];
+    int best = b0;
+    float bestS = -3.0e38f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float mine = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (j != k) mine += p[j];
+        S[k] = b0 + k < nBS ? (gdb[k] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + (others + mine)) : -3.0e38f;
+        if (S[k] > bestS) { bestS = S[k]; best = b0 + k; }             // first maximum inside the quad
+        if (a.sinr_all && b0 + k < nBS) reinterpret_cast<float *>(a.sinr_all)[pair0 + b0 + k] = S[k];
+    }
+    // best server over the group: butterfly argmax, ties to the lower BS index (np.argmax, channel.py:141)
+#pragma unroll
+    for (int o = 1; o < LPU; o <<= 1) {
+        const float oS = __shfl_xor_sync(0xffffffffu, bestS, o);
+        const int oB = __shfl_xor_sync(0xffffffffu, best, o);
+        if (oS > bestS || (oS == bestS && oB < best)) { bestS = oS; best = oB; }
+    }
+    // SINR of the UE's current (pre-handover) cell lives on lane cur/4 of the group
+    const int cur = word & 31;
+    float mineS = S[0];
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k == (cur & 3)) mineS = S[k];
+    const float curS = __shfl_sync(0xffffffffu, mineS, gbase | ((cur >> 2) & (LPU - 1)));
+    return ho_decide<float>(c, mode, best, bestS, curS, word, new_out, did_ho);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -654,6 +735,52 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     }
     double sum_sinr = 0.0;
     int cnt_out = 0, cnt_ho = 0;
+    if constexpr (!F64 && NB > 4) {
+        // ---- more than 4 BSs, fp32: two mappings.  (A) thread = UE: movement; cells staged through shared memory.
+        short2 *cells = a.cells_off >= 0 ? reinterpret_cast<short2 *>(dyn_smem + a.cells_off)
+                                         : reinterpret_cast<short2 *>(c.ue_cell) + (size_t)e * nUE;
+        for (int u = tid; u < nUE; u += NT) {
+            const size_t i = (size_t)e * nUE + u;
+            short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
+            if (incremental) {
+                // the cell of the previous step leaves its association plane
+                atomicAdd(obs_env + ((size_t)(1 + (c.ho[i] & 31)) * G + cell.x) * G + cell.y, -1.f);
+            }
+            if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, c.x[i], c.y[i], inj ? c.th_u[i] : 0.0);
+            else if (tr) {
+                const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
+                cell = make_short2((short)xy.x, (short)xy.y);
+            }
+            if (mode != MODE_CTOR || c.mobility == MOB_TRACE) reinterpret_cast<short2 *>(c.ue_cell)[i] = cell;
+            if (a.cells_off >= 0) cells[u] = cell;
+            if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
+        }
+        __syncthreads();
+        // ---- (B) NB/4 lanes = one UE, lane = 4 BSs: channel pass with shuffle reductions (ue_channel_quad)
+        constexpr int LPU = NB / 4, UPW = 32 / LPU;
+        const int q = lane & (LPU - 1);
+        for (int base = warp * UPW; base < nUE; base += NW * UPW) {
+            const int uu = base + lane / LPU;
+            const bool live = uu < nUE;
+            const int u = live ? uu : nUE - 1;
+            const size_t i = (size_t)e * nUE + u;
+            const short2 cell = cells[u];
+            uint32_t word = mode == MODE_STEP ? c.ho[i] : 0u;
+            int new_out, did_ho;
+            const float curS = ue_channel_quad<NB>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
+                                                   new_out, did_ho);
+            if (live && q == 0) {
+                c.ho[i] = word;
+                sum_sinr += (double)curS;
+                cnt_out += new_out;
+                cnt_ho += did_ho;
+                const int srv = word & 31;
+                if (a.serving) a.serving[i] = (uint8_t)srv;
+                if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = curS;
+                if (incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+            }
+        }
+    } else {
     for (int u = tid; u < nUE; u += NT) {
         const size_t i = (size_t)e * nUE + u;
         short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
@@ -681,6 +808,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         if (a.serving_sinr) reinterpret_cast<T *>(a.serving_sinr)[i] = curS;
         if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
         if (incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+    }
     }
     if (group_tick) { mob_phase_advance(c, agg, deagg); tick++; }
 

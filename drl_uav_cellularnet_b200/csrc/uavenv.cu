@@ -39,7 +39,7 @@ struct uavenv {
     bool ctor_done;
     // launch plan of the persistent step kernel
     void *kernel;
-    int threads, grid, tile_bytes, ctas_per_sm;
+    int threads, grid, tile_bytes, ctas_per_sm, cells_off;
     size_t dyn_smem;
     bool tiles_ok;
 };
@@ -101,7 +101,20 @@ int plan_kernel(uavenv_t *h) {
     }
     if (tile + (int64_t)fa.sharedSizeBytes + 1024 > dev_smem) tile = (dev_smem - (int64_t)fa.sharedSizeBytes - 1024) / 128 * 128;
     h->tile_bytes = h->tiles_ok ? (int)tile : 0;
-    h->dyn_smem = (size_t)h->tile_bytes;
+    /* fp32 kernels with more than 4 BSs stage the env's UE cells in shared memory between the movement pass
+     * (thread = UE) and the channel pass (lane = 4 BSs of a UE); if they do not fit, HBM is the staging area */
+    const int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 4 + 127) & ~(int64_t)127) : 0;
+    h->cells_off = -1;
+    if (cells_bytes && cells_bytes <= 32768) {
+        if (h->tile_bytes + cells_bytes + (int64_t)fa.sharedSizeBytes + 1024 > dev_smem) {
+            /* shrink the tile (re-balanced) to make room */
+            const int64_t total = n_cells * 4, room = (dev_smem - (int64_t)fa.sharedSizeBytes - 1024 - cells_bytes) / 128 * 128;
+            const int64_t n_ops = (total + room - 1) / room;
+            h->tile_bytes = h->tiles_ok ? (int)(((total + n_ops - 1) / n_ops + 127) / 128 * 128) : 0;
+        }
+        h->cells_off = h->tile_bytes;
+    }
+    h->dyn_smem = (size_t)h->tile_bytes + (h->cells_off >= 0 ? (size_t)cells_bytes : 0);
     if (h->dyn_smem) CU(h, cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
     int per_sm = 0;
     CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)h->kernel, h->threads, h->dyn_smem));
@@ -138,6 +151,7 @@ int run_env(uavenv_t *h, int mode, const uavenv_in *in, const uavenv_out *out, v
     h->d.trace = (const int32_t *)h->trace;
     /* the TMA warp streams the observation's zeros when the plan allows it and the buffer is float4-aligned */
     a.tile_bytes = (h->tiles_ok && a.obs && mode != MODE_CTOR && ((uintptr_t)a.obs & 15) == 0) ? h->tile_bytes : 0;
+    a.cells_off = h->cells_off;
     ((env_kernel_fn)h->kernel)<<<h->grid, h->threads, h->dyn_smem, (cudaStream_t)stream>>>(h->d, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, UAVENV_ECUDA, "env_kernel launch: %s", cudaGetErrorString(e));

@@ -738,3 +738,56 @@ double orc_bench_run(const orc_cfg *c, const int32_t *group_sizes, const int32_t
     if (checksum) *checksum = acc;
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------- */
+/* Trace-replay sweep (BASELINE config 5): one read_trace env, `n_steps` step_test calls with the given joint actions
+ * and Philox fading (env id = env_id), recording per step the new-outage count, the handover count, the reward and
+ * an exact integer hash of current_BS (sum_u (u+1)*(cur[u]+1)).  MAXSTEP/done is ignored like main_test.py:70-103
+ * ignores it.  Returns 0, or the step index + 1 at which the trace ran out. */
+int orc_replay_run(const orc_cfg *c, const int32_t *trace, int64_t T, uint64_t seed, uint32_t env_id,
+                   const int64_t *actions, int n_steps, int32_t *n_out, int32_t *n_ho, double *reward,
+                   int64_t *serving_hash) {
+    int32_t gs[64];
+    int32_t digits[ORC_MAX_BS];
+    for (int g = 0; g < c->n_groups; g++) gs[g] = c->n_ue / c->n_groups + (g < c->n_ue % c->n_groups ? 1 : 0);
+    orc_env *e = orc_env_create(c, gs, NULL, ORC_MOB_TRACE, ORC_FADE_PHILOX, seed, env_id, 0);
+    orc_env_set_trace(e, trace, T);
+    int rc = orc_env_ctor_channel(e, NULL);
+    if (!rc) rc = orc_env_reset(e, NULL, NULL, NULL);
+    for (int s = 0; s < n_steps && !rc; s++) {
+        orc_step_out o;
+        orc_action_digits(actions[s], c->n_act, c->n_bs, digits);
+        if (orc_env_step(e, digits, NULL, NULL, NULL, &o)) { rc = s + 1; break; }
+        n_out[s] = o.n_out; n_ho[s] = o.n_ho; reward[s] = o.reward;
+        const orc_chan *ch = orc_env_chan(e);
+        int64_t h = 0;
+        for (int u = 0; u < c->n_ue; u++) h += (int64_t)(u + 1) * (ch->cur[u] + 1);
+        serving_hash[s] = h;
+    }
+    orc_env_destroy(e);
+    return rc;
+}
+
+/* A (T, nUE, 2) int32 cell trace from the oracle's own reference_point_group port (Philox draws of env `env_id`,
+ * 200 warm-up ticks like mobile_env.py:77-79) -- how the README says ue_trace_10k.npy was made (README.md:31-32). */
+void orc_make_trace(const orc_cfg *c, uint64_t seed, uint32_t env_id, int64_t T, int32_t *trace_out) {
+    int32_t gs[64];
+    for (int g = 0; g < c->n_groups; g++) gs[g] = c->n_ue / c->n_groups + (g < c->n_ue % c->n_groups ? 1 : 0);
+    orc_mob *m = orc_mob_create(c, gs);
+    double *xy = (double *)malloc(sizeof(double) * 2 * c->n_ue);
+    orc_mob_init_philox(m, seed, env_id);
+    uint32_t tick = 0;
+    for (int i = 0; i < 200; i++) orc_mob_tick_philox(m, seed, env_id, tick++, NULL);
+    for (int64_t t = 0; t < T; t++) {
+        orc_mob_tick_philox(m, seed, env_id, tick++, xy);
+        for (int u = 0; u < c->n_ue; u++) {
+            int x = (int)xy[2 * u], y = (int)xy[2 * u + 1];
+            if (x >= c->grid_n) x = c->grid_n - 1;
+            if (y >= c->grid_n) y = c->grid_n - 1;
+            trace_out[(t * c->n_ue + u) * 2] = x;
+            trace_out[(t * c->n_ue + u) * 2 + 1] = y;
+        }
+    }
+    free(xy);
+    orc_mob_destroy(m);
+}

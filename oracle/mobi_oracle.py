@@ -137,6 +137,11 @@ def lib():
     L.orc_bench_run.argtypes = [P(OrcCfg), P(C.c_int32), P(C.c_int32), C.c_int, C.c_int, C.c_uint64, C.c_uint32,
                                 P(C.c_double)]
     L.orc_bench_run.restype = C.c_double
+    L.orc_replay_run.argtypes = [P(OrcCfg), P(C.c_int32), C.c_int64, C.c_uint64, C.c_uint32, P(C.c_int64), C.c_int,
+                                 P(C.c_int32), P(C.c_int32), P(C.c_double), P(C.c_int64)]
+    L.orc_replay_run.restype = C.c_int
+    L.orc_make_trace.argtypes = [P(OrcCfg), C.c_uint64, C.c_uint32, C.c_int64, P(C.c_int32)]
+    L.orc_make_trace.restype = None
     _lib = L
     return L
 
@@ -358,3 +363,24 @@ def bench_run(cfg: OrcCfg, n_envs: int, n_steps: int, seed: int = 0, env_id0: in
     chk = C.c_double()
     t = lib().orc_bench_run(C.byref(cfg), _ip32(gs), _ip32(ibs), n_envs, n_steps, seed, env_id0, C.byref(chk))
     return t, chk.value
+
+
+def make_trace(cfg: OrcCfg, seed: int, env_id: int, T: int):
+    """(T, nUE, 2) int32 cells from the oracle's reference_point_group port (how ue_trace_10k.npy was made, README.md:31-32)."""
+    out = np.empty((T, cfg.n_ue, 2), dtype=np.int32)
+    lib().orc_make_trace(C.byref(cfg), seed, env_id, T, _ip32(out))
+    return out
+
+
+def replay_run(cfg: OrcCfg, trace, seed: int, env_id: int, actions):
+    """One read_trace env, len(actions) step_test calls with Philox fading: (n_out, n_ho, reward, serving_hash) per step."""
+    tr = np.ascontiguousarray(trace, dtype=np.int32)
+    act = np.ascontiguousarray(actions, dtype=np.int64)
+    n = len(act)
+    n_out, n_ho = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+    rew, hsh = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int64)
+    rc = lib().orc_replay_run(C.byref(cfg), _ip32(tr), tr.shape[0], seed, env_id, _ip64(act), n, _ip32(n_out), _ip32(n_ho),
+                              _dp(rew), _ip64(hsh))
+    if rc:
+        raise IndexError("trace exhausted at step %d" % (rc - 1))
+    return n_out, n_ho, rew, hsh

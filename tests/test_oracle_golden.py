@@ -180,3 +180,20 @@ def test_dense_channel_golden(orc, golden_dir):
             assert abs(ms.value - g["mean_sinr"][t]) < 1e-11
     finally:
         L.orc_chan_destroy(ch)
+
+
+def test_replay_run_matches_env_stepping(orc):
+    """The config-5 sweep helper (orc_replay_run: one C call per env) == stepping the oracle env from Python."""
+    cfg = orc.default_cfg()
+    tr = orc.make_trace(cfg, 7, 0, 120)
+    assert tr.shape == (120, 40, 2) and tr.min() >= 0 and tr.max() <= 99
+    acts = np.random.RandomState(0).randint(0, 625, size=119)
+    n_out, n_ho, rew, hsh = orc.replay_run(cfg, tr, 7, 3, acts)
+    o = orc.OracleEnv(cfg, mobility=orc.MOB_TRACE, seed=7, env_id=3, trace=tr, warmup_ticks=0)
+    o.reset()
+    for t in range(119):
+        s, r, d, info = o.step(int(acts[t]), want_state=False)
+        assert (info["n_out"], info["n_ho"], r) == (n_out[t], n_ho[t], rew[t]), t
+        assert int(((np.arange(40) + 1) * (o.current_BS + 1)).sum()) == hsh[t], t
+    with pytest.raises(IndexError):
+        orc.replay_run(cfg, tr, 7, 3, np.zeros(121, dtype=np.int64))
