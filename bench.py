@@ -250,20 +250,22 @@ def main():
         h2d, d2h = E * N_BS, E * 9
     else:
         act_host = torch.randint(0, env.action_space_dim, (8, E), dtype=torch.int64).pin_memory()
+        act_rows = [act_host[i] for i in range(8)]
 
         def e2e_step(i):
-            env.step_host(act_host[i % 8], rew_host, done_host)
+            env.step_host(act_rows[i % 8], rew_host, done_host)
         h2d, d2h = E * 8, E * 9
     for i in range(3):
         e2e_step(i)
     barrier()
+    rew_np, done_np = rew_host.numpy(), done_host.numpy()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     acc = 0.0
     for i in range(n_e2e):
         e2e_step(i)
-        acc += float(rew_host[0])               # the host consumes the step's result
-        if bool(done_host[0]):
+        acc += rew_np[0]                        # the host consumes the step's result
+        if done_np[0]:
             env.reset()
     e1.record()
     barrier()

@@ -401,13 +401,20 @@ int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, dou
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t E = (size_t)h->d.E;
-    /* Actions go to HBM with one async copy (the kernel's prologue must not wait on PCIe).  Results are written by
-     * the kernel straight into the caller's buffers when those are pinned (mapped) host memory -- posted PCIe
-     * writes, no device-to-host copies on the stream -- and through device staging + copies otherwise. */
-    CU(h, cudaMemcpyAsync(h->h_action, action_host, E * 8, cudaMemcpyHostToDevice, st));
+    /* Pinned (mapped) host buffers are used in place: the BS warp of every CTA reads its env's action over PCIe
+     * (the observation stream does not wait for it) and the kernel writes the results straight into the caller's
+     * buffers with posted PCIe writes -- one launch and one synchronise per step, no copies on the stream.
+     * Pageable buffers go through device staging and cudaMemcpyAsync.  UAVENV_HOST_ACTION_COPY=1 forces the staged
+     * copy for the actions (tuning). */
+    static const bool force_copy = getenv("UAVENV_HOST_ACTION_COPY") != nullptr;
+    const void *act = force_copy ? nullptr : pinned_alias(action_host);
+    if (!act) {
+        CU(h, cudaMemcpyAsync(h->h_action, action_host, E * 8, cudaMemcpyHostToDevice, st));
+        act = h->h_action;
+    }
     uavenv_in in;
     memset(&in, 0, sizeof(in));
-    in.action = (const int64_t *)h->h_action;
+    in.action = (const int64_t *)act;
     void *rw = pinned_alias(reward_host), *dn = pinned_alias(done_host), *ms = pinned_alias(mean_sinr_host),
          *no = pinned_alias(n_out_host);
     uavenv_out out;

@@ -123,6 +123,7 @@ class BatchedMobiEnvironment:
                           fading_used=_ptr(self.fading_used), ue_xy=_ptr(self.ue_xy), bs_xy=_ptr(self.bs_xy),
                           bs_digits=_ptr(self.bs_digits))
         self._keep = []          # tensors that must outlive the asynchronous call that reads them
+        self._host_args = {}     # step_host: cached ctypes pointers per host-buffer set
         self._ctor_done = mobility_model == "group" and fading != "injected"
         if mobility_model == "read_trace":
             if trace is None:
@@ -235,8 +236,15 @@ class BatchedMobiEnvironment:
         for t in (action_host, reward_host, done_host, mean_sinr_host, n_out_host):
             if t is not None and (t.is_cuda or not t.is_contiguous() or t.numel() != self.n_envs):
                 raise ValueError("step_host takes contiguous host tensors of n_envs elements")
-        rc = self._lib.uavenv_step_host(self._h, _ptr(action_host), _ptr(self.obs), _ptr(reward_host), _ptr(done_host),
-                                        _ptr(mean_sinr_host), _ptr(n_out_host), self._stream())
+        key = tuple(0 if t is None else t.data_ptr() for t in (action_host, reward_host, done_host, mean_sinr_host,
+                                                               n_out_host))
+        args = self._host_args.get(key)
+        if args is None:                      # ctypes argument objects are cached per buffer set (hot loop)
+            if len(self._host_args) > 64:
+                self._host_args.clear()
+            args = self._host_args[key] = (_ptr(action_host), _ptr(self.obs), _ptr(reward_host), _ptr(done_host),
+                                           _ptr(mean_sinr_host), _ptr(n_out_host))
+        rc = self._lib.uavenv_step_host(self._h, *args, self._stream())
         if rc:
             self._raise(rc, "step_host")
         return self.obs
