@@ -48,7 +48,8 @@ class Out(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("reward", C.c_void_p), ("mean_sinr", C.c_void_p), ("n_out", C.c_void_p),
                 ("n_ho", C.c_void_p), ("n_blocked", C.c_void_p), ("done", C.c_void_p), ("step_n", C.c_void_p),
                 ("serving", C.c_void_p), ("serving_sinr", C.c_void_p), ("sinr_all", C.c_void_p),
-                ("fading_used", C.c_void_p), ("ue_xy", C.c_void_p), ("bs_xy", C.c_void_p), ("bs_digits", C.c_void_p)]
+                ("fading_used", C.c_void_p), ("ue_xy", C.c_void_p), ("bs_xy", C.c_void_p), ("bs_digits", C.c_void_p),
+                ("obs_idx", C.c_void_p)]
 
 
 # every symbol include/uavenv.h declares
@@ -56,6 +57,7 @@ SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
+    "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop",
     "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
 ]
 
@@ -96,6 +98,9 @@ def lib():
     L.uavenv_launch_plan.argtypes = [vp, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32)]
     L.uavenv_diag_fill_ring.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.uavenv_diag_fill_env.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+    L.uavnet_sparse_fwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp]
+    L.uavnet_sparse_bwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp]
+    L.uavnet_rmsprop.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, vp]
     L.uavenv_diag_fill.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp]
     _lib = L
     return L

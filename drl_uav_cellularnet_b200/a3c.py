@@ -1,0 +1,258 @@
+"""The actor-critic learner on top of the batched env step path -- host-side mirror of the
+reference's ``ACNet`` / ``Worker`` (main.py:43-271) for ``netType='MLP'``.
+
+What changes against the reference
+  * The first layer never sees the dense 50 000-wide observation: the env kernel emits the ~44 non-zero cells as flat
+    indices (``obs_idx``) and ``uavnet_sparse_fwd`` / ``uavnet_sparse_bwd`` (include/uavnet.h) do the gather-sum and
+    the scatter-add.  Actor and critic first layers are stored side by side in one ``[N_S, 2*200]`` matrix so that one
+    gather feeds both.  The 200x200 / 200x625 / 200x1 layers are plain library GEMMs (torch.matmul).
+  * Four asynchronous worker threads pushing gradients into a shared net (Hogwild, main.py:85-86,159-163) become one
+    synchronous batch: every rank rolls its E envs UPDATE_GLOBAL_ITER steps, the loss is the mean over all samples
+    (like the reference's own synchronous variant, a2c_single_thread.py:153-186), gradients are summed over ranks with
+    one NCCL all-reduce of the flat buffer and both RMSProp optimisers (same hyper-parameters) run as one fused pass.
+  * Backward is written out by hand (formulas of main.py:64-78); tests/test_gpu_a3c.py checks it against
+    torch.autograd on the dense restatement of the same graph.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _native as N
+
+# the reference's hyper-parameters (main.py:19-27)
+UPDATE_GLOBAL_ITER = 10
+GAMMA = 0.9
+ENTROPY_BETA = 0.001
+LR_A = 0.0001
+LR_C = 0.0001
+TENSOR_SEED = 6
+HIDDEN = 200
+# tf.train.RMSPropOptimizer defaults (TF 1.x): decay, momentum (0), epsilon; the `rms` slot starts at ones
+RMS_DECAY, RMS_EPS = 0.9, 1e-10
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _relu6(x):
+    return torch.clamp(x, 0.0, 6.0)
+
+
+class ACNet:
+    """Actor 50000->200->200->N_A softmax and critic 50000->200->200->1 (main.py:143-156) on sparse observations.
+
+    All parameters live in ONE flat float32 buffer (``self.flat``; gradient ``self.grad`` and RMSProp slot ``self.ms``
+    have the same layout), segments 16-byte aligned:
+        W1 [N_S, 2H] (cols :H = actor 'la', H: = critic 'lc') | b1 [2H] | Wa2 [H,H] | ba2 [H] | Wa3 [H,N_A] | ba3 [N_A]
+        | Wc2 [H,H] | bc2 [H] | Wc3 [H,1] | bc3 [1]
+    """
+
+    def __init__(self, n_s: int, n_a: int, device, hidden: int = HIDDEN, seed: int = TENSOR_SEED):
+        self.n_s, self.n_a, self.h = int(n_s), int(n_a), int(hidden)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ACNet needs a CUDA device (sm_100a); there is no CPU fallback")
+        self._lib = N.lib()
+        H = self.h
+        shapes = [("W1", (n_s, 2 * H)), ("b1", (2 * H,)), ("Wa2", (H, H)), ("ba2", (H,)), ("Wa3", (H, n_a)), ("ba3", (n_a,)),
+                  ("Wc2", (H, H)), ("bc2", (H,)), ("Wc3", (H, 1)), ("bc3", (1,))]
+        self.segments, off = {}, 0
+        for name, shp in shapes:
+            n = int(np.prod(shp))
+            self.segments[name] = (off, n, shp)
+            off += (n + 3) // 4 * 4
+        self.n_flat = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros_like(self.flat)
+        self.ms = torch.ones_like(self.flat)                # TF1 RMSProp: rms slot initialised to ones
+        self.p = {k: self.flat[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        self.g = {k: self.grad[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        # tf.random_normal_initializer(0., .1, seed) kernels, zero biases (main.py:145-153).  The TF stream itself is
+        # not reproducible here (TensorFlow absent); the distribution is.
+        gen = torch.Generator(device="cpu").manual_seed(int(seed))
+        for k in ("W1", "Wa2", "Wa3", "Wc2", "Wc3"):
+            self.p[k].copy_(torch.randn(self.segments[k][2], generator=gen) * 0.1)
+        self.n_params = sum(n for _, n, _ in self.segments.values())
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def first_layer(self, idx: torch.Tensor) -> torch.Tensor:
+        """relu6(s @ [la | lc] + b) for count vectors given as flat indices idx int32 [M, K] -> [M, 2H]."""
+        assert idx.dtype == torch.int32 and idx.is_cuda and idx.is_contiguous() and idx.dim() == 2
+        M, K = idx.shape
+        out = torch.empty((M, 2 * self.h), dtype=torch.float32, device=self.device)
+        rc = self._lib.uavnet_sparse_fwd(_ptr(idx), M, K, self.n_s, _ptr(self.p["W1"]), _ptr(self.p["b1"]), 2 * self.h,
+                                         _ptr(out), 1, self._stream())
+        if rc:
+            raise RuntimeError("uavnet_sparse_fwd failed (%d)" % rc)
+        return out
+
+    def forward(self, idx: torch.Tensor, want: str = "both"):
+        """-> (a_prob [M, N_A] or None, v [M] or None, cache)"""
+        H, p = self.h, self.p
+        h1 = self.first_layer(idx)
+        cache = {"idx": idx, "h1": h1}
+        prob = v = None
+        if want in ("both", "actor"):
+            h2a = _relu6(torch.addmm(p["ba2"], h1[:, :H], p["Wa2"]))
+            prob = torch.softmax(torch.addmm(p["ba3"], h2a, p["Wa3"]), dim=1)
+            cache.update(h2a=h2a, prob=prob)
+        if want in ("both", "critic"):
+            h2c = _relu6(torch.addmm(p["bc2"], h1[:, H:], p["Wc2"]))
+            v = torch.addmm(p["bc3"], h2c, p["Wc3"]).squeeze(1)
+            cache.update(h2c=h2c, v=v)
+        return prob, v, cache
+
+    def choose_action(self, idx: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """np.random.choice(N_A, p=a_prob) per env (main.py:165-169) -> int64 [M]"""
+        prob, _, _ = self.forward(idx, "actor")
+        return torch.multinomial(prob, 1, generator=generator).squeeze(1)
+
+    def greedy_action(self, idx: torch.Tensor) -> torch.Tensor:
+        """tf.argmax(a_prob, 1) of the evaluation driver (main_test.py:68)"""
+        prob, _, _ = self.forward(idx, "actor")
+        return prob.argmax(dim=1)
+
+    def value(self, idx: torch.Tensor) -> torch.Tensor:
+        return self.forward(idx, "critic")[1]
+
+    # ---- losses + gradients (main.py:64-78), accumulated into self.grad -------------------------------------
+    def accumulate_grads(self, idx: torch.Tensor, a_his: torch.Tensor, v_target: torch.Tensor):
+        """Adds d(a_loss)/d(actor params) and d(c_loss)/d(critic params) for the batch to ``self.grad``;
+        returns (a_loss, c_loss) as 0-d tensors.  a_loss = mean(-(log(pi(a)+1e-5) * sg(td) + beta * H)),
+        c_loss = mean(td^2), td = v_target - v."""
+        H, p, g = self.h, self.p, self.g
+        M = idx.shape[0]
+        prob, v, c = self.forward(idx, "both")
+        h1, h2a, h2c = c["h1"], c["h2a"], c["h2c"]
+        td = v_target - v
+        # -- critic --
+        c_loss = (td * td).mean()
+        dv = (-2.0 / M) * td                                              # [M]
+        g["Wc3"].addmm_(h2c.t(), dv.unsqueeze(1))
+        g["bc3"].add_(dv.sum())
+        dpre2c = (dv.unsqueeze(1) * p["Wc3"].t()) * ((h2c > 0) & (h2c < 6))
+        g["Wc2"].addmm_(h1[:, H:].t(), dpre2c)
+        g["bc2"].add_(dpre2c.sum(0))
+        dpre1 = torch.empty_like(h1)
+        dpre1[:, H:].copy_(dpre2c @ p["Wc2"].t())
+        # -- actor --
+        lp = torch.log(prob + 1e-5)
+        p_a = prob.gather(1, a_his.unsqueeze(1)).squeeze(1)
+        entropy = -(prob * lp).sum(1)
+        a_loss = -(torch.log(p_a + 1e-5) * td + ENTROPY_BETA * entropy).mean()
+        gp = (ENTROPY_BETA / M) * (lp + prob / (prob + 1e-5))             # dL/dp, entropy part
+        gp.scatter_add_(1, a_his.unsqueeze(1), ((-1.0 / M) * td / (p_a + 1e-5)).unsqueeze(1))
+        dz = prob * (gp - (prob * gp).sum(1, keepdim=True))               # through the softmax
+        g["Wa3"].addmm_(h2a.t(), dz)
+        g["ba3"].add_(dz.sum(0))
+        dpre2a = (dz @ p["Wa3"].t()) * ((h2a > 0) & (h2a < 6))
+        g["Wa2"].addmm_(h1[:, :H].t(), dpre2a)
+        g["ba2"].add_(dpre2a.sum(0))
+        dpre1[:, :H].copy_(dpre2a @ p["Wa2"].t())
+        dpre1.mul_((h1 > 0) & (h1 < 6))
+        g["b1"].add_(dpre1.sum(0))
+        rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
+                                         self._stream())
+        if rc:
+            raise RuntimeError("uavnet_sparse_bwd failed (%d)" % rc)
+        return a_loss, c_loss
+
+    # ---- the "push" (main.py:85-86,159-160): all-reduce + both RMSProp optimisers in one pass ---------------
+    def apply_grads(self, lr: float = LR_A, world_size: int = 1):
+        """grad /= world_size (after the caller's all-reduce), RMSProp step on every parameter, grad = 0."""
+        rc = self._lib.uavnet_rmsprop(_ptr(self.flat), _ptr(self.grad), _ptr(self.ms), self.n_flat, lr, RMS_DECAY, RMS_EPS,
+                                      1.0 / world_size, 1, self._stream())
+        if rc:
+            raise RuntimeError("uavnet_rmsprop failed (%d)" % rc)
+
+    # ---- on-disk format of the reference (main.py:264-269,314; main_test.py:15-25) ---------------------------
+    def actor_params(self):
+        """[la/kernel, la/bias, la2/kernel, la2/bias, ap/kernel, ap/bias] as host arrays (GLOBAL_AC.a_params order)"""
+        H, p = self.h, self.p
+        return [p["W1"][:, :H].cpu().numpy().copy(), p["b1"][:H].cpu().numpy().copy(), p["Wa2"].cpu().numpy().copy(),
+                p["ba2"].cpu().numpy().copy(), p["Wa3"].cpu().numpy().copy(), p["ba3"].cpu().numpy().copy()]
+
+    def save_actor_npz(self, path: str):
+        """np.savez(path, SESS.run(GLOBAL_AC.a_params)) (main.py:269): one ragged object array under 'arr_0'"""
+        arr = np.empty(6, dtype=object)
+        for i, a in enumerate(self.actor_params()):
+            arr[i] = a
+        np.savez(path, arr)
+
+    def load_actor_npz(self, path: str):
+        """main_test.py:15-25: assign arr_0[0..5] to la/kernel, la/bias, la2/kernel, la2/bias, ap/kernel, ap/bias"""
+        a = np.load(path, allow_pickle=True)["arr_0"]
+        H, p = self.h, self.p
+        p["W1"][:, :H].copy_(torch.from_numpy(np.asarray(a[0], dtype=np.float32)))
+        p["b1"][:H].copy_(torch.from_numpy(np.asarray(a[1], dtype=np.float32)))
+        for k, i in (("Wa2", 2), ("ba2", 3), ("Wa3", 4), ("ba3", 5)):
+            p[k].copy_(torch.from_numpy(np.asarray(a[i], dtype=np.float32)))
+
+
+def n_step_targets(rewards: torch.Tensor, dones: torch.Tensor, v_boot: torch.Tensor, gamma: float = GAMMA) -> torch.Tensor:
+    """Discounted n-step value targets of main.py:217-227, batched over envs: walking the buffer backwards,
+    v = r + gamma * v, starting from the bootstrap value of the state after the last step -- 0 where the episode ended
+    (`if done: v_s_ = 0`), and never carried across an episode end.  rewards/dones [T, E], v_boot [E] -> [T, E]."""
+    T = rewards.shape[0]
+    out = torch.empty_like(rewards)
+    v = v_boot
+    for t in range(T - 1, -1, -1):
+        v = rewards[t] + gamma * torch.where(dones[t], torch.zeros_like(v), v)
+        out[t] = v
+    return out
+
+
+class A3CTrainer:
+    """Synchronous batched restatement of Worker.work (main.py:182-271) for one rank: E envs, rollouts of
+    UPDATE_GLOBAL_ITER steps, one update per rollout.  With torch.distributed initialised the gradient buffer is
+    all-reduced (NCCL over NVLink) before the optimiser pass -- the reference's push/pull (main.py:159-163)."""
+
+    def __init__(self, env, net: ACNet, rollout: int = UPDATE_GLOBAL_ITER, seed: int = 0):
+        self.env, self.net, self.T = env, net, int(rollout)
+        self.E, self.K = env.n_envs, env.nUE + env.nBS
+        dev = env.device
+        self.gen = torch.Generator(device=dev).manual_seed(int(seed))
+        self.buf_idx = torch.empty((self.T, self.E, self.K), dtype=torch.int32, device=dev)
+        self.buf_a = torch.empty((self.T, self.E), dtype=torch.int64, device=dev)
+        self.buf_r = torch.empty((self.T, self.E), dtype=torch.float32, device=dev)
+        self.buf_done = torch.empty((self.T, self.E), dtype=torch.bool, device=dev)
+        self.ep_return = torch.zeros(self.E, dtype=torch.float64, device=dev)
+        self.env.reset()
+        self.updates = 0
+
+    def rollout(self):
+        env, net = self.env, self.net
+        for t in range(self.T):
+            self.buf_idx[t].copy_(env.obs_idx)
+            a = net.choose_action(self.buf_idx[t], self.gen)                 # main.py:195
+            _, r, done, _ = env.step(a)                                      # main.py:198
+            self.buf_a[t].copy_(a)
+            self.buf_r[t].copy_(r)
+            self.buf_done[t].copy_(done)
+            self.ep_return += r
+            env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)
+        v_boot = net.value(env.obs_idx.clone())                              # main.py:217-220
+        return n_step_targets(self.buf_r, self.buf_done, v_boot)
+
+    def update(self, v_target: torch.Tensor):
+        net, M = self.net, self.T * self.E
+        a_loss, c_loss = net.accumulate_grads(self.buf_idx.view(M, self.K), self.buf_a.view(M), v_target.reshape(M))
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size()
+            if world > 1:
+                torch.distributed.all_reduce(net.grad)                       # the gradient push, summed over ranks
+        net.apply_grads(LR_A, world)
+        self.updates += 1
+        return a_loss, c_loss
+
+    def train_iteration(self):
+        return self.update(self.rollout())

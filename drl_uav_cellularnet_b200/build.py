@@ -15,8 +15,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libuavenv.so")
-SOURCES = ["uavenv.cu"]
-HEADERS = ["env_kernels.cuh", "philox.cuh", os.path.join(ROOT, "include", "uavenv.h")]
+SOURCES = ["uavenv.cu", "uavnet.cu"]
+HEADERS = ["env_kernels.cuh", "philox.cuh", os.path.join(ROOT, "include", "uavenv.h"), os.path.join(ROOT, "include", "uavnet.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

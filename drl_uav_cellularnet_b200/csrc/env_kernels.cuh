@@ -95,6 +95,7 @@ struct CallArgs {
     float *fading_used;          // [E,nUE,nBS]
     int16_t *ue_xy, *bs_xy_out;  // [E,nUE,2], [E,nBS,2]
     uint8_t *bs_digits;          // [E,nBS]
+    int32_t *obs_idx;            // [E,nUE+nBS] flat indices of the observation's non-zero cells
     int tile_bytes;              // bytes of the zeroed shared-memory tile the TMA warp streams from (0: no TMA path)
     int cells_off;               // byte offset of the UE-cell staging area in dynamic shared memory (-1: use HBM)
 };
@@ -709,6 +710,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 if (mode != MODE_CTOR) reinterpret_cast<short2 *>(c.bs_xy)[(size_t)e * nBS + lane] = nb;
                 if (a.bs_xy_out) reinterpret_cast<short2 *>(a.bs_xy_out)[(size_t)e * nBS + lane] = nb;
                 if (a.bs_digits && mode == MODE_STEP) a.bs_digits[(size_t)e * nBS + lane] = (uint8_t)digit;
+                if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + nUE + lane] = bx * G + by;
                 if (incremental && (ox != bx || oy != by)) {
                     atomicAdd(obs_env + (size_t)ox * G + oy, -1.f);
                     atomicAdd(obs_env + (size_t)bx * G + by, 1.f);
@@ -777,6 +779,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 const int srv = word & 31;
                 if (a.serving) a.serving[i] = (uint8_t)srv;
                 if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = curS;
+                if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
                 if (incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
             }
         }
@@ -807,6 +810,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         if (a.serving) a.serving[i] = (uint8_t)srv;
         if (a.serving_sinr) reinterpret_cast<T *>(a.serving_sinr)[i] = curS;
         if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
+        if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
         if (incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
     }
     }

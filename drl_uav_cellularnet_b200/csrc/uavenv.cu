@@ -142,6 +142,7 @@ int run_env(uavenv_t *h, int mode, const uavenv_in *in, const uavenv_out *out, v
         a.n_ho = out->n_ho; a.n_blocked = out->n_blocked; a.done = out->done; a.step_n = out->step_n;
         a.serving = out->serving; a.serving_sinr = out->serving_sinr; a.sinr_all = out->sinr_all;
         a.fading_used = out->fading_used; a.ue_xy = out->ue_xy; a.bs_xy_out = out->bs_xy; a.bs_digits = out->bs_digits;
+        a.obs_idx = out->obs_idx;
     }
     if (mode == MODE_STEP && !a.action && !a.digits) return fail(h, UAVENV_EACTION, "step needs in->action or in->digits%s");
     if (h->cfg.fading == UAVENV_FADE_INJECTED && !a.fading)

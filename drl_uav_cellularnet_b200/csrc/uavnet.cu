@@ -1,0 +1,133 @@
+// C-ABI of the actor-critic MLP's sparse first layer and optimiser step (include/uavnet.h), sm_100a.
+//
+// Reference semantics restated (file:line into the reference repo):
+//   main.py:147,151   tf.layers.dense(self.s, 200, tf.nn.relu6)  on a count vector with ~44 non-zeros of 50 000
+//                     -> sparse_fwd_kernel (gather-sum of weight rows) / sparse_bwd_kernel (scatter-add of the gradient)
+//   main.py:300-301   tf.train.RMSPropOptimizer(1e-4)            -> rmsprop_kernel (TF1 defaults: decay .9, eps 1e-10)
+#include "../../include/uavnet.h"
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uavk {
+
+constexpr int NET_THREADS = 256;
+
+// One thread per (sample m, float4 column c4): consecutive threads read consecutive 16-byte pieces of the same weight
+// row (coalesced, rows come from L2 -- the 80 MB first-layer matrix is L2-resident on B200), the row indices are
+// warp-broadcast loads.  K is unrolled by 8 so that 8 independent row reads are in flight per thread.
+__global__ void __launch_bounds__(NET_THREADS) sparse_fwd_kernel(const int32_t *__restrict__ idx, long long M, int K,
+                                                                 const float4 *__restrict__ W4, const float4 *__restrict__ b4,
+                                                                 int H4, float4 *__restrict__ out4, int relu6) {
+    const long long total = M * H4;
+    for (long long w = (long long)blockIdx.x * NET_THREADS + threadIdx.x; w < total; w += (long long)gridDim.x * NET_THREADS) {
+        const long long m = w / H4;
+        const int c4 = (int)(w - m * H4);
+        const int32_t *row = idx + m * K;
+        float4 acc = b4 ? __ldg(b4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = 0;
+        for (; k + 8 <= K; k += 8) {
+            int r[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) r[j] = __ldg(row + k + j);
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = __ldg(W4 + (size_t)r[j] * H4 + c4);
+#pragma unroll
+            for (int j = 0; j < 8; j++) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+        }
+        for (; k < K; k++) {
+            const float4 v = __ldg(W4 + (size_t)__ldg(row + k) * H4 + c4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        if (relu6) {
+            acc.x = fminf(fmaxf(acc.x, 0.f), 6.f); acc.y = fminf(fmaxf(acc.y, 0.f), 6.f);
+            acc.z = fminf(fmaxf(acc.z, 0.f), 6.f); acc.w = fminf(fmaxf(acc.w, 0.f), 6.f);
+        }
+        out4[w] = acc;
+    }
+}
+
+// dW[idx[m,k], :] += dpre[m, :] with 16-byte vector REDs (red.global.add.v4.f32).  Pieces whose four gradients are all
+// zero (units outside relu6's linear range) are skipped.
+__global__ void __launch_bounds__(NET_THREADS) sparse_bwd_kernel(const int32_t *__restrict__ idx, long long M, int K,
+                                                                 const float4 *__restrict__ dpre4, int H4, float4 *dW4) {
+    const long long total = M * H4;
+    for (long long w = (long long)blockIdx.x * NET_THREADS + threadIdx.x; w < total; w += (long long)gridDim.x * NET_THREADS) {
+        const long long m = w / H4;
+        const int c4 = (int)(w - m * H4);
+        const float4 g = __ldg(dpre4 + w);
+        if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+        const int32_t *row = idx + m * K;
+        for (int k = 0; k < K; k++) atomicAdd(dW4 + (size_t)__ldg(row + k) * H4 + c4, g);
+    }
+}
+
+__global__ void __launch_bounds__(NET_THREADS) rmsprop_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ ms,
+                                                              long long n, float lr, float decay, float eps, float gs, int zero_grad) {
+    const long long n4 = n >> 2;
+    float4 *p4 = reinterpret_cast<float4 *>(p), *g4 = reinterpret_cast<float4 *>(g), *m4 = reinterpret_cast<float4 *>(ms);
+    const float od = 1.f - decay;
+    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * NET_THREADS) {
+        float4 gv = g4[i], mv = m4[i], pv = p4[i];
+        gv.x *= gs; gv.y *= gs; gv.z *= gs; gv.w *= gs;
+        mv.x = decay * mv.x + od * gv.x * gv.x; mv.y = decay * mv.y + od * gv.y * gv.y;
+        mv.z = decay * mv.z + od * gv.z * gv.z; mv.w = decay * mv.w + od * gv.w * gv.w;
+        pv.x -= lr * gv.x / sqrtf(mv.x + eps); pv.y -= lr * gv.y / sqrtf(mv.y + eps);
+        pv.z -= lr * gv.z / sqrtf(mv.z + eps); pv.w -= lr * gv.w / sqrtf(mv.w + eps);
+        m4[i] = mv; p4[i] = pv;
+        if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail (n not a multiple of 4)
+    const long long t = (n4 << 2) + (long long)blockIdx.x * NET_THREADS + threadIdx.x;
+    if (t < n) {
+        const float gv = g[t] * gs;
+        const float mv = decay * ms[t] + od * gv * gv;
+        ms[t] = mv;
+        p[t] -= lr * gv / sqrtf(mv + eps);
+        if (zero_grad) g[t] = 0.f;
+    }
+}
+
+int grid_for(long long items) {
+    long long g = (items + NET_THREADS - 1) / NET_THREADS;
+    const long long cap = 148LL * 8 * 4;          // a few waves of 8 CTAs per SM; the kernels are grid-stride
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace uavk
+using namespace uavk;
+
+extern "C" {
+
+int uavnet_sparse_fwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *W, const float *b, int32_t H,
+                      float *out, int32_t relu6, void *stream) {
+    if (!idx || !W || !out || M < 1 || K < 1 || n_rows < 1 || H < 4 || (H & 3) || !aligned16(W) || !aligned16(out) ||
+        (b && !aligned16(b)))
+        return UAVNET_EINVAL;
+    sparse_fwd_kernel<<<grid_for(M * (H / 4)), NET_THREADS, 0, (cudaStream_t)stream>>>(
+        idx, M, K, (const float4 *)W, (const float4 *)b, H / 4, (float4 *)out, relu6);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
+                      void *stream) {
+    if (!idx || !dpre || !dW || M < 1 || K < 1 || n_rows < 1 || H < 4 || (H & 3) || !aligned16(dpre) || !aligned16(dW))
+        return UAVNET_EINVAL;
+    sparse_bwd_kernel<<<grid_for(M * (H / 4)), NET_THREADS, 0, (cudaStream_t)stream>>>(idx, M, K, (const float4 *)dpre,
+                                                                                    H / 4, (float4 *)dW);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_rmsprop(float *param, float *grad, float *ms, int64_t n, float lr, float decay, float eps, float grad_scale,
+                   int32_t zero_grad, void *stream) {
+    if (!param || !grad || !ms || n < 1 || !aligned16(param) || !aligned16(grad) || !aligned16(ms)) return UAVNET_EINVAL;
+    rmsprop_kernel<<<grid_for((n + 3) / 4), NET_THREADS, 0, (cudaStream_t)stream>>>(param, grad, ms, n, lr, decay, eps,
+                                                                                   grad_scale, zero_grad);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+}  // extern "C"

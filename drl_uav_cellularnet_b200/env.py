@@ -114,6 +114,7 @@ class BatchedMobiEnvironment:
         self.serving, self.serving_sinr = z((E, nUE), torch.uint8), z((E, nUE), ft)
         self.ue_xy, self.bs_xy = z((E, nUE, 2), torch.int16), z((E, nBS, 2), torch.int16)
         self.bs_digits = z((E, nBS), torch.uint8)
+        self.obs_idx = z((E, nUE + nBS), torch.int32)       # sparse form of the observation (valid after reset())
         self.sinr_all = z((E, nUE, nBS), ft) if diagnostics else None
         self.fading_used = z((E, nUE, nBS), torch.float32) if diagnostics else None
         self._out = N.Out(obs=_ptr(self.obs), reward=_ptr(self.reward), mean_sinr=_ptr(self.mean_sinr),
@@ -121,7 +122,7 @@ class BatchedMobiEnvironment:
                           done=_ptr(self.done_u8), step_n=_ptr(self.step_n), serving=_ptr(self.serving),
                           serving_sinr=_ptr(self.serving_sinr), sinr_all=_ptr(self.sinr_all),
                           fading_used=_ptr(self.fading_used), ue_xy=_ptr(self.ue_xy), bs_xy=_ptr(self.bs_xy),
-                          bs_digits=_ptr(self.bs_digits))
+                          bs_digits=_ptr(self.bs_digits), obs_idx=_ptr(self.obs_idx))
         self._keep = []          # tensors that must outlive the asynchronous call that reads them
         self._host_args = {}     # step_host: cached ctypes pointers per host-buffer set
         self._ctor_done = mobility_model == "group" and fading != "injected"
@@ -224,7 +225,7 @@ class BatchedMobiEnvironment:
             self._raise(rc, "step")
         info = {"mean_sinr": self.mean_sinr, "n_out": self.n_out, "n_ho": self.n_ho, "n_blocked": self.n_blocked,
                 "step_n": self.step_n, "serving": self.serving, "serving_sinr": self.serving_sinr,
-                "ue_xy": self.ue_xy, "bs_xy": self.bs_xy, "bs_digits": self.bs_digits}
+                "ue_xy": self.ue_xy, "bs_xy": self.bs_xy, "bs_digits": self.bs_digits, "obs_idx": self.obs_idx}
         return self.obs, self.reward, self.done_u8.view(torch.bool), info
 
     step_test = step

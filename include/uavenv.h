@@ -101,6 +101,9 @@ typedef struct uavenv_out {
     int16_t *ue_xy;              /* [E,nUE,2] UE cells                             (mobile_env.py:155) */
     int16_t *bs_xy;              /* [E,nBS,2] BS cells after the move              (mobile_env.py:157) */
     uint8_t *bs_digits;          /* [E,nBS] decoded per-BS actions (act_all)       (mobile_env.py:209) */
+    int32_t *obs_idx;            /* [E,nUE+nBS] the observation in sparse form: flat index (plane*G + x)*G + y of every count of
+                                    `obs` (UE u -> plane 1+serving[u]; BS b -> plane 0), duplicates = counts > 1.  What the
+                                    policy network's first layer consumes (main.py:147-153 on ~44 non-zeros of 50 000) */
 } uavenv_out;
 
 typedef struct uavenv uavenv_t;

@@ -1,0 +1,45 @@
+/* uavnet -- C-ABI of the kernels under the A3C actor-critic MLP (the caller of the env step path, SURVEY.md 8(f1/f2)).
+ *
+ * The reference builds two 3-layer MLPs on the flattened (nBS+1)*G*G observation in TensorFlow 1.x
+ * (main.py:143-156: actor 50000->200->200->625 softmax, critic 50000->200->200->1, relu6, N(0,0.1) kernels) and
+ * trains them with two RMSProp optimisers (main.py:300-301) from 10-step rollouts (main.py:212-238).  The observation
+ * has ~44 non-zero cells of 50 000, so the first layer is a gather-sum of weight rows: the env kernel emits the
+ * non-zero cells as flat indices (uavenv_out.obs_idx) and these entry points consume them.  The small dense layers
+ * (200x200, 200x625) are plain library GEMMs on the Python side.
+ *
+ * Plain C types, raw device pointers, the stream is a cudaStream_t passed as void*.  Every entry point returns 0 or a
+ * negative UAVNET_E* code and only enqueues work on the stream.
+ */
+#ifndef UAVNET_H
+#define UAVNET_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { UAVNET_OK = 0, UAVNET_EINVAL = -1, UAVNET_ECUDA = -2 };
+
+/* First dense layer on a sparse count vector (tf.layers.dense(self.s, 200, relu6), main.py:147,151):
+ *   out[m, :] = act( b + sum_k W[idx[m,k], :] ),  act = relu6 (relu6 != 0) or identity.
+ * idx int32 [M,K] (duplicates count twice), W float32 [n_rows, H] row-major, H a multiple of 4 (actor and critic first
+ * layers are stored side by side: H = 400), out float32 [M,H]. */
+int uavnet_sparse_fwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *W, const float *b,
+                      int32_t H, float *out, int32_t relu6, void *stream);
+
+/* Its weight gradient: dW[idx[m,k], :] += dpre[m, :] (float atomics; dW float32 [n_rows,H], zeroed by the caller or by
+ * uavnet_rmsprop), and db[:] += sum_m dpre[m, :] is left to the caller (a column sum). */
+int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
+                      void *stream);
+
+/* TensorFlow-1 RMSPropOptimizer step (main.py:300-301; decay 0.9, momentum 0, epsilon 1e-10, slot `ms` starts at 1):
+ *   g = grad * grad_scale;  ms = decay*ms + (1-decay)*g*g;  param -= lr * g / sqrt(ms + eps);  grad = 0 (if zero_grad)
+ * over n float32 elements (any n; 16-byte aligned pointers). */
+int uavnet_rmsprop(float *param, float *grad, float *ms, int64_t n, float lr, float decay, float eps, float grad_scale,
+                   int32_t zero_grad, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UAVNET_H */

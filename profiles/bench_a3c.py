@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""config[2]-style measurement of the learner on top of the env step path: synchronous A3C iterations (rollout of 10
+steps + one update) over E envs per GPU, device-timed; prints one JSON line with env-steps/s and the time split.
+    python profiles/bench_a3c.py [--envs 8192] [--iters 20]         (torchrun for N > 1: NCCL gradient all-reduce)"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from drl_uav_cellularnet_b200 import BatchedMobiEnvironment  # noqa: E402
+from drl_uav_cellularnet_b200 import dist as udist  # noqa: E402
+from drl_uav_cellularnet_b200.a3c import A3CTrainer, ACNet  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, default=8192)
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--warmup", type=int, default=3)
+args = ap.parse_args()
+rank, world, local = udist.world()
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+udist.init("nccl", dev)
+env = BatchedMobiEnvironment(args.envs, 4, 40, 100, "group", seed=2026, obs="none", env_offset=rank * args.envs, device=local)
+net = ACNet(env.observation_space_dim, env.action_space_dim, dev)
+tr = A3CTrainer(env, net, seed=100 + rank)
+
+
+def timed(fn, n):
+    udist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    udist.barrier()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+for _ in range(args.warmup):
+    tr.train_iteration()
+ms_iter = timed(tr.train_iteration, args.iters)
+ms_roll = timed(tr.rollout, args.iters)
+vt = tr.rollout()
+ms_upd = timed(lambda: tr.update(vt), args.iters)
+ms_env = timed(lambda: env.step(tr.buf_a[0]), 50)
+ms_iter, ms_roll, ms_upd, ms_env = udist.max_over_ranks([ms_iter, ms_roll, ms_upd, ms_env], dev)
+if rank == 0:
+    steps = args.envs * world * tr.T
+    print(json.dumps({"metric": "A3C env-steps/sec (rollout + update)", "value": steps / (ms_iter * 1e-3), "n_gpus": world,
+                      "envs_per_gpu": args.envs, "rollout_steps": tr.T, "ms_per_iteration": ms_iter, "ms_rollout": ms_roll,
+                      "ms_update": ms_upd, "ms_env_step_no_obs": ms_env, "params": net.n_params,
+                      "allreduce_bytes": net.n_flat * 4 if world > 1 else 0}))

@@ -1,0 +1,197 @@
+"""GPU tests of the actor-critic learner built on the env step path: the sparse first layer,
+the hand-written backward, the fused RMSProp step, the n-step targets and the trainer loop, each against a plain
+PyTorch restatement of the reference's TF1 graph (main.py:64-78,143-156,217-227,300-301) on the DENSE observation.
+TensorFlow is absent, so these restatements are the learner's oracle: parity unpinned by the reference.
+Tolerances: float32 arithmetic vs a float64 reference -- 1e-5 absolute on probabilities / values, 1e-4 relative
+(of the largest gradient entry) on gradients."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import drl_uav_cellularnet_b200 as p
+    return p
+
+
+def _dense(idx, n_s):
+    d = torch.zeros((idx.shape[0], n_s), dtype=torch.float64, device=idx.device)
+    d.scatter_add_(1, idx.long(), torch.ones(idx.shape, dtype=torch.float64, device=idx.device))
+    return d
+
+
+def _ref_params(net):
+    """float64 leaf copies of the net's parameters in the reference's per-net layout"""
+    H, p = net.h, net.p
+    names = dict(la=p["W1"][:, :H], la_b=p["b1"][:H], la2=p["Wa2"], la2_b=p["ba2"], ap=p["Wa3"], ap_b=p["ba3"],
+                 lc=p["W1"][:, H:], lc_b=p["b1"][H:], lc2=p["Wc2"], lc2_b=p["bc2"], v=p["Wc3"], v_b=p["bc3"])
+    return {k: t.detach().double().clone().requires_grad_(True) for k, t in names.items()}
+
+
+def _ref_forward(P, s):
+    r6 = lambda x: torch.clamp(x, 0, 6)  # noqa: E731
+    l_a = r6(r6(s @ P["la"] + P["la_b"]) @ P["la2"] + P["la2_b"])
+    a_prob = torch.softmax(l_a @ P["ap"] + P["ap_b"], dim=1)                    # main.py:147-149
+    l_c = r6(r6(s @ P["lc"] + P["lc_b"]) @ P["lc2"] + P["lc2_b"])
+    v = l_c @ P["v"] + P["v_b"]                                                  # main.py:151-153
+    return a_prob, v
+
+
+def _rand_idx(M, K, n_s, seed, dup=True):
+    g = torch.Generator().manual_seed(seed)
+    idx = torch.randint(0, n_s, (M, K), generator=g, dtype=torch.int32)
+    if dup:
+        idx[:, 1] = idx[:, 0]                                                   # two UEs on one cell: count 2
+    return idx.cuda()
+
+
+def test_obs_idx_is_the_sparse_form_of_the_observation(pkg):
+    env = pkg.BatchedMobiEnvironment(16, 4, 40, 100, "group", seed=3)
+    obs = env.reset()
+    assert torch.equal(_dense(env.obs_idx, 50000).float().view_as(obs), obs)
+    for t in range(12):
+        obs, r, d, info = env.step(np.random.RandomState(t).randint(0, 625, size=16))
+        assert torch.equal(_dense(info["obs_idx"], 50000).float().view_as(obs), obs), t
+    env2 = pkg.BatchedMobiEnvironment(16, 4, 40, 100, "group", seed=3, obs="none")  # no dense observation at all
+    env3 = pkg.BatchedMobiEnvironment(16, 4, 40, 100, "group", seed=3)
+    env2.reset()
+    env3.reset()
+    assert env2.obs is None and torch.equal(env2.obs_idx, env3.obs_idx)
+
+
+def test_forward_matches_dense_reference(pkg):
+    from drl_uav_cellularnet_b200.a3c import ACNet
+    net = ACNet(50000, 625, "cuda:0")
+    with torch.no_grad():
+        net.p["b1"].normal_(0, 0.5)
+        net.p["ba2"].normal_(0, 0.5)
+        net.p["bc3"].fill_(0.3)
+    idx = _rand_idx(64, 44, 50000, 1)
+    prob, v, _ = net.forward(idx)
+    P = _ref_params(net)
+    rp, rv = _ref_forward(P, _dense(idx, 50000))
+    assert float((prob.double() - rp.detach()).abs().max()) < 1e-5
+    assert float((v.double() - rv.detach().squeeze(1)).abs().max()) < 1e-4
+    assert torch.equal(net.greedy_action(idx), prob.argmax(1))
+    a = net.choose_action(idx, torch.Generator(device="cuda").manual_seed(0))
+    assert a.shape == (64,) and int(a.min()) >= 0 and int(a.max()) < 625
+
+
+def test_gradients_match_autograd_of_the_reference_losses(pkg):
+    from drl_uav_cellularnet_b200.a3c import ACNet, ENTROPY_BETA
+    net = ACNet(50000, 625, "cuda:0")
+    M = 96
+    idx = _rand_idx(M, 44, 50000, 2)
+    g = torch.Generator().manual_seed(5)
+    a_his = torch.randint(0, 625, (M,), generator=g).cuda()
+    v_target = torch.randn(M, generator=g).cuda()
+    a_loss, c_loss = net.accumulate_grads(idx, a_his, v_target)
+    # reference: the TF graph of main.py:64-78 on the dense observation, float64, autograd
+    P = _ref_params(net)
+    a_prob, v = _ref_forward(P, _dense(idx, 50000))
+    td = v_target.double().unsqueeze(1) - v
+    rc_loss = (td ** 2).mean()
+    log_prob = (torch.log(a_prob + 1e-5) * torch.nn.functional.one_hot(a_his, 625)).sum(1, keepdim=True)
+    entropy = -(a_prob * torch.log(a_prob + 1e-5)).sum(1, keepdim=True)
+    ra_loss = (-(ENTROPY_BETA * entropy + log_prob * td.detach())).mean()
+    ga = torch.autograd.grad(ra_loss, [P[k] for k in ("la", "la_b", "la2", "la2_b", "ap", "ap_b")])
+    gc = torch.autograd.grad(rc_loss, [P[k] for k in ("lc", "lc_b", "lc2", "lc2_b", "v", "v_b")])
+    assert abs(float(a_loss) - float(ra_loss)) < 1e-5 and abs(float(c_loss) - float(rc_loss)) < 1e-5 * max(1, float(rc_loss))
+    H, G = net.h, net.g
+    mine = [G["W1"][:, :H], G["b1"][:H], G["Wa2"], G["ba2"], G["Wa3"], G["ba3"],
+            G["W1"][:, H:], G["b1"][H:], G["Wc2"], G["bc2"], G["Wc3"], G["bc3"]]
+    for m, r in zip(mine, list(ga) + list(gc)):
+        scale = float(r.abs().max())
+        assert scale > 0
+        assert float((m.double() - r).abs().max()) <= 1e-4 * scale, (m.shape, scale)
+    # accumulation: a second call adds the same gradient again
+    before = net.grad.clone()
+    net.accumulate_grads(idx, a_his, v_target)
+    assert torch.allclose(net.grad, 2 * before, rtol=1e-4, atol=1e-7)
+
+
+def test_rmsprop_matches_tf1_update_rule(pkg):
+    from drl_uav_cellularnet_b200.a3c import ACNet, RMS_DECAY, RMS_EPS
+    net = ACNet(1000, 25, "cuda:0", hidden=8)
+    rs = np.random.RandomState(0)
+    p0 = net.flat.cpu().numpy().astype(np.float64)
+    ms = np.ones_like(p0)
+    p = p0.copy()
+    for it in range(3):
+        gnp = rs.normal(0, 1e-2, size=p.shape).astype(np.float32)
+        net.grad.copy_(torch.from_numpy(gnp))
+        net.apply_grads(1e-4, world_size=2)
+        gg = gnp.astype(np.float64) / 2                                  # averaged over 2 ranks
+        ms = RMS_DECAY * ms + (1 - RMS_DECAY) * gg * gg                  # tf.train.RMSPropOptimizer, momentum 0
+        p = p - 1e-4 * gg / np.sqrt(ms + RMS_EPS)
+        assert float(net.grad.abs().max()) == 0.0                        # zeroed for the next accumulation
+    assert np.max(np.abs(net.flat.cpu().numpy() - p)) < 1e-6
+    assert np.max(np.abs(net.ms.cpu().numpy() - ms)) < 1e-6
+
+
+def test_n_step_targets_match_worker_loop(pkg):
+    from drl_uav_cellularnet_b200.a3c import GAMMA, n_step_targets
+    T, E = 10, 7
+    rs = np.random.RandomState(4)
+    r = rs.normal(size=(T, E))
+    done = rs.rand(T, E) < 0.15
+    vb = rs.normal(size=E)
+    got = n_step_targets(torch.from_numpy(r).cuda(), torch.from_numpy(done).cuda(), torch.from_numpy(vb).cuda()).cpu().numpy()
+    for e in range(E):
+        # main.py:212-238 flushes the buffer at `done` with v_s_ = 0 and at the end of the rollout with v(s')
+        t0 = 0
+        for t in range(T):
+            if done[t, e] or t == T - 1:
+                v_s_ = 0.0 if done[t, e] else vb[e]
+                tgt = []
+                for rr in r[t0:t + 1, e][::-1]:
+                    v_s_ = rr + GAMMA * v_s_
+                    tgt.append(v_s_)
+                tgt.reverse()
+                assert np.allclose(got[t0:t + 1, e], tgt, rtol=0, atol=1e-12), (e, t0, t)
+                t0 = t + 1
+
+
+def test_actor_npz_round_trip(pkg, tmp_path):
+    from drl_uav_cellularnet_b200.a3c import ACNet
+    a, b = ACNet(500, 25, "cuda:0", hidden=8), ACNet(500, 25, "cuda:0", hidden=8, seed=9)
+    path = str(tmp_path / "Global_A_PARA.npz")
+    a.save_actor_npz(path)
+    arr = np.load(path, allow_pickle=True)["arr_0"]                       # main_test.py:15
+    assert [x.shape for x in arr] == [(500, 8), (8,), (8, 8), (8,), (8, 25), (25,)]
+    b.load_actor_npz(path)
+    idx = _rand_idx(5, 6, 500, 3)
+    assert torch.equal(a.forward(idx, "actor")[0], b.forward(idx, "actor")[0])
+
+
+def test_trainer_iterations_run_and_learn_signal(pkg):
+    """A few synchronous A3C iterations on 64 envs: finite losses, parameters move, gradients are consumed, episodes
+    restart at MAXSTEP, and the critic loss on a fixed batch drops when the same batch is replayed (sanity of the
+    sign conventions of the hand-written backward + RMSProp)."""
+    from drl_uav_cellularnet_b200.a3c import A3CTrainer, ACNet
+    env = pkg.BatchedMobiEnvironment(64, 4, 40, 100, "group", seed=1, obs="none", max_step=25)
+    net = ACNet(env.observation_space_dim, env.action_space_dim, env.device)
+    tr = A3CTrainer(env, net, seed=2)
+    p0 = net.flat.clone()
+    saw_done = False
+    for it in range(4):
+        a_loss, c_loss = tr.train_iteration()
+        assert torch.isfinite(a_loss) and torch.isfinite(c_loss)
+        saw_done = saw_done or bool(tr.buf_done.any())
+    assert float((net.flat - p0).abs().max()) > 0 and float(net.grad.abs().max()) == 0.0
+    assert int(env.step_n.max()) == 15 and saw_done                            # 40 steps, MAXSTEP 25: episodes restarted
+    M = tr.T * tr.E
+    idx, a, vt = tr.buf_idx.view(M, -1), tr.buf_a.view(M), torch.zeros(M, device=env.device)
+    first = last = None
+    for it in range(60):
+        _, c_loss = net.accumulate_grads(idx, a, vt)
+        net.apply_grads(1e-4)
+        first = float(c_loss) if first is None else first
+        last = float(c_loss)
+    assert last < first
+    assert env.check() == 0
