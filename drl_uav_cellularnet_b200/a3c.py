@@ -256,3 +256,28 @@ class A3CTrainer:
 
     def train_iteration(self):
         return self.update(self.rollout())
+
+    # ---- one CUDA graph per iteration: ~250 small launches (env step, reset, GEMMs, softmax, sampling, ...) replayed
+    # ---- without Python or launch latency between them
+    def capture(self, warmup: int = 2):
+        """Capture ``train_iteration`` into a CUDA graph (after `warmup` eager iterations on a side stream).
+        The env / net / trainer buffers are all persistent, so the captured pointers stay valid; the sampling
+        generator is registered with the graph so that every replay draws fresh actions."""
+        dev = self.env.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.train_iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self._graph = torch.cuda.CUDAGraph()
+        self._graph.register_generator_state(self.gen)
+        with torch.cuda.graph(self._graph):
+            self._graph_out = self.train_iteration()
+        return self
+
+    def train_iteration_graph(self):
+        """Replay the captured iteration; returns the (a_loss, c_loss) tensors of the replay (static buffers)."""
+        self._graph.replay()
+        return self._graph_out

@@ -29,7 +29,17 @@ enum { MODE_STEP = 0, MODE_RESET = 1, MODE_CTOR = 2 };
 enum { MOB_GROUP = 0, MOB_TRACE = 1 };
 enum { FADE_PHILOX = 0, FADE_INJECTED = 1, FADE_NONE = 2 };
 enum { OBS_NONE = 0, OBS_F32 = 1, OBS_F32_INCREMENTAL = 3 };
-enum { ERR_ACTION = 1u, ERR_TRACE = 2u, ERR_CLAMP = 4u };
+enum { ERR_ACTION = 1u, ERR_TRACE = 2u, ERR_CLAMP = 4u, ERR_BOUNDS = 8u };
+
+// Observation count update.  -DUAVENV_BOUNDS_CHECK builds verify every index against the env's observation and raise
+// the sticky ERR_BOUNDS flag instead of writing (compute-sanitizer is closed on the measurement pool; this is the
+// bounds check of our own that profiles/all_paths_case.py runs).
+__device__ __forceinline__ void obs_add(float *obs_env, long long lin, float v, long long n_cells, uint32_t *err_flags) {
+#ifdef UAVENV_BOUNDS_CHECK
+    if (lin < 0 || lin >= n_cells) { atomicOr(err_flags, ERR_BOUNDS); return; }
+#endif
+    atomicAdd(obs_env + lin, v);
+}
 enum { CTR_TICK = 0, CTR_EPOCH = 1, CTR_STEP = 2, CTR_AGG = 3, CTR_DEAGG = 4, CTR_STRIDE = 8 };
 
 // handover word, one per UE (channel.py:75-81,92-93): current_BS, the <=3 rows of bestBS_buf, its depth, and
@@ -651,6 +661,10 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         __syncwarp();
         const uint32_t total = (uint32_t)n_cells * 4u;
         char *dst = reinterpret_cast<char *>(obs_env);
+#ifdef UAVENV_BOUNDS_CHECK
+        if (tile_bytes == 0 || (tile_bytes & 15) || (total & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+            atomicOr(c.err_flags, ERR_BOUNDS);
+#endif
 #ifndef UAVENV_NO_L2_HINT
         const uint64_t pol = l2_policy_evict_first();      // write-once stream: first in line for eviction
         for (uint32_t off = (uint32_t)lane * tile_bytes; off < total; off += 32u * tile_bytes)
@@ -712,8 +726,8 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 if (a.bs_digits && mode == MODE_STEP) a.bs_digits[(size_t)e * nBS + lane] = (uint8_t)digit;
                 if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + nUE + lane] = bx * G + by;
                 if (incremental && (ox != bx || oy != by)) {
-                    atomicAdd(obs_env + (size_t)ox * G + oy, -1.f);
-                    atomicAdd(obs_env + (size_t)bx * G + by, 1.f);
+                    obs_add(obs_env, (long long)((size_t)ox * G + oy), -1.f, n_cells, c.err_flags);
+                    obs_add(obs_env, (long long)((size_t)bx * G + by), 1.f, n_cells, c.err_flags);
                 }
             }
             if (lane == 0) s.blocked = blocked;
@@ -746,7 +760,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
             if (incremental) {
                 // the cell of the previous step leaves its association plane
-                atomicAdd(obs_env + ((size_t)(1 + (c.ho[i] & 31)) * G + cell.x) * G + cell.y, -1.f);
+                obs_add(obs_env, (long long)(((size_t)(1 + (c.ho[i] & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
             }
             if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, c.x[i], c.y[i], inj ? c.th_u[i] : 0.0);
             else if (tr) {
@@ -780,7 +794,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 if (a.serving) a.serving[i] = (uint8_t)srv;
                 if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = curS;
                 if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
-                if (incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+                if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
             }
         }
     } else {
@@ -790,7 +804,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         uint32_t word = c.ho[i];
         if (incremental) {
             // the cell of the previous step leaves its association plane
-            atomicAdd(obs_env + ((size_t)(1 + (word & 31)) * G + cell.x) * G + cell.y, -1.f);
+            obs_add(obs_env, (long long)(((size_t)(1 + (word & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
         }
         if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, c.x[i], c.y[i], inj ? c.th_u[i] : 0.0);
         else if (tr) {
@@ -811,7 +825,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         if (a.serving_sinr) reinterpret_cast<T *>(a.serving_sinr)[i] = curS;
         if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
         if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
-        if (incremental) atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+        if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
     }
     }
     if (group_tick) { mob_phase_advance(c, agg, deagg); tick++; }
@@ -834,9 +848,9 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             const size_t i = (size_t)e * nUE + u;
             const short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
             const int srv = c.ho[i] & 31;
-            atomicAdd(obs_env + ((size_t)(1 + srv) * G + cell.x) * G + cell.y, 1.f);
+            obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
         }
-        if (tid < nBS) atomicAdd(obs_env + (size_t)s.bsx[tid] * G + s.bsy[tid], 1.f);
+        if (tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);
     }
     if (tid == 0) {
         double tot = 0.0;

@@ -488,6 +488,7 @@ int uavenv_check(uavenv_t *h, uint32_t *flags_out, void *stream) {
     CU(h, cudaStreamSynchronize(st));
     if (flags_out) *flags_out = f;
     if (f & 1u) return fail(h, UAVENV_EACTION, "an action was outside [0, n_act^n_bs) (or a digit >= n_act); those envs were not stepped%s");
+    if (f & 8u) return fail(h, UAVENV_ECUDA, "bounds-check build: an observation index fell outside the env's observation%s");
     if (f & 2u) return fail(h, UAVENV_ETRACE, "trace exhausted (step_n past the end of the trace); those envs were not stepped%s");
     return UAVENV_OK;
 }

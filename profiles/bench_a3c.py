@@ -19,11 +19,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=8192)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--tf32", action="store_true", help="TF32 tensor-core GEMMs for the dense layers (default: fp32 SIMT)")
+ap.add_argument("--graph", action="store_true", help="also time the iteration replayed as one CUDA graph")
 args = ap.parse_args()
 rank, world, local = udist.world()
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 udist.init("nccl", dev)
+if args.tf32:
+    torch.backends.cuda.matmul.allow_tf32 = True
 env = BatchedMobiEnvironment(args.envs, 4, 40, 100, "group", seed=2026, obs="none", env_offset=rank * args.envs, device=local)
 net = ACNet(env.observation_space_dim, env.action_space_dim, dev)
 tr = A3CTrainer(env, net, seed=100 + rank)
@@ -49,10 +53,17 @@ ms_roll = timed(tr.rollout, args.iters)
 vt = tr.rollout()
 ms_upd = timed(lambda: tr.update(vt), args.iters)
 ms_env = timed(lambda: env.step(tr.buf_a[0]), 50)
-ms_iter, ms_roll, ms_upd, ms_env = udist.max_over_ranks([ms_iter, ms_roll, ms_upd, ms_env], dev)
+ms_graph = float("nan")
+if args.graph:
+    tr.capture()
+    for _ in range(2):
+        tr.train_iteration_graph()
+    ms_graph = timed(tr.train_iteration_graph, args.iters)
+ms_iter, ms_roll, ms_upd, ms_env, ms_graph = udist.max_over_ranks([ms_iter, ms_roll, ms_upd, ms_env, ms_graph], dev)
 if rank == 0:
     steps = args.envs * world * tr.T
     print(json.dumps({"metric": "A3C env-steps/sec (rollout + update)", "value": steps / (ms_iter * 1e-3), "n_gpus": world,
                       "envs_per_gpu": args.envs, "rollout_steps": tr.T, "ms_per_iteration": ms_iter, "ms_rollout": ms_roll,
-                      "ms_update": ms_upd, "ms_env_step_no_obs": ms_env, "params": net.n_params,
+                      "ms_update": ms_upd, "ms_env_step_no_obs": ms_env, "ms_per_iteration_graph": ms_graph,
+                      "value_graph": steps / (ms_graph * 1e-3) if args.graph else None, "tf32": bool(args.tf32), "params": net.n_params,
                       "allreduce_bytes": net.n_flat * 4 if world > 1 else 0}))
