@@ -124,15 +124,21 @@ class ACNet:
         return self.forward(idx, "critic")[1]
 
     # ---- losses + gradients (main.py:64-78), accumulated into self.grad -------------------------------------
-    def accumulate_grads(self, idx: torch.Tensor, a_his: torch.Tensor, v_target: torch.Tensor):
+    def accumulate_grads(self, idx: torch.Tensor, a_his: torch.Tensor, v_target: torch.Tensor, saved: Optional[dict] = None):
         """Adds d(a_loss)/d(actor params) and d(c_loss)/d(critic params) for the batch to ``self.grad``;
         returns (a_loss, c_loss) as 0-d tensors.  a_loss = mean(-(log(pi(a)+1e-5) * sg(td) + beta * H)),
-        c_loss = mean(td^2), td = v_target - v."""
+        c_loss = mean(td^2), td = v_target - v.  `saved`: activations kept from the rollout (h1, h2a, prob -- the
+        parameters do not change between the rollout and its update), else they are recomputed from idx."""
         H, p, g = self.h, self.p, self.g
         M = idx.shape[0]
-        prob, v, c = self.forward(idx, "both")
-        h1, h2a, h2c = c["h1"], c["h2a"], c["h2c"]
-        td = v_target - v
+        if saved is not None:
+            h1, h2a, prob = saved["h1"], saved["h2a"], saved["prob"]
+        else:
+            prob, _, c = self.forward(idx, "actor")
+            h1, h2a = c["h1"], c["h2a"]
+        h2c = _relu6(torch.addmm(p["bc2"], h1[:, H:], p["Wc2"]))
+        v = torch.addmm(p["bc3"], h2c, p["Wc3"]).squeeze(1)
+        td = (v_target - v).contiguous()
         # -- critic --
         c_loss = (td * td).mean()
         dv = (-2.0 / M) * td                                              # [M]
@@ -142,21 +148,21 @@ class ACNet:
         g["Wc2"].addmm_(h1[:, H:].t(), dpre2c)
         g["bc2"].add_(dpre2c.sum(0))
         dpre1 = torch.empty_like(h1)
-        dpre1[:, H:].copy_(dpre2c @ p["Wc2"].t())
-        # -- actor --
-        lp = torch.log(prob + 1e-5)
-        p_a = prob.gather(1, a_his.unsqueeze(1)).squeeze(1)
-        entropy = -(prob * lp).sum(1)
-        a_loss = -(torch.log(p_a + 1e-5) * td + ENTROPY_BETA * entropy).mean()
-        gp = (ENTROPY_BETA / M) * (lp + prob / (prob + 1e-5))             # dL/dp, entropy part
-        gp.scatter_add_(1, a_his.unsqueeze(1), ((-1.0 / M) * td / (p_a + 1e-5)).unsqueeze(1))
-        dz = prob * (gp - (prob * gp).sum(1, keepdim=True))               # through the softmax
+        torch.mm(dpre2c, p["Wc2"].t(), out=dpre1[:, H:])
+        # -- actor: d(a_loss)/d(logits) in one fused pass over the softmax output --
+        dz = torch.empty_like(prob)
+        loss_row = torch.empty(M, dtype=torch.float32, device=self.device)
+        rc = self._lib.uavnet_actor_head_bwd(_ptr(prob), _ptr(a_his), _ptr(td), M, self.n_a, ENTROPY_BETA, _ptr(dz),
+                                             _ptr(loss_row), self._stream())
+        if rc:
+            raise RuntimeError("uavnet_actor_head_bwd failed (%d)" % rc)
+        a_loss = loss_row.mean()
         g["Wa3"].addmm_(h2a.t(), dz)
         g["ba3"].add_(dz.sum(0))
         dpre2a = (dz @ p["Wa3"].t()) * ((h2a > 0) & (h2a < 6))
         g["Wa2"].addmm_(h1[:, :H].t(), dpre2a)
         g["ba2"].add_(dpre2a.sum(0))
-        dpre1[:, :H].copy_(dpre2a @ p["Wa2"].t())
+        torch.mm(dpre2a, p["Wa2"].t(), out=dpre1[:, :H])
         dpre1.mul_((h1 > 0) & (h1 < 6))
         g["b1"].add_(dpre1.sum(0))
         rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
@@ -224,6 +230,10 @@ class A3CTrainer:
         self.buf_a = torch.empty((self.T, self.E), dtype=torch.int64, device=dev)
         self.buf_r = torch.empty((self.T, self.E), dtype=torch.float32, device=dev)
         self.buf_done = torch.empty((self.T, self.E), dtype=torch.bool, device=dev)
+        # activations of the rollout's forward passes, reused by the update (same parameters)
+        self.buf_h1 = torch.empty((self.T, self.E, 2 * net.h), dtype=torch.float32, device=dev)
+        self.buf_h2a = torch.empty((self.T, self.E, net.h), dtype=torch.float32, device=dev)
+        self.buf_prob = torch.empty((self.T, self.E, net.n_a), dtype=torch.float32, device=dev)
         self.ep_return = torch.zeros(self.E, dtype=torch.float64, device=dev)
         self.env.reset()
         self.updates = 0
@@ -232,7 +242,11 @@ class A3CTrainer:
         env, net = self.env, self.net
         for t in range(self.T):
             self.buf_idx[t].copy_(env.obs_idx)
-            a = net.choose_action(self.buf_idx[t], self.gen)                 # main.py:195
+            prob, _, c = net.forward(self.buf_idx[t], "actor")
+            self.buf_h1[t].copy_(c["h1"])
+            self.buf_h2a[t].copy_(c["h2a"])
+            self.buf_prob[t].copy_(prob)
+            a = torch.multinomial(prob, 1, generator=self.gen).squeeze(1)    # np.random.choice(p=a_prob), main.py:165-169,195
             _, r, done, _ = env.step(a)                                      # main.py:198
             self.buf_a[t].copy_(a)
             self.buf_r[t].copy_(r)
@@ -244,7 +258,8 @@ class A3CTrainer:
 
     def update(self, v_target: torch.Tensor):
         net, M = self.net, self.T * self.E
-        a_loss, c_loss = net.accumulate_grads(self.buf_idx.view(M, self.K), self.buf_a.view(M), v_target.reshape(M))
+        saved = {"h1": self.buf_h1.view(M, -1), "h2a": self.buf_h2a.view(M, -1), "prob": self.buf_prob.view(M, -1)}
+        a_loss, c_loss = net.accumulate_grads(self.buf_idx.view(M, self.K), self.buf_a.view(M), v_target.reshape(M), saved)
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()

@@ -618,12 +618,13 @@ __device__ __forceinline__ void obs_zero_fill_lsu(float *obs_env, int n_cells) {
 #ifndef UAVENV_MINB
 #define UAVENV_MINB 3
 #endif
-constexpr int min_blocks(int nb, bool f64) { return (f64 || nb > 8) ? 1 : UAVENV_MINB; }
+constexpr int NT_SMALL = 128;   // CTA size for handles without a dense observation stream and <= 64 UEs per env
+constexpr int min_blocks(int nb, bool f64, int nt) { return (f64 || nb > 8) ? 1 : (nt == NT_SMALL ? 6 : UAVENV_MINB); }
 
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
 //   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
 template <int NB, bool F64, int NT>
-__global__ void __launch_bounds__(NT, min_blocks(NB, F64))
+__global__ void __launch_bounds__(NT, min_blocks(NB, F64, NT))
 env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a) {
     using T = typename Real<F64>::T;
     constexpr int NW = NT / 32;

@@ -68,12 +68,12 @@ int use_device(uavenv_t *h) {
 
 typedef void (*env_kernel_fn)(const DevCfg, const CallArgs);
 
-template <bool F64>
+template <bool F64, int NT>
 env_kernel_fn pick_nb(int nBS) {
-    if (nBS <= 4) return env_kernel<4, F64, CTA_THREADS>;
-    if (nBS <= 8) return env_kernel<8, F64, CTA_THREADS>;
-    if (nBS <= 16) return env_kernel<16, F64, CTA_THREADS>;
-    return env_kernel<32, F64, CTA_THREADS>;
+    if (nBS <= 4) return env_kernel<4, F64, NT>;
+    if (nBS <= 8) return env_kernel<8, F64, NT>;
+    if (nBS <= 16) return env_kernel<16, F64, NT>;
+    return env_kernel<32, F64, NT>;
 }
 
 /* Launch plan of the step kernel (one CTA per env): the zero tile the TMA warp streams from and the CTAs per SM.
@@ -83,8 +83,12 @@ env_kernel_fn pick_nb(int nBS) {
  * size also sets the residency: 64 KB -> 3 CTAs per SM -> 444 x 200 KB = 89 MB in flight at the reference sizes. */
 int plan_kernel(uavenv_t *h) {
     const bool f64 = h->cfg.precision == UAVENV_PREC_FP64_PARITY;
-    h->kernel = (void *)(f64 ? pick_nb<true>(h->d.nBS) : pick_nb<false>(h->d.nBS));
-    h->threads = CTA_THREADS;
+    /* Without a dense observation to stream (obs NONE / INCREMENTAL: the policy reads obs_idx) the step is pure
+     * latency-bound arithmetic: small envs then run in 128-thread CTAs, twice as many resident per SM. */
+    const bool small = !f64 && h->cfg.obs_mode != UAVENV_OBS_F32 && h->d.nUE <= 64;
+    h->threads = small ? NT_SMALL : CTA_THREADS;
+    if (small) h->kernel = (void *)pick_nb<false, NT_SMALL>(h->d.nBS);
+    else h->kernel = (void *)(f64 ? pick_nb<true, CTA_THREADS>(h->d.nBS) : pick_nb<false, CTA_THREADS>(h->d.nBS));
     const int64_t n_cells = (int64_t)(h->d.nBS + 1) * h->d.G * h->d.G;
     int dev_smem = 0, n_sm = 0;
     CU(h, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));

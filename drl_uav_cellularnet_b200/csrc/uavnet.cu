@@ -89,6 +89,47 @@ __global__ void __launch_bounds__(NET_THREADS) rmsprop_kernel(float *__restrict_
     }
 }
 
+// Gradient of the actor loss w.r.t. the logits, one warp per sample (main.py:68-76 through the softmax):
+//   L = -(1/M) sum_i [ log(p_i,a_i + 1e-5) * td_i + beta * H_i ],   H_i = -sum_j p_ij log(p_ij + 1e-5)
+//   g_ij = dL/dp_ij = (beta/M) (log(p_ij + 1e-5) + p_ij / (p_ij + 1e-5)) - [j = a_i] td_i / (M (p_i,a_i + 1e-5))
+//   dz_ij = p_ij (g_ij - sum_k p_ik g_ik)
+// One read of the probabilities (the second pass hits L1), one write of dz, and the sample's loss term.
+__global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float *__restrict__ prob, const long long *__restrict__ a_his,
+                                                                     const float *__restrict__ td, long long M, int A, float beta,
+                                                                     float inv_m, float *__restrict__ dz, float *__restrict__ loss_row) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * NET_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * NET_THREADS) >> 5;
+    for (long long m = warp0; m < M; m += n_warps) {
+        const float *pr = prob + m * A;
+        const int a = (int)a_his[m];
+        const float t = td[m];
+        const float pa = pr[a];
+        const float ga = -t * inv_m / (pa + 1e-5f);
+        float ent = 0.f, dot = 0.f;                       // -H/1 accumulators: sum p*lp, sum p*g
+        for (int j = lane; j < A; j += 32) {
+            const float p = pr[j];
+            const float lp = logf(p + 1e-5f);
+            const float g = beta * inv_m * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f);
+            ent += p * lp;
+            dot += p * g;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ent += __shfl_xor_sync(0xffffffffu, ent, o);
+            dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        }
+        float *dr = dz + m * A;
+        for (int j = lane; j < A; j += 32) {
+            const float p = pr[j];
+            const float lp = logf(p + 1e-5f);
+            const float g = beta * inv_m * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f);
+            dr[j] = p * (g - dot);
+        }
+        if (lane == 0 && loss_row) loss_row[m] = -(logf(pa + 1e-5f) * t - beta * ent);
+    }
+}
+
 int grid_for(long long items) {
     long long g = (items + NET_THREADS - 1) / NET_THREADS;
     const long long cap = 148LL * 8 * 4;          // a few waves of 8 CTAs per SM; the kernels are grid-stride
@@ -119,6 +160,14 @@ int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
         return UAVNET_EINVAL;
     sparse_bwd_kernel<<<grid_for(M * (H / 4)), NET_THREADS, 0, (cudaStream_t)stream>>>(idx, M, K, (const float4 *)dpre,
                                                                                     H / 4, (float4 *)dW);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
+                          float *dz, float *loss_row, void *stream) {
+    if (!prob || !a_his || !td || !dz || M < 1 || A < 1) return UAVNET_EINVAL;
+    actor_head_bwd_kernel<<<grid_for(M * 32), NET_THREADS, 0, (cudaStream_t)stream>>>(
+        prob, (const long long *)a_his, td, M, A, beta, 1.0f / (float)M, dz, loss_row);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 

@@ -33,6 +33,13 @@ int uavnet_sparse_fwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
 int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
                       void *stream);
 
+/* d(a_loss)/d(logits) of the actor loss (main.py:68-76), fused over the softmax output:
+ *   a_loss = mean_i -( log(prob[i,a_i] + 1e-5) * td_i + beta * H_i ),  H_i = -sum_j prob_ij log(prob_ij + 1e-5)
+ * prob float32 [M,A] (softmax output), a_his int64 [M], td float32 [M] (v_target - v, treated as constant),
+ * dz float32 [M,A] out, loss_row float32 [M] out (the per-sample loss term; its mean is a_loss; may be NULL). */
+int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
+                          float *dz, float *loss_row, void *stream);
+
 /* TensorFlow-1 RMSPropOptimizer step (main.py:300-301; decay 0.9, momentum 0, epsilon 1e-10, slot `ms` starts at 1):
  *   g = grad * grad_scale;  ms = decay*ms + (1-decay)*g*g;  param -= lr * g / sqrt(ms + eps);  grad = 0 (if zero_grad)
  * over n float32 elements (any n; 16-byte aligned pointers). */
