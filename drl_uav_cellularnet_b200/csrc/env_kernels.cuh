@@ -362,7 +362,7 @@ template <> struct Real<true> { using T = double; };
 // The channel pass of one UE against all BSs + its handover-word update.
 // NB: compile-time bound on nBS (register arrays).  Returns the serving-cell SINR (pre-handover cell,
 // channel.py:145-146) and updates `word`; flags receive new-outage / handover events.
-template <int NB, bool F64>
+template <int NB, bool F64, bool DIAG>
 __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c, const CallArgs &a,
                                                                  const EnvShared &s, int e, uint32_t genv, int u,
                                                                  int cx, int cy, uint32_t epoch, int mode,
@@ -398,9 +398,11 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 #pragma unroll
         for (int b = 0; b < NB; b++) fade[b] = (T)0;
     }
-    if (a.fading_used) {
+    if constexpr (DIAG) {
+        if (a.fading_used) {
 #pragma unroll
-        for (int b = 0; b < NB; b++) if (b < nBS) a.fading_used[pair0 + b] = (float)fade[b];
+            for (int b = 0; b < NB; b++) if (b < nBS) a.fading_used[pair0 + b] = (float)fade[b];
+        }
     }
 
     T S[NB];   // SINR in dB per BS
@@ -477,9 +479,11 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
             S[b] = b < nBS ? (gdb[b] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + interf) : -3.0e38f;
         }
     }
-    if (a.sinr_all) {
+    if constexpr (DIAG) {
+        if (a.sinr_all) {
 #pragma unroll
-        for (int b = 0; b < NB; b++) if (b < nBS) reinterpret_cast<T *>(a.sinr_all)[pair0 + b] = S[b];
+            for (int b = 0; b < NB; b++) if (b < nBS) reinterpret_cast<T *>(a.sinr_all)[pair0 + b] = S[b];
+        }
     }
 
     // ---- best server: first maximum (np.argmax / np.max, channel.py:141-142) ----
@@ -501,33 +505,35 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 // never total - own; the best server is a shuffle argmax with lowest-index tie break.  All lanes of a
 // group end up with the same decision; the caller lets lane q == 0 write it.  `u` must be clamped to a valid UE on
 // every lane (shuffles need the whole warp).
-template <int NB>
+template <int NB, bool DIAG, bool FULL>
 __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs &a, const EnvShared &s, int e,
                                                  uint32_t genv, int u, int cx, int cy, uint32_t epoch, int mode,
                                                  uint32_t &word, int &new_out, int &did_ho) {
     constexpr int LPU = NB / 4;                                        // lanes per UE
     static_assert(NB == 8 || NB == 16 || NB == 32, "quad mapping");
     const int lane = threadIdx.x & 31, q = lane & (LPU - 1), gbase = lane & ~(LPU - 1);
-    const int nBS = c.nBS, cpu = (nBS + 3) >> 2, b0 = 4 * q;
+    // FULL: nBS == NB, every lane owns four real BSs and no validity test is compiled in
+    const int nBS = FULL ? NB : c.nBS, cpu = FULL ? LPU : (c.nBS + 3) >> 2, b0 = 4 * q;
     const size_t pair0 = ((size_t)e * c.nUE + u) * nBS;
     float fade[4] = {0.f, 0.f, 0.f, 0.f};
-    if (c.fading == FADE_INJECTED) {
+    if (c.fading == FADE_PHILOX) {
+        if (FULL || q < cpu) {
+            const Philox4 p = philox4x32_10(genv, (uint32_t)(u * cpu + q), epoch, DOM_FADING, c.k0, c.k1);
+            float z[4];
+            normal4_f32(p, z);
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (b0 + k < nBS) fade[k] = (float)a.fading[pair0 + b0 + k];
-    } else if (c.fading == FADE_PHILOX && q < cpu) {
-        const Philox4 p = philox4x32_10(genv, (uint32_t)(u * cpu + q), epoch, DOM_FADING, c.k0, c.k1);
-        float z[4];
-        normal4_f32(p, z);
+            for (int k = 0; k < 4; k++) fade[k] = fmaf(c.f_sh_sd, z[k], c.f_sh_mean);
+        }
+    } else if (c.fading == FADE_INJECTED) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) fade[k] = fmaf(c.f_sh_sd, z[k], c.f_sh_mean);
+        for (int k = 0; k < 4; k++) if (FULL || b0 + k < nBS) fade[k] = (float)a.fading[pair0 + b0 + k];
     }
     float gdb[4], p[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         gdb[k] = 0.f; p[k] = 0.f;
         const int b = b0 + k;
-        if (b < nBS) {
-            if (a.fading_used) a.fading_used[pair0 + b] = fade[k];
+        if (FULL || b < nBS) {
             const int dx = cx - s.bsx[b], dy = cy - s.bsy[b];
             const float qd = c.f_q_scale * (float)(dx * dx + dy * dy);
             const float loss = qd > c.f_q_min ? fmaf(c.f_loss_k, __log2f(qd), c.f_loss_a) : 0.f;
@@ -539,19 +545,33 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
     float others = 0.f;                                                // quad sums of the other lanes of the group
 #pragma unroll
     for (int r = 1; r < LPU; r++) others += __shfl_sync(0xffffffffu, quad, gbase | ((q + r) & (LPU - 1)));
-    float S[4];
-    int best = b0;
-    float bestS = -3.0e38f;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float mine = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) if (j != k) mine += p[j];
-        S[k] = b0 + k < nBS ? (gdb[k] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + (others + mine)) : -3.0e38f;
-        if (S[k] > bestS) { bestS = S[k]; best = b0 + k; }             // first maximum inside the quad
-        if (a.sinr_all && b0 + k < nBS) reinterpret_cast<float *>(a.sinr_all)[pair0 + b0 + k] = S[k];
+    // exclude-self sums inside the quad: (others + the other three)
+    const float i0 = others + ((p[1] + p[2]) + p[3]), i1 = others + ((p[0] + p[2]) + p[3]);
+    const float i2 = others + ((p[0] + p[1]) + p[3]), i3 = others + ((p[0] + p[1]) + p[2]);
+    float S0 = (gdb[0] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i0), S1 = (gdb[1] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i1);
+    float S2 = (gdb[2] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i2), S3 = (gdb[3] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i3);
+    if (!FULL) {
+        if (b0 + 0 >= nBS) S0 = -3.0e38f;
+        if (b0 + 1 >= nBS) S1 = -3.0e38f;
+        if (b0 + 2 >= nBS) S2 = -3.0e38f;
+        if (b0 + 3 >= nBS) S3 = -3.0e38f;
     }
-    // best server over the group: butterfly argmax, ties to the lower BS index (np.argmax, channel.py:141)
+    if constexpr (DIAG) {
+        const float Sv[4] = {S0, S1, S2, S3};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (FULL || b0 + k < nBS) {
+                if (a.sinr_all) reinterpret_cast<float *>(a.sinr_all)[pair0 + b0 + k] = Sv[k];
+                if (a.fading_used) a.fading_used[pair0 + b0 + k] = fade[k];
+            }
+    }
+    // first maximum inside the quad, then a butterfly argmax over the group: ties to the lower BS index
+    // (np.argmax, channel.py:141)
+    int best = b0;
+    float bestS = S0;
+    if (S1 > bestS) { bestS = S1; best = b0 + 1; }
+    if (S2 > bestS) { bestS = S2; best = b0 + 2; }
+    if (S3 > bestS) { bestS = S3; best = b0 + 3; }
 #pragma unroll
     for (int o = 1; o < LPU; o <<= 1) {
         const float oS = __shfl_xor_sync(0xffffffffu, bestS, o);
@@ -559,10 +579,8 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
         if (oS > bestS || (oS == bestS && oB < best)) { bestS = oS; best = oB; }
     }
     // SINR of the UE's current (pre-handover) cell lives on lane cur/4 of the group
-    const int cur = word & 31;
-    float mineS = S[0];
-#pragma unroll
-    for (int k = 1; k < 4; k++) if (k == (cur & 3)) mineS = S[k];
+    const int cur = word & 31, ks = cur & 3;
+    const float mineS = ks == 0 ? S0 : (ks == 1 ? S1 : (ks == 2 ? S2 : S3));
     const float curS = __shfl_sync(0xffffffffu, mineS, gbase | ((cur >> 2) & (LPU - 1)));
     return ho_decide<float>(c, mode, best, bestS, curS, word, new_out, did_ho);
 }
@@ -623,7 +641,7 @@ constexpr int min_blocks(int nb, bool f64, int nt) { return (f64 || nb > 8) ? 1 
 
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
 //   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
-template <int NB, bool F64, int NT>
+template <int NB, bool F64, int NT, bool DIAG>
 __global__ void __launch_bounds__(NT, min_blocks(NB, F64, NT))
 env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a) {
     using T = typename Real<F64>::T;
@@ -776,6 +794,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // ---- (B) NB/4 lanes = one UE, lane = 4 BSs: channel pass with shuffle reductions (ue_channel_quad)
         constexpr int LPU = NB / 4, UPW = 32 / LPU;
         const int q = lane & (LPU - 1);
+        const bool full_bs = nBS == NB;
         for (int base = warp * UPW; base < nUE; base += NW * UPW) {
             const int uu = base + lane / LPU;
             const bool live = uu < nUE;
@@ -784,8 +803,9 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             const short2 cell = cells[u];
             uint32_t word = mode == MODE_STEP ? c.ho[i] : 0u;
             int new_out, did_ho;
-            const float curS = ue_channel_quad<NB>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
-                                                   new_out, did_ho);
+            const float curS = full_bs
+                ? ue_channel_quad<NB, DIAG, true>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho)
+                : ue_channel_quad<NB, DIAG, false>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho);
             if (live && q == 0) {
                 c.ho[i] = word;
                 sum_sinr += (double)curS;
@@ -814,8 +834,8 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         }
         if (mode != MODE_STEP) word = 0u;
         int new_out, did_ho;
-        const T curS = ue_channel_pass<NB, F64>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
-                                                new_out, did_ho);
+        const T curS = ue_channel_pass<NB, F64, DIAG>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
+                                                      new_out, did_ho);
         if (mode != MODE_CTOR || c.mobility == MOB_TRACE) reinterpret_cast<short2 *>(c.ue_cell)[i] = cell;
         c.ho[i] = word;
         sum_sinr += (double)curS;

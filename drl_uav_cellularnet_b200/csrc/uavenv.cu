@@ -38,7 +38,7 @@ struct uavenv {
     Field fields[F_COUNT];
     bool ctor_done;
     // launch plan of the persistent step kernel
-    void *kernel;
+    void *kernel, *kernel_diag;
     int threads, grid, tile_bytes, ctas_per_sm, cells_off;
     size_t dyn_smem;
     bool tiles_ok;
@@ -68,12 +68,12 @@ int use_device(uavenv_t *h) {
 
 typedef void (*env_kernel_fn)(const DevCfg, const CallArgs);
 
-template <bool F64, int NT>
+template <bool F64, int NT, bool DIAG>
 env_kernel_fn pick_nb(int nBS) {
-    if (nBS <= 4) return env_kernel<4, F64, NT>;
-    if (nBS <= 8) return env_kernel<8, F64, NT>;
-    if (nBS <= 16) return env_kernel<16, F64, NT>;
-    return env_kernel<32, F64, NT>;
+    if (nBS <= 4) return env_kernel<4, F64, NT, DIAG>;
+    if (nBS <= 8) return env_kernel<8, F64, NT, DIAG>;
+    if (nBS <= 16) return env_kernel<16, F64, NT, DIAG>;
+    return env_kernel<32, F64, NT, DIAG>;
 }
 
 /* Launch plan of the step kernel (one CTA per env): the zero tile the TMA warp streams from and the CTAs per SM.
@@ -87,8 +87,11 @@ int plan_kernel(uavenv_t *h) {
      * latency-bound arithmetic: small envs then run in 128-thread CTAs, twice as many resident per SM. */
     const bool small = !f64 && h->cfg.obs_mode != UAVENV_OBS_F32 && h->d.nUE <= 64;
     h->threads = small ? NT_SMALL : CTA_THREADS;
-    if (small) h->kernel = (void *)pick_nb<false, NT_SMALL>(h->d.nBS);
-    else h->kernel = (void *)(f64 ? pick_nb<true, CTA_THREADS>(h->d.nBS) : pick_nb<false, CTA_THREADS>(h->d.nBS));
+    /* two builds of every kernel: the lean one, and one that can also write the full SINR matrix / the applied fading
+     * (uavenv_out.sinr_all / fading_used; selected on the first call that passes either pointer) */
+    if (small) { h->kernel = (void *)pick_nb<false, NT_SMALL, false>(h->d.nBS); h->kernel_diag = (void *)pick_nb<false, NT_SMALL, true>(h->d.nBS); }
+    else if (f64) { h->kernel = (void *)pick_nb<true, CTA_THREADS, false>(h->d.nBS); h->kernel_diag = (void *)pick_nb<true, CTA_THREADS, true>(h->d.nBS); }
+    else { h->kernel = (void *)pick_nb<false, CTA_THREADS, false>(h->d.nBS); h->kernel_diag = (void *)pick_nb<false, CTA_THREADS, true>(h->d.nBS); }
     const int64_t n_cells = (int64_t)(h->d.nBS + 1) * h->d.G * h->d.G;
     int dev_smem = 0, n_sm = 0;
     CU(h, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -119,7 +122,10 @@ int plan_kernel(uavenv_t *h) {
         h->cells_off = h->tile_bytes;
     }
     h->dyn_smem = (size_t)h->tile_bytes + (h->cells_off >= 0 ? (size_t)cells_bytes : 0);
-    if (h->dyn_smem) CU(h, cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+    if (h->dyn_smem) {
+        CU(h, cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+        CU(h, cudaFuncSetAttribute((const void *)h->kernel_diag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+    }
     int per_sm = 0;
     CU(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)h->kernel, h->threads, h->dyn_smem));
     if (per_sm < 1) return fail(h, UAVENV_ECUDA, "step kernel does not fit on an SM%s");
@@ -157,7 +163,8 @@ int run_env(uavenv_t *h, int mode, const uavenv_in *in, const uavenv_out *out, v
     /* the TMA warp streams the observation's zeros when the plan allows it and the buffer is float4-aligned */
     a.tile_bytes = (h->tiles_ok && a.obs && mode != MODE_CTOR && ((uintptr_t)a.obs & 15) == 0) ? h->tile_bytes : 0;
     a.cells_off = h->cells_off;
-    ((env_kernel_fn)h->kernel)<<<h->grid, h->threads, h->dyn_smem, (cudaStream_t)stream>>>(h->d, a);
+    const env_kernel_fn k = (env_kernel_fn)((a.sinr_all || a.fading_used) ? h->kernel_diag : h->kernel);
+    k<<<h->grid, h->threads, h->dyn_smem, (cudaStream_t)stream>>>(h->d, a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, UAVENV_ECUDA, "env_kernel launch: %s", cudaGetErrorString(e));
     h->launches++;
