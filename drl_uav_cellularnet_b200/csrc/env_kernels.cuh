@@ -38,7 +38,9 @@ __device__ __forceinline__ void obs_add(float *obs_env, long long lin, float v, 
 #ifdef UAVENV_BOUNDS_CHECK
     if (lin < 0 || lin >= n_cells) { atomicOr(err_flags, ERR_BOUNDS); return; }
 #endif
+#ifndef UAVENV_DBG_NO_RED
     atomicAdd(obs_env + lin, v);
+#endif
 }
 enum { CTR_TICK = 0, CTR_EPOCH = 1, CTR_STEP = 2, CTR_AGG = 3, CTR_DEAGG = 4, CTR_STRIDE = 8 };
 
@@ -126,6 +128,47 @@ __device__ __forceinline__ double U_(double lo, double hi, double r) { return __
 constexpr double TWO_PI = 6.283185307179586;
 
 // ---------------------------------------------------------------------------------------------------------
+// L2 eviction-priority hints.  Every step streams hundreds of MB of write-once observation through L2 (evict-first,
+// below) while the environments' own state (a few MB: positions, handover words, cells) is read and written every
+// step: it is tagged evict-last so that it stays L2-resident under the stream instead of being re-fetched from HBM
+// behind the stream's write queue.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#ifndef UAVENV_NO_KEEP_HINT
+__device__ __forceinline__ double ldk(const double *a, uint64_t pol) {
+    double v;
+    asm volatile("ld.global.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldk(const uint32_t *a, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stk(double *a, double v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(a), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stk(uint32_t *a, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+#else
+__device__ __forceinline__ double ldk(const double *a, uint64_t) { return *a; }
+__device__ __forceinline__ uint32_t ldk(const uint32_t *a, uint64_t) { return *a; }
+__device__ __forceinline__ void stk(double *a, double v, uint64_t) { *a = v; }
+__device__ __forceinline__ void stk(uint32_t *a, uint32_t v, uint64_t) { *a = v; }
+#endif
+__device__ __forceinline__ short2 ldk_cell(const int16_t *cells, size_t i, uint64_t pol) {
+    const uint32_t w = ldk(reinterpret_cast<const uint32_t *>(cells) + i, pol);
+    return make_short2((short)(w & 0xffffu), (short)(w >> 16));
+}
+__device__ __forceinline__ void stk_cell(int16_t *cells, size_t i, short2 c, uint64_t pol) {
+    stk(reinterpret_cast<uint32_t *>(cells) + i, (uint32_t)(uint16_t)c.x | ((uint32_t)(uint16_t)c.y << 16), pol);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // One tick of the reference_point_group generator (ue_mobility.py:453-523), split in three so that the step
 // kernel can fuse the per-UE part with the channel pass of the same thread:
 //   mob_group_load   (nG lanes of one warp)  group centres advance, state -> shared memory      :458-459
@@ -156,7 +199,7 @@ __device__ __forceinline__ void mob_group_load(EnvShared &s, const GroupRow &r, 
 // x, y (and thu, the injected direction uniform) are the UE's stored state, loaded by the caller.
 __device__ __forceinline__ short2 mob_ue_move(const DevCfg &c, EnvShared &s, int e, uint32_t genv, int tick,
                                               bool aggregating, const double *inj, int u, double x, double y,
-                                              double thu) {
+                                              double thu, uint64_t keep) {
     const size_t i = (size_t)e * c.nUE + u;
     // direction drawn at the end of the previous tick (:508-510) or at init (:437-439)
     double tu;
@@ -186,9 +229,9 @@ __device__ __forceinline__ short2 mob_ue_move(const DevCfg &c, EnvShared &s, int
     if (x > c.max_xy) { x = __dadd_rn(__dmul_rn(2.0, c.max_xy), -x); s.refl[1][g] = 1; }
     if (y < 0.0) { y = -y; s.refl[2][g] = 1; }
     if (y > c.max_xy) { y = __dadd_rn(__dmul_rn(2.0, c.max_xy), -y); s.refl[3][g] = 1; }
-    c.x[i] = x;
-    c.y[i] = y;
-    if (inj) c.th_u[i] = inj[u];
+    stk(c.x + i, x, keep);
+    stk(c.y + i, y, keep);
+    if (inj) stk(c.th_u + i, inj[u], keep);
     // np.concatenate(...).astype(int): truncation toward zero (mobile_env.py:154-155).  A UE exactly on the far
     // wall would index cell G (IndexError in the reference, ue_mobility.py:186): clamp + flag.
     int cx = (int)x, cy = (int)y;
@@ -274,12 +317,13 @@ __global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_cons
     }
     __syncthreads();
     int agg = agg0, deagg = deagg0;
+    const uint64_t keep = l2_policy_evict_last();
     for (int t = 0; t <= warmup; t++) {
         if (tid < c.nG) mob_group_load(s, group_row_load(c, e, tid), tid);
         __syncthreads();
         for (int u = tid; u < c.nUE; u += blockDim.x) {
             const size_t i = (size_t)e * c.nUE + u;
-            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u, c.x[i], c.y[i], 0.0);
+            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u, c.x[i], c.y[i], 0.0, keep);
             if (t == warmup) reinterpret_cast<short2 *>(c.ue_cell)[(size_t)e * c.nUE + u] = cell;
         }
         mob_phase_advance(c, agg, deagg);
@@ -631,6 +675,29 @@ __device__ __forceinline__ void obs_zero_fill_lsu(float *obs_env, int n_cells) {
     for (int i = threadIdx.x; i < n_cells; i += blockDim.x) __stcs(obs_env + i, 0.f);
 }
 
+// The env's observation as ceil(total / tile_bytes) bulk copies of the zero tile: copy k is issued (and committed as
+// its own bulk group) by lane k % 32 of the calling warp.
+__device__ __forceinline__ void issue_zero_stream(float *obs_env, const float *zero_tile, uint32_t tile_bytes, uint32_t total,
+                                                  int lane, uint32_t *err_flags) {
+    char *dst = reinterpret_cast<char *>(obs_env);
+#ifdef UAVENV_BOUNDS_CHECK
+    if (tile_bytes == 0 || (tile_bytes & 15) || (total & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+        atomicOr(err_flags, ERR_BOUNDS);
+#endif
+#ifndef UAVENV_NO_L2_HINT
+    const uint64_t pol = l2_policy_evict_first();      // write-once stream: first in line for eviction
+    for (uint32_t off = (uint32_t)lane * tile_bytes; off < total; off += 32u * tile_bytes)
+        bulk_store_hint(dst + off, zero_tile, min(tile_bytes, total - off), pol);
+#else
+    for (uint32_t off = (uint32_t)lane * tile_bytes; off < total; off += 32u * tile_bytes)
+        bulk_store(dst + off, zero_tile, min(tile_bytes, total - off));
+#endif
+    bulk_commit();
+}
+#ifdef UAVENV_DBG_NO_ZERO
+#define issue_zero_stream(...) ((void)0)
+#endif
+
 // CTAs per SM the fp32 kernels are compiled for (register budget); the launch plan (uavenv.cu: plan_kernel) keeps
 // (resident CTAs) x (bytes of one env's observation) well inside the 126 MB L2 so that the REDs hit.
 #ifndef UAVENV_MINB
@@ -678,21 +745,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         for (int i = lane; i < (int)(tile_bytes / 16); i += 32) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         fence_proxy_async_smem();          // generic-proxy writes of the tile -> visible to the async proxy
         __syncwarp();
-        const uint32_t total = (uint32_t)n_cells * 4u;
-        char *dst = reinterpret_cast<char *>(obs_env);
-#ifdef UAVENV_BOUNDS_CHECK
-        if (tile_bytes == 0 || (tile_bytes & 15) || (total & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
-            atomicOr(c.err_flags, ERR_BOUNDS);
-#endif
-#ifndef UAVENV_NO_L2_HINT
-        const uint64_t pol = l2_policy_evict_first();      // write-once stream: first in line for eviction
-        for (uint32_t off = (uint32_t)lane * tile_bytes; off < total; off += 32u * tile_bytes)
-            bulk_store_hint(dst + off, zero_tile, min(tile_bytes, total - off), pol);
-#else
-        for (uint32_t off = (uint32_t)lane * tile_bytes; off < total; off += 32u * tile_bytes)
-            bulk_store(dst + off, zero_tile, min(tile_bytes, total - off));
-#endif
-        bulk_commit();
+        issue_zero_stream(obs_env, zero_tile, tile_bytes, (uint32_t)n_cells * 4u, lane, c.err_flags);
     }
     if (warp == WARP_BS) {
         // validate + decode the action (Decimal_to_Base_N, ue_mobility.py:310-336: MSB first, digit 0 <-> BS 0)
@@ -770,23 +823,25 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     }
     double sum_sinr = 0.0;
     int cnt_out = 0, cnt_ho = 0;
+    const uint64_t keep = l2_policy_evict_last();                      // the env's own state stays in L2 under the stream
     if constexpr (!F64 && NB > 4) {
         // ---- more than 4 BSs, fp32: two mappings.  (A) thread = UE: movement; cells staged through shared memory.
         short2 *cells = a.cells_off >= 0 ? reinterpret_cast<short2 *>(dyn_smem + a.cells_off)
                                          : reinterpret_cast<short2 *>(c.ue_cell) + (size_t)e * nUE;
         for (int u = tid; u < nUE; u += NT) {
             const size_t i = (size_t)e * nUE + u;
-            short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
+            short2 cell = ldk_cell(c.ue_cell, i, keep);
             if (incremental) {
                 // the cell of the previous step leaves its association plane
-                obs_add(obs_env, (long long)(((size_t)(1 + (c.ho[i] & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
+                obs_add(obs_env, (long long)(((size_t)(1 + (ldk(c.ho + i, keep) & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
             }
-            if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, c.x[i], c.y[i], inj ? c.th_u[i] : 0.0);
+            if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, ldk(c.x + i, keep), ldk(c.y + i, keep),
+                                               inj ? ldk(c.th_u + i, keep) : 0.0, keep);
             else if (tr) {
                 const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
                 cell = make_short2((short)xy.x, (short)xy.y);
             }
-            if (mode != MODE_CTOR || c.mobility == MOB_TRACE) reinterpret_cast<short2 *>(c.ue_cell)[i] = cell;
+            if (mode != MODE_CTOR || c.mobility == MOB_TRACE) stk_cell(c.ue_cell, i, cell, keep);
             if (a.cells_off >= 0) cells[u] = cell;
             if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
         }
@@ -801,13 +856,13 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             const int u = live ? uu : nUE - 1;
             const size_t i = (size_t)e * nUE + u;
             const short2 cell = cells[u];
-            uint32_t word = mode == MODE_STEP ? c.ho[i] : 0u;
+            uint32_t word = mode == MODE_STEP ? ldk(c.ho + i, keep) : 0u;
             int new_out, did_ho;
             const float curS = full_bs
                 ? ue_channel_quad<NB, DIAG, true>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho)
                 : ue_channel_quad<NB, DIAG, false>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho);
             if (live && q == 0) {
-                c.ho[i] = word;
+                stk(c.ho + i, word, keep);
                 sum_sinr += (double)curS;
                 cnt_out += new_out;
                 cnt_ho += did_ho;
@@ -821,13 +876,14 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     } else {
     for (int u = tid; u < nUE; u += NT) {
         const size_t i = (size_t)e * nUE + u;
-        short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
-        uint32_t word = c.ho[i];
+        short2 cell = ldk_cell(c.ue_cell, i, keep);
+        uint32_t word = ldk(c.ho + i, keep);
         if (incremental) {
             // the cell of the previous step leaves its association plane
             obs_add(obs_env, (long long)(((size_t)(1 + (word & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
         }
-        if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, c.x[i], c.y[i], inj ? c.th_u[i] : 0.0);
+        if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, ldk(c.x + i, keep), ldk(c.y + i, keep),
+                                           inj ? ldk(c.th_u + i, keep) : 0.0, keep);
         else if (tr) {
             const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
             cell = make_short2((short)xy.x, (short)xy.y);
@@ -836,8 +892,8 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         int new_out, did_ho;
         const T curS = ue_channel_pass<NB, F64, DIAG>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
                                                       new_out, did_ho);
-        if (mode != MODE_CTOR || c.mobility == MOB_TRACE) reinterpret_cast<short2 *>(c.ue_cell)[i] = cell;
-        c.ho[i] = word;
+        if (mode != MODE_CTOR || c.mobility == MOB_TRACE) stk_cell(c.ue_cell, i, cell, keep);
+        stk(c.ho + i, word, keep);
         sum_sinr += (double)curS;
         cnt_out += new_out;
         cnt_ho += did_ho;
@@ -867,8 +923,8 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // non-zero cells: UEs on the plane of their (post-handover) serving BS, BSs on plane 0
         for (int u = tid; u < nUE; u += NT) {
             const size_t i = (size_t)e * nUE + u;
-            const short2 cell = reinterpret_cast<const short2 *>(c.ue_cell)[i];
-            const int srv = c.ho[i] & 31;
+            const short2 cell = ldk_cell(c.ue_cell, i, keep);
+            const int srv = ldk(c.ho + i, keep) & 31;
             obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
         }
         if (tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);
