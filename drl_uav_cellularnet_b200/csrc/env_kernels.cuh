@@ -154,7 +154,19 @@ __device__ __forceinline__ void stk(double *a, double v, uint64_t pol) {
 __device__ __forceinline__ void stk(uint32_t *a, uint32_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void stk(float *a, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stk(int32_t *a, int32_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stk(uint8_t *a, uint8_t v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(a), "r"((uint32_t)v), "l"(pol) : "memory");
+}
 #else
+__device__ __forceinline__ void stk(float *a, float v, uint64_t) { *a = v; }
+__device__ __forceinline__ void stk(int32_t *a, int32_t v, uint64_t) { *a = v; }
+__device__ __forceinline__ void stk(uint8_t *a, uint8_t v, uint64_t) { *a = v; }
 __device__ __forceinline__ double ldk(const double *a, uint64_t) { return *a; }
 __device__ __forceinline__ uint32_t ldk(const uint32_t *a, uint64_t) { return *a; }
 __device__ __forceinline__ void stk(double *a, double v, uint64_t) { *a = v; }
@@ -898,10 +910,11 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         cnt_out += new_out;
         cnt_ho += did_ho;
         const int srv = word & 31;
-        if (a.serving) a.serving[i] = (uint8_t)srv;
-        if (a.serving_sinr) reinterpret_cast<T *>(a.serving_sinr)[i] = curS;
-        if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
-        if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
+        // per-call outputs live at the same addresses every step: kept in L2 like the state
+        if (a.serving) stk(a.serving + i, (uint8_t)srv, keep);
+        if (a.serving_sinr) stk(reinterpret_cast<T *>(a.serving_sinr) + i, curS, keep);
+        if (a.ue_xy) stk_cell(a.ue_xy, i, cell, keep);
+        if (a.obs_idx) stk(a.obs_idx + (size_t)e * (nUE + nBS) + u, ((1 + srv) * G + cell.x) * G + cell.y, keep);
         if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
     }
     }
