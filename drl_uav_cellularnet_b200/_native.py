@@ -55,7 +55,7 @@ class Out(C.Structure):
 # every symbol include/uavenv.h declares
 SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
-    "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_state_bytes", "uavenv_state_field",
+    "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
     "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd",
     "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
@@ -82,6 +82,7 @@ def lib():
     for f in (L.uavenv_ctor_pass, L.uavenv_reset, L.uavenv_step):
         f.argtypes = [vp, P(In), P(Out), vp]
     L.uavenv_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.uavenv_coverage_map.argtypes = [vp, vp, vp, vp, vp]
     L.uavenv_state_bytes.argtypes = [vp]
     L.uavenv_state_bytes.restype = C.c_int64
     L.uavenv_state_field.argtypes = [vp, C.c_int32, P(C.c_int64), P(C.c_int64)]

@@ -967,6 +967,72 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Coverage map, LTEChannel.GetSinrInArea (channel.py:411-433): one thread per grid cell.  For every cell (x, y) in
+// [1, G)^2 the downlink SINR from the NEAREST BS (first minimum, :420-422) against all the others, a fresh fading draw
+// per gain (:426,429); row / column 0 stay 0.  Fading: `injected` = the draws in the reference's call order
+// ([E, (G-1)^2, nBS]: per cell the interferers in ascending index order, then the serving BS); else Philox keyed by
+// (env, cell, BS, call number), or none.
+template <bool F64>
+__global__ void __launch_bounds__(CTA_THREADS) coverage_kernel(const __grid_constant__ DevCfg c, const int16_t *__restrict__ bs_xy,
+                                                               const double *__restrict__ injected, uint32_t seq, void *out) {
+    using T = typename Real<F64>::T;
+    __shared__ int sbx[MAX_BS], sby[MAX_BS];
+    const int e = blockIdx.y, G = c.G, nBS = c.nBS;
+    if (threadIdx.x < nBS) {
+        sbx[threadIdx.x] = bs_xy[((size_t)e * nBS + threadIdx.x) * 2];
+        sby[threadIdx.x] = bs_xy[((size_t)e * nBS + threadIdx.x) * 2 + 1];
+    }
+    __syncthreads();
+    const int id = blockIdx.x * CTA_THREADS + threadIdx.x;
+    if (id >= G * G) return;
+    const int x = id / G, y = id - x * G;
+    T *o = reinterpret_cast<T *>(out) + (size_t)e * G * G + id;
+    if (x == 0 || y == 0) { *o = (T)0; return; }                       // dl_sinr = np.zeros(...); range(xMin, xMax) (:413,416)
+    // nearest BS: dist = gridWidth * sqrt(d2) is monotone in the integer d2, so the first minimum of d2 is np.argmin's
+    int srv = 0, best = 0x7fffffff;
+    for (int b = 0; b < nBS; b++) {
+        const int dx = x - sbx[b], dy = y - sby[b], d2 = dx * dx + dy * dy;
+        if (d2 < best) { best = d2; srv = b; }
+    }
+    const int cell = (x - 1) * (G - 1) + (y - 1), cpu = (nBS + 3) >> 2;
+    const uint32_t genv = c.env_offset + (uint32_t)e;
+    const double *inj = injected ? injected + ((size_t)e * (G - 1) * (G - 1) + cell) * nBS : nullptr;
+    T p_interf = (T)0, g_srv = (T)0;
+    T z[4] = {(T)0, (T)0, (T)0, (T)0};
+    int k = 0;                                                          // position in the reference's draw order
+    for (int b = 0; b < nBS; b++) {
+        T fade = (T)0;
+        if (inj) fade = (T)(b == srv ? inj[nBS - 1] : inj[k++]);
+        else if (c.fading != FADE_NONE) {
+            if ((b & 3) == 0) {
+                const Philox4 ph = philox4x32_10(genv, (uint32_t)(cell * cpu + (b >> 2)), seq, DOM_AREA, c.k0, c.k1);
+                if constexpr (F64) normal4_f64(ph, z); else normal4_f32(ph, z);
+            }
+            if constexpr (F64) fade = __dadd_rn(c.sh_mean, __dmul_rn(c.sh_sd, z[b & 3]));
+            else fade = fmaf(c.f_sh_sd, z[b & 3], c.f_sh_mean);
+        }
+        const int dx = x - sbx[b], dy = y - sby[b];
+        T gain;
+        if constexpr (F64) {
+            const double ax = __dadd_rn(__dmul_rn((double)x, c.grid_width), -__dmul_rn((double)sbx[b], c.grid_width));
+            const double ay = __dadd_rn(__dmul_rn((double)y, c.grid_width), -__dmul_rn((double)sby[b], c.grid_width));
+            const double d = sqrt(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));
+            double loss = 0.0;
+            if (d > c.pl_dis) loss = __dadd_rn(c.pl_a, __dmul_rn(c.pl_b, log10(d)));
+            gain = pow(10.0, __dadd_rn(__dadd_rn(__dadd_rn(c.ant_gain, -loss), -fade), -c.eq_loss) / 10.0);
+            if (b == srv) g_srv = gain; else p_interf = __dadd_rn(p_interf, __dmul_rn(c.P, gain));
+        } else {
+            const float qd = c.f_q_scale * (float)(dx * dx + dy * dy);
+            const float loss = qd > c.f_q_min ? fmaf(c.f_loss_k, __log2f(qd), c.f_loss_a) : 0.f;
+            gain = exp2f(((c.f_g0 - loss) - fade) * c.f_exp_k);
+            if (b == srv) g_srv = gain; else p_interf = fmaf((float)c.P, gain, p_interf);
+        }
+    }
+    if constexpr (F64) *o = __dmul_rn(10.0, log10(__dmul_rn(c.P, g_srv) / __dadd_rn(c.N, p_interf)));
+    else *o = c.f_db_k * (__log2f((float)c.P * g_srv) - __log2f(c.f_N + p_interf));
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Diagnostic: a pure zero-fill of `bytes` bytes with the two store mechanisms the step kernel can use, so the
 // write-only HBM ceiling of the box can be measured next to the step kernel (bench.py --write-ceiling).
 //   mode 0: st.global.cs.v4 from all threads;  mode 1: cp.async.bulk shared->global of a zero tile (UBLKCP)

@@ -21,7 +21,8 @@ enum PhiloxDomain : uint32_t {
     DOM_GRP_TF = 7,    // idx = group, seq = tick: a -> theta, b -> g_fl       (ue_mobility.py:516,519)
     DOM_GRP_V = 8,     // idx = group, seq = tick: a -> g_v                    (ue_mobility.py:520)
     DOM_FADING = 9,    // idx = UE*ceil(nBS/4) + b/4, seq = channel pass: 4 normals (channel.py:240)
-    DOM_ACTION = 10    // idx = BS, seq = step: a -> digit (synthetic actions for benchmarks)
+    DOM_ACTION = 10,   // idx = BS, seq = step: a -> digit (synthetic actions for benchmarks)
+    DOM_AREA = 11      // idx = cell*ceil(nBS/4) + b/4, seq = coverage-map call: 4 normals (channel.py:426,429)
 };
 
 struct Philox4 {

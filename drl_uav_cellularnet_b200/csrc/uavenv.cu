@@ -39,6 +39,7 @@ struct uavenv {
     bool ctor_done;
     // launch plan of the persistent step kernel
     void *kernel, *kernel_diag;
+    int64_t area_calls;          // coverage-map call counter (Philox sequence number)
     int threads, grid, tile_bytes, ctas_per_sm, cells_off;
     size_t dyn_smem;
     bool tiles_ok;
@@ -443,6 +444,24 @@ int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, dou
     if (mean_sinr_host && !ms) CU(h, cudaMemcpyAsync(mean_sinr_host, h->h_mean, E * 8, cudaMemcpyDeviceToHost, st));
     if (n_out_host && !no) CU(h, cudaMemcpyAsync(n_out_host, h->h_nout, E * 4, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
+    return UAVENV_OK;
+}
+
+int uavenv_coverage_map(uavenv_t *h, const int16_t *bs_xy_dev, const double *fading_dev, void *out_dev, void *stream) {
+    if (!h || !out_dev) return fail(h, UAVENV_EINVAL, "coverage_map: out_dev is NULL%s");
+    int rc = use_device(h);
+    if (rc) return rc;
+    const int G = h->d.G;
+    const dim3 grid((G * G + CTA_THREADS - 1) / CTA_THREADS, h->d.E);
+    const int16_t *bs = bs_xy_dev ? bs_xy_dev : (const int16_t *)h->bs_xy;
+    const uint32_t seq = (uint32_t)h->area_calls++;
+    if (h->cfg.precision == UAVENV_PREC_FP64_PARITY)
+        coverage_kernel<true><<<grid, CTA_THREADS, 0, (cudaStream_t)stream>>>(h->d, bs, fading_dev, seq, out_dev);
+    else
+        coverage_kernel<false><<<grid, CTA_THREADS, 0, (cudaStream_t)stream>>>(h->d, bs, fading_dev, seq, out_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, UAVENV_ECUDA, "coverage_kernel launch: %s", cudaGetErrorString(e));
+    h->launches++;
     return UAVENV_OK;
 }
 

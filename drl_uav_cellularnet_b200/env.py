@@ -250,6 +250,23 @@ class BatchedMobiEnvironment:
             self._raise(rc, "step_host")
         return self.obs
 
+    def coverage_map(self, bs_xy=None, fading=None) -> torch.Tensor:
+        """LTEChannel.GetSinrInArea (channel.py:411-433) for every env -> [E, G, G] (float32 / float64 per precision).
+        bs_xy: [E, nBS, 2|3] BS cells (default: the current ones); fading: float64 [E, (G-1)^2, nBS] draws in the
+        reference's call order (default: Philox / none per the env's fading mode)."""
+        E, G = self.n_envs, self.grid_n
+        self._keep = []
+        b = None
+        if bs_xy is not None:
+            bb = bs_xy if isinstance(bs_xy, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(bs_xy))
+            b = self._dev(bb[..., :2], torch.int16, (E, self.nBS, 2), "bs_xy")
+        f = self._dev(fading, torch.float64, (E, (G - 1) * (G - 1), self.nBS), "fading") if fading is not None else None
+        out = torch.empty((E, G, G), dtype=torch.float64 if self.precision == "fp64" else torch.float32, device=self.device)
+        rc = self._lib.uavenv_coverage_map(self._h, _ptr(b), _ptr(f), _ptr(out), self._stream())
+        if rc:
+            self._raise(rc, "coverage_map")
+        return out
+
     def check(self) -> int:
         """Sticky device-side error flags since the last check; raises like the reference would
         (ValueError for a bad action, IndexError past the trace end, mobile_env.py:203). Synchronises."""
@@ -314,6 +331,12 @@ class _ChannelView:
     @property
     def current_BS(self):
         return self._env._b.serving[0].cpu().numpy().astype(np.int64)
+
+    def GetSinrInArea(self, bsLoc, fading=None):
+        """channel.py:411-433 (called every 500 evaluation steps, main_test.py:89) -> (G, G) float64"""
+        b = np.asarray(bsLoc)[None, :, :2]
+        f = None if fading is None else np.asarray(fading, dtype=np.float64).reshape(1, -1, self._env.nBS)
+        return self._env._b.coverage_map(b, f)[0].double().cpu().numpy()
 
 
 class MobiEnvironment:

@@ -137,6 +137,13 @@ int uavenv_step(uavenv_t *h, const uavenv_in *in, const uavenv_out *out, void *s
 int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
                      double *mean_sinr_host, int32_t *n_out_host, void *stream);
 
+/* LTEChannel.GetSinrInArea (channel.py:411-433; main_test.py:89): per env the coverage map out[e, x, y] = downlink SINR (dB)
+ * of cell (x, y) from its nearest BS, row / column 0 zero; out is float32 (fast) / float64 (parity) [E, G, G].
+ * bs_xy_dev: int16 [E,nBS,2] BS cells, NULL = the envs' current BS cells.  fading_dev: float64 [E, (G-1)^2, nBS] draws in
+ * the reference's call order (per cell: interferers in ascending index order, then the serving BS), NULL = Philox draws
+ * keyed by (seed, env, cell, BS, number of this call) or none, per cfg.fading. */
+int uavenv_coverage_map(uavenv_t *h, const int16_t *bs_xy_dev, const double *fading_dev, void *out_dev, void *stream);
+
 /* State blob (copy.deepcopy(env), gradient.py:15; checkpoint).  Host buffer; layout in DESIGN.md. Synchronises. */
 int64_t uavenv_state_bytes(const uavenv_t *h);
 /* byte offset / size inside the blob of field 0..7: x f64[E,nUE], y f64[E,nUE], theta_u f64[E,nUE],

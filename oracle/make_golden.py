@@ -20,6 +20,8 @@ Bundles
   ref_mobility.npz      reference_point_group alone, 3000 ticks from RandomState(seed).rand stream: positions.
   ref_bs_move.npz       BS_move + Decimal_to_Base_N over uniform and biased action sequences (lock-up included).
   ref_dense_channel.npz LTEChannel(2048 UE, 32 BS) + BS_move driven directly for 3 steps (config 4 sizes).
+  ref_sinr_area.npz     LTEChannel.GetSinrInArea (the coverage map main_test.py:89 saves) for three BS layouts with all
+                        fading draws recorded.
 """
 from __future__ import annotations
 
@@ -319,11 +321,42 @@ def golden_dense_channel(n_ue=2048, n_bs=32, n_steps=3, seed=31337):
     print("ref_dense_channel: done")
 
 
+def golden_sinr_area(seed=2468):
+    """GetSinrInArea (channel.py:411-433) of the UNMODIFIED reference for three BS layouts (the initial one, one after
+    random moves, one with two BSs equidistant from many cells), with every fading draw recorded in call order."""
+    mods = rl.load_reference()
+    chm = mods["channel"]
+    G = 100
+    rs = np.random.RandomState(seed)
+    layouts = [np.array([[25, 25, 10], [25, 75, 10], [75, 25, 10], [75, 75, 10]]),
+               np.array([[rs.randint(2, G), rs.randint(2, G), 10] for _ in range(4)]),
+               np.array([[40, 50, 10], [60, 50, 10], [50, 40, 10], [50, 60, 10]])]
+    ue = rs.randint(0, G, size=(40, 2))
+    np.random.seed(seed)
+    ch = chm.LTEChannel(40, 4, [1, G, 1, G], ue, layouts[0])
+    outs, draws = [], []
+    for bs in layouts:
+        log = []
+        real_np = chm.np
+        chm.np = _NpProxy(log)
+        try:
+            outs.append(np.array(ch.GetSinrInArea(bs)))
+        finally:
+            chm.np = real_np
+        draws.append(np.concatenate(log))
+        assert draws[-1].size == (G - 1) ** 2 * 4
+    np.savez_compressed(os.path.join(OUT, "ref_sinr_area.npz"), bs=np.stack(layouts).astype(np.int16),
+                        fading=np.stack(draws).astype(np.float64), sinr=np.stack(outs))
+    print("ref_sinr_area: done", outs[0].shape, float(outs[0][1:, 1:].mean()))
+
+
 if __name__ == "__main__":
     if not rl.reference_available():
         sys.exit("reference sources not found; run this in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["trace", "group", "mobility", "bs", "dense"]
+    which = sys.argv[1:] or ["trace", "group", "mobility", "bs", "dense", "area"]
+    if "area" in which:
+        golden_sinr_area()
     if "bs" in which:
         golden_bs_move()
     if "mobility" in which:

@@ -791,3 +791,53 @@ void orc_make_trace(const orc_cfg *c, uint64_t seed, uint32_t env_id, int64_t T,
     free(xy);
     orc_mob_destroy(m);
 }
+
+/* ------------------------------------------------------------------------- */
+/* GetSinrInArea, channel.py:411-433: per cell (x, y) in [xMin, xMax) x [yMin, yMax) = [1, G)^2 (row / column 0 stay 0)
+ * the downlink SINR from the NEAREST BS (np.argmin: first minimum, :420-422), interference from all the other BSs in
+ * ascending index order with a fresh fading draw per gain (:425-427, GetChannelGain :237-247), then the serving gain
+ * with one more draw (:429).  P_interf is a plain sequential Python sum.
+ *   fading != NULL: the draws in the reference's order, (G-1)^2 * nBS values (x outer, y inner; per cell: interferers
+ *                   ascending, then the serving BS)
+ *   fading == NULL and by_bs != NULL: by_bs[cell * nBS + b] is the draw used for BS b at that cell (cell = (x-1)*(G-1)+(y-1))
+ *   both NULL: no fading. */
+void orc_sinr_in_area(const orc_cfg *c, const int64_t *bs_xy, const double *fading, const double *by_bs, double *out) {
+    const int G = c->grid_n, nb = c->n_bs;
+    const double P = pow(10.0, c->p_bs_dbm / 10.0) * 1e-3, N = pow(10.0, c->noise_dbm / 10.0) * 1e-3;
+    memset(out, 0, sizeof(double) * (size_t)G * G);
+    size_t k = 0;
+    for (int x = 1; x < G; x++)
+        for (int y = 1; y < G; y++) {
+            double dist[ORC_MAX_BS];
+            int bs_id = 0;
+            for (int b = 0; b < nb; b++) {
+                double ax = (double)x * c->grid_width - (double)bs_xy[2 * b] * c->grid_width;
+                double ay = (double)y * c->grid_width - (double)bs_xy[2 * b + 1] * c->grid_width;
+                dist[b] = sqrt(ax * ax + ay * ay);
+                if (dist[b] < dist[bs_id]) bs_id = b;
+            }
+            const size_t cell = (size_t)(x - 1) * (G - 1) + (y - 1);
+            double p_interf = 0, g_srv = 0;
+            for (int pass = 0; pass < 2; pass++)
+                for (int b = 0; b < nb; b++) {
+                    if ((pass == 0) == (b == bs_id)) continue;          /* pass 0: interferers, pass 1: serving */
+                    double loss = 0;
+                    if (dist[b] > c->pl_dis) loss = c->pl_a + c->pl_b * log10(dist[b]);
+                    double f = fading ? fading[k++] : (by_bs ? by_bs[cell * nb + b] : 0.0);
+                    double gain = pow(10.0, (c->ant_gain - loss - f - c->eq_loss) / 10.0);
+                    if (pass == 0) p_interf += P * gain; else g_srv = gain;
+                }
+            out[(size_t)x * G + y] = 10 * log10(P * g_srv / (N + p_interf));
+        }
+}
+
+/* the draws the repo's Philox scheme gives GetSinrInArea call number `seq` of env `env_id`: by_bs[cell * nBS + b] */
+void orc_philox_area_fading(const orc_cfg *c, uint64_t seed, uint32_t env_id, uint32_t seq, double *by_bs) {
+    const int G = c->grid_n, nb = c->n_bs, cpu = (nb + 3) / 4;
+    for (int cell = 0; cell < (G - 1) * (G - 1); cell++)
+        for (int q = 0; q < cpu; q++) {
+            double z[4];
+            orc_philox_normal4(seed, env_id, (uint32_t)(cell * cpu + q), seq, 11 /* DOM_AREA */, z);
+            for (int k = 0; k < 4 && 4 * q + k < nb; k++) by_bs[(size_t)cell * nb + 4 * q + k] = c->shadow_mean + c->shadow_sd * z[k];
+        }
+}

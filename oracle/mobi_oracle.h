@@ -152,6 +152,10 @@ void orc_env_set_step_n(orc_env *e, int32_t s);
 double orc_bench_run(const orc_cfg *c, const int32_t *group_sizes, const int32_t *init_bs_xy,
                      int n_envs, int n_steps, uint64_t seed, uint32_t env_id0, double *checksum);
 
+/* ---- GetSinrInArea, channel.py:411-433 (coverage map; see mobi_oracle.c) ---- */
+void orc_sinr_in_area(const orc_cfg *c, const int64_t *bs_xy, const double *fading, const double *by_bs, double *out);
+void orc_philox_area_fading(const orc_cfg *c, uint64_t seed, uint32_t env_id, uint32_t seq, double *by_bs);
+
 /* config-5 sweep helpers (see mobi_oracle.c) */
 int orc_replay_run(const orc_cfg *c, const int32_t *trace, int64_t T, uint64_t seed, uint32_t env_id,
                    const int64_t *actions, int n_steps, int32_t *n_out, int32_t *n_ho, double *reward,

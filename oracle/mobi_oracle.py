@@ -142,6 +142,10 @@ def lib():
     L.orc_replay_run.restype = C.c_int
     L.orc_make_trace.argtypes = [P(OrcCfg), C.c_uint64, C.c_uint32, C.c_int64, P(C.c_int32)]
     L.orc_make_trace.restype = None
+    L.orc_sinr_in_area.argtypes = [P(OrcCfg), P(C.c_int64), P(C.c_double), P(C.c_double), P(C.c_double)]
+    L.orc_sinr_in_area.restype = None
+    L.orc_philox_area_fading.argtypes = [P(OrcCfg), C.c_uint64, C.c_uint32, C.c_uint32, P(C.c_double)]
+    L.orc_philox_area_fading.restype = None
     _lib = L
     return L
 
@@ -384,3 +388,20 @@ def replay_run(cfg: OrcCfg, trace, seed: int, env_id: int, actions):
     if rc:
         raise IndexError("trace exhausted at step %d" % (rc - 1))
     return n_out, n_ho, rew, hsh
+
+
+def sinr_in_area(cfg: OrcCfg, bs_xy, fading=None, by_bs=None):
+    """GetSinrInArea (channel.py:411-433) -> (G, G) float64.  fading: the draws in the reference's order; by_bs: draws per
+    (cell, BS); neither: no fading."""
+    bs = np.ascontiguousarray(np.asarray(bs_xy)[:, :2], dtype=np.int64)
+    f = None if fading is None else np.ascontiguousarray(fading, dtype=np.float64)
+    g = None if by_bs is None else np.ascontiguousarray(by_bs, dtype=np.float64)
+    out = np.empty((cfg.grid_n, cfg.grid_n), dtype=np.float64)
+    lib().orc_sinr_in_area(C.byref(cfg), _ip64(bs), _dp(f), _dp(g), _dp(out))
+    return out
+
+
+def philox_area_fading(cfg: OrcCfg, seed: int, env_id: int, seq: int):
+    out = np.empty(((cfg.grid_n - 1) ** 2, cfg.n_bs), dtype=np.float64)
+    lib().orc_philox_area_fading(C.byref(cfg), seed, env_id, seq, _dp(out))
+    return out

@@ -101,7 +101,8 @@ def test_gradients_match_autograd_of_the_reference_losses(pkg):
     ra_loss = (-(ENTROPY_BETA * entropy + log_prob * td.detach())).mean()
     ga = torch.autograd.grad(ra_loss, [P[k] for k in ("la", "la_b", "la2", "la2_b", "ap", "ap_b")])
     gc = torch.autograd.grad(rc_loss, [P[k] for k in ("lc", "lc_b", "lc2", "lc2_b", "v", "v_b")])
-    assert abs(float(a_loss) - float(ra_loss)) < 1e-5 and abs(float(c_loss) - float(rc_loss)) < 1e-5 * max(1, float(rc_loss))
+    assert abs(float(a_loss) - float(ra_loss.detach())) < 1e-5
+    assert abs(float(c_loss) - float(rc_loss.detach())) < 1e-5 * max(1, float(rc_loss.detach()))
     H, G = net.h, net.g
     mine = [G["W1"][:, :H], G["b1"][:H], G["Wa2"], G["ba2"], G["Wa3"], G["ba3"],
             G["W1"][:, H:], G["b1"][H:], G["Wc2"], G["bc2"], G["Wc3"], G["bc3"]]
@@ -195,3 +196,31 @@ def test_trainer_iterations_run_and_learn_signal(pkg):
         last = float(c_loss)
     assert last < first
     assert env.check() == 0
+
+
+def test_evaluation_driver_writes_the_reference_files(pkg, tmp_path):
+    """main_test.py: load Global_A_PARA.npz, replay a trace with greedy actions, write the nine .npy files."""
+    from oracle import mobi_oracle as orc
+    from drl_uav_cellularnet_b200.a3c import ACNet
+    from drl_uav_cellularnet_b200.evaluate import FILES, load_ac_net, run_test
+    cfg = orc.default_cfg()
+    trace = orc.make_trace(cfg, 3, 0, 40)
+    src = ACNet(50000, 625, "cuda:0", seed=11)
+    npz = str(tmp_path / "Global_A_PARA.npz")
+    src.save_actor_npz(npz)
+    net = load_ac_net(npz, 50000, 625, "cuda:0")
+    out = run_test(net, trace, str(tmp_path / "test"), max_step=30, seed=4)
+    shapes = dict(reward=(31,), decomposed_reward=(31, 2), sinr=(31, 40), time=(31,), outage_fraction=(31,),
+                  ue_location=(31, 40, 2), bs_location=(31, 4, 3), action=(31, 4), sinr_area=(2, 100, 100))
+    for k in FILES:
+        a = np.load(str(tmp_path / "test" / (k + ".npy")))
+        assert a.shape == shapes[k], (k, a.shape)
+        assert np.array_equal(a, out[k])
+    # the recorded episode is what stepping the env with the same greedy policy gives
+    env = pkg.BatchedMobiEnvironment(1, 4, 40, 100, "read_trace", trace=trace, precision="fp64", obs="none", seed=4)
+    env.reset()
+    for t in range(31):
+        _, r, _, info = env.step(net.greedy_action(env.obs_idx))
+        assert float(r[0]) == out["reward"][t]
+        assert np.array_equal(info["ue_xy"][0].cpu().numpy(), out["ue_location"][t]) and np.array_equal(out["ue_location"][t], trace[t])
+        assert np.allclose(out["reward"][t], max(out["decomposed_reward"][t].sum(), -1.0), rtol=0, atol=1e-12)

@@ -258,3 +258,31 @@ def test_full_size_properties_dense(pkg):
         assert int(info["n_ho"].sum()) == int(changed.sum()), t
         prev_srv = info["serving"].clone()
     assert env.check() == 0
+
+
+def test_coverage_map_matches_reference_fixture_and_oracle(pkg, golden_dir):
+    """GetSinrInArea (channel.py:411-433; saved every 500 evaluation steps, main_test.py:89): float64 kernel vs the
+    fixture recorded from the unmodified reference (injected draws, 1e-9 dB), Philox mode vs the oracle with the same
+    counters (fp64 1e-9 dB, fp32 1e-3 dB), and the single-env shim's env.channel.GetSinrInArea."""
+    import os
+    from oracle import mobi_oracle as orc
+    g = np.load(os.path.join(golden_dir, "ref_sinr_area.npz"))
+    n = g["bs"].shape[0]
+    env = pkg.BatchedMobiEnvironment(n, 4, 40, 100, "group", precision="fp64", seed=9)
+    out = env.coverage_map(g["bs"], g["fading"].reshape(n, 99 * 99, 4))
+    assert float(np.abs(_np(out) - g["sinr"]).max()) < 1e-9
+    cfg = orc.default_cfg()
+    for prec, tol in (("fp64", 1e-9), ("fp32", 1e-3)):
+        e2 = pkg.BatchedMobiEnvironment(2, 4, 40, 100, "group", precision=prec, seed=77, env_offset=5)
+        e2.reset()
+        for call in range(2):                                             # the call number is part of the Philox counter
+            got = _np(e2.coverage_map()).astype(np.float64)
+            bs = e2.get_state()["bs_xy"]
+            for e in range(2):
+                want = orc.sinr_in_area(cfg, bs[e], by_bs=orc.philox_area_fading(cfg, 77, 5 + e, call))
+                assert float(np.abs(got[e] - want).max()) < tol, (prec, call, e)
+    single = pkg.MobiEnvironment(4, 40, 100, fading="none")
+    single.reset()
+    m = single.channel.GetSinrInArea(single.bsLoc)
+    assert m.shape == (100, 100) and m.dtype == np.float64 and float(np.abs(m[0]).max()) == 0.0
+    assert float(np.abs(m - orc.sinr_in_area(cfg, single.bsLoc)).max()) < 1e-9

@@ -197,3 +197,17 @@ def test_replay_run_matches_env_stepping(orc):
         assert int(((np.arange(40) + 1) * (o.current_BS + 1)).sum()) == hsh[t], t
     with pytest.raises(IndexError):
         orc.replay_run(cfg, tr, 7, 3, np.zeros(121, dtype=np.int64))
+
+
+def test_sinr_in_area_golden(orc, golden_dir):
+    """GetSinrInArea (channel.py:411-433) of the unmodified reference, three BS layouts (one with equidistant BSs),
+    fading draws replayed in the reference's call order: the oracle's coverage map is bit-identical."""
+    g = _load(golden_dir, "ref_sinr_area.npz")
+    cfg = orc.default_cfg()
+    for i in range(g["bs"].shape[0]):
+        out = orc.sinr_in_area(cfg, g["bs"][i], fading=g["fading"][i])
+        assert np.array_equal(out[0], np.zeros(100)) and np.array_equal(out[:, 0], np.zeros(100))
+        assert np.max(np.abs(out - g["sinr"][i])) <= 1e-12, i
+    # per-(cell, BS) draws are the same numbers in a different layout
+    by_bs = orc.philox_area_fading(cfg, 5, 0, 0)
+    assert by_bs.shape == (99 * 99, 4) and abs(by_bs.std() - 2.0) < 0.02 and abs(by_bs.mean()) < 0.02
