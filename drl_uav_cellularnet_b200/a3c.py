@@ -83,26 +83,32 @@ class ACNet:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def first_layer(self, idx: torch.Tensor) -> torch.Tensor:
+    def first_layer(self, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """relu6(s @ [la | lc] + b) for count vectors given as flat indices idx int32 [M, K] -> [M, 2H]."""
         assert idx.dtype == torch.int32 and idx.is_cuda and idx.is_contiguous() and idx.dim() == 2
         M, K = idx.shape
-        out = torch.empty((M, 2 * self.h), dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty((M, 2 * self.h), dtype=torch.float32, device=self.device)
         rc = self._lib.uavnet_sparse_fwd(_ptr(idx), M, K, self.n_s, _ptr(self.p["W1"]), _ptr(self.p["b1"]), 2 * self.h,
                                          _ptr(out), 1, self._stream())
         if rc:
             raise RuntimeError("uavnet_sparse_fwd failed (%d)" % rc)
         return out
 
-    def forward(self, idx: torch.Tensor, want: str = "both"):
-        """-> (a_prob [M, N_A] or None, v [M] or None, cache)"""
+    def forward(self, idx: torch.Tensor, want: str = "both", out: Optional[dict] = None):
+        """-> (a_prob [M, N_A] or None, v [M] or None, cache).  `out`: preallocated h1 / h2a / prob buffers (the
+        trainer's rollout storage) to write the activations into."""
         H, p = self.h, self.p
-        h1 = self.first_layer(idx)
+        h1 = self.first_layer(idx, None if out is None else out["h1"])
         cache = {"idx": idx, "h1": h1}
         prob = v = None
         if want in ("both", "actor"):
-            h2a = _relu6(torch.addmm(p["ba2"], h1[:, :H], p["Wa2"]))
-            prob = torch.softmax(torch.addmm(p["ba3"], h2a, p["Wa3"]), dim=1)
+            if out is None:
+                h2a = _relu6(torch.addmm(p["ba2"], h1[:, :H], p["Wa2"]))
+                prob = torch.softmax(torch.addmm(p["ba3"], h2a, p["Wa3"]), dim=1)
+            else:
+                h2a = torch.addmm(p["ba2"], h1[:, :H], p["Wa2"], out=out["h2a"]).clamp_(0.0, 6.0)
+                prob = torch.softmax(torch.addmm(p["ba3"], h2a, p["Wa3"]), dim=1, out=out["prob"])
             cache.update(h2a=h2a, prob=prob)
         if want in ("both", "critic"):
             h2c = _relu6(torch.addmm(p["bc2"], h1[:, H:], p["Wc2"]))
@@ -123,6 +129,11 @@ class ACNet:
     def value(self, idx: torch.Tensor) -> torch.Tensor:
         return self.forward(idx, "critic")[1]
 
+    def _ones(self, m: int) -> torch.Tensor:
+        if getattr(self, "_ones_buf", None) is None or self._ones_buf.numel() < m:
+            self._ones_buf = torch.ones(m, dtype=torch.float32, device=self.device)
+        return self._ones_buf[:m]
+
     # ---- losses + gradients (main.py:64-78), accumulated into self.grad -------------------------------------
     def accumulate_grads(self, idx: torch.Tensor, a_his: torch.Tensor, v_target: torch.Tensor, saved: Optional[dict] = None):
         """Adds d(a_loss)/d(actor params) and d(c_loss)/d(critic params) for the batch to ``self.grad``;
@@ -139,6 +150,7 @@ class ACNet:
         h2c = _relu6(torch.addmm(p["bc2"], h1[:, H:], p["Wc2"]))
         v = torch.addmm(p["bc3"], h2c, p["Wc3"]).squeeze(1)
         td = (v_target - v).contiguous()
+        ones = self._ones(M)                                              # bias gradients = column sums = ones^T @ d (GEMV)
         # -- critic --
         c_loss = (td * td).mean()
         dv = (-2.0 / M) * td                                              # [M]
@@ -146,7 +158,7 @@ class ACNet:
         g["bc3"].add_(dv.sum())
         dpre2c = (dv.unsqueeze(1) * p["Wc3"].t()) * ((h2c > 0) & (h2c < 6))
         g["Wc2"].addmm_(h1[:, H:].t(), dpre2c)
-        g["bc2"].add_(dpre2c.sum(0))
+        g["bc2"].addmv_(dpre2c.t(), ones)
         dpre1 = torch.empty_like(h1)
         torch.mm(dpre2c, p["Wc2"].t(), out=dpre1[:, H:])
         # -- actor: d(a_loss)/d(logits) in one fused pass over the softmax output --
@@ -158,13 +170,13 @@ class ACNet:
             raise RuntimeError("uavnet_actor_head_bwd failed (%d)" % rc)
         a_loss = loss_row.mean()
         g["Wa3"].addmm_(h2a.t(), dz)
-        g["ba3"].add_(dz.sum(0))
+        g["ba3"].addmv_(dz.t(), ones)
         dpre2a = (dz @ p["Wa3"].t()) * ((h2a > 0) & (h2a < 6))
         g["Wa2"].addmm_(h1[:, :H].t(), dpre2a)
-        g["ba2"].add_(dpre2a.sum(0))
+        g["ba2"].addmv_(dpre2a.t(), ones)
         torch.mm(dpre2a, p["Wa2"].t(), out=dpre1[:, :H])
         dpre1.mul_((h1 > 0) & (h1 < 6))
-        g["b1"].add_(dpre1.sum(0))
+        g["b1"].addmv_(dpre1.t(), ones)
         rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
                                          self._stream())
         if rc:
@@ -242,10 +254,8 @@ class A3CTrainer:
         env, net = self.env, self.net
         for t in range(self.T):
             self.buf_idx[t].copy_(env.obs_idx)
-            prob, _, c = net.forward(self.buf_idx[t], "actor")
-            self.buf_h1[t].copy_(c["h1"])
-            self.buf_h2a[t].copy_(c["h2a"])
-            self.buf_prob[t].copy_(prob)
+            prob, _, _ = net.forward(self.buf_idx[t], "actor",
+                                     out={"h1": self.buf_h1[t], "h2a": self.buf_h2a[t], "prob": self.buf_prob[t]})
             a = torch.multinomial(prob, 1, generator=self.gen).squeeze(1)    # np.random.choice(p=a_prob), main.py:165-169,195
             _, r, done, _ = env.step(a)                                      # main.py:198
             self.buf_a[t].copy_(a)

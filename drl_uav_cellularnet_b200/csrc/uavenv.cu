@@ -243,6 +243,8 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
     const int E = cfg->n_envs, nBS = cfg->n_bs, nUE = cfg->n_ue, G = cfg->grid_n, nG = cfg->n_groups;
     if (E < 1 || nBS < 1 || nBS > UAVENV_MAX_BS || nUE < 1 || G < 4 || G > 32767)
         return fail(h, UAVENV_EINVAL, "bad sizes (need n_envs>=1, 1<=n_bs<=32, n_ue>=1, 4<=grid_n<=32767)%s");
+    if ((int64_t)(nBS + 1) * G * G >= 0x7fffffffLL)
+        return fail(h, UAVENV_EINVAL, "(n_bs+1)*grid_n^2 must stay below 2^31 (observation cells are indexed with int32)%s");
     if (cfg->n_act < 2 || cfg->n_act > 9) return fail(h, UAVENV_EINVAL, "n_act must be in [2,9]%s");
     if (cfg->mobility != UAVENV_MOB_GROUP && cfg->mobility != UAVENV_MOB_TRACE)
         return fail(h, UAVENV_EINVAL, "mobility model not defined%s");   /* sys.exit at mobile_env.py:91 */
