@@ -43,6 +43,14 @@ def _relu6(x):
     return torch.clamp(x, 0.0, 6.0)
 
 
+class _ForeignCudaBuffer:
+    """float32 device memory owned by libuavenv (uavnet_p2p_alloc), exposed to torch through __cuda_array_interface__"""
+
+    def __init__(self, ptr: int, n: int):
+        self.ptr, self.n = ptr, n
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2, "strides": None}
+
+
 class ACNet:
     """Actor 50000->200->200->N_A softmax and critic 50000->200->200->1 (main.py:143-156) on sparse observations.
 
@@ -185,11 +193,88 @@ class ACNet:
 
     # ---- the "push" (main.py:85-86,159-160): all-reduce + both RMSProp optimisers in one pass ---------------
     def apply_grads(self, lr: float = LR_A, world_size: int = 1):
-        """grad /= world_size (after the caller's all-reduce), RMSProp step on every parameter, grad = 0."""
+        """grad /= world_size (after the caller's all-reduce), RMSProp step on every parameter, grad = 0.
+        With ``enable_p2p()`` the all-reduce is not needed: one peer-memory kernel does reduce + step + broadcast."""
+        if getattr(self, "_p2p", None):
+            return self._apply_grads_p2p(lr)
         rc = self._lib.uavnet_rmsprop(_ptr(self.flat), _ptr(self.grad), _ptr(self.ms), self.n_flat, lr, RMS_DECAY, RMS_EPS,
                                       1.0 / world_size, 1, self._stream())
         if rc:
             raise RuntimeError("uavnet_rmsprop failed (%d)" % rc)
+
+    # ---- the push over NVLink peer memory: reduce-scatter + RMSProp + all-gather in ONE kernel per rank ----------
+    def enable_p2p(self):
+        """Move the flat parameter / gradient buffers into IPC-shareable allocations, exchange their handles between
+        the ranks' processes and map every peer's buffers (cudaIpcOpenMemHandle, peer access over NVLink).  From then
+        on ``apply_grads`` runs ``uavnet_p2p_rmsprop`` instead of all-reduce + ``uavnet_rmsprop``.  World size 1 (no
+        process group) takes the same code path with the local buffers only."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        if world > 8:
+            raise ValueError("uavnet_p2p_rmsprop supports up to 8 ranks")
+        vp = C.c_void_p
+        bufs, handles = [], []
+        for _ in range(2):                                            # 0: gradients, 1: parameters
+            ptr, hdl = vp(), (C.c_uint8 * 64)()
+            rc = self._lib.uavnet_p2p_alloc(self.n_flat * 4, C.byref(ptr), C.cast(hdl, vp))
+            if rc:
+                raise RuntimeError("uavnet_p2p_alloc failed (%d)" % rc)
+            bufs.append(_ForeignCudaBuffer(ptr.value, self.n_flat))
+            handles.append(bytes(hdl))
+        grad = torch.as_tensor(bufs[0], device=self.device)
+        flat = torch.as_tensor(bufs[1], device=self.device)
+        flat.copy_(self.flat)
+        grad.copy_(self.grad)
+        self.flat, self.grad = flat, grad
+        self.p = {k: self.flat[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        self.g = {k: self.grad[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        gptrs, pptrs, opened = (vp * world)(), (vp * world)(), []
+        gptrs[rank], pptrs[rank] = bufs[0].ptr, bufs[1].ptr
+        if world > 1:
+            every = [None] * world
+            dist.all_gather_object(every, handles)
+            for r in range(world):
+                if r == rank:
+                    continue
+                for which, table in ((0, gptrs), (1, pptrs)):
+                    peer = vp()
+                    rc = self._lib.uavnet_p2p_open(C.cast(C.c_char_p(every[r][which]), vp), C.byref(peer))
+                    if rc:
+                        raise RuntimeError("uavnet_p2p_open failed (%d): no peer access to rank %d" % (rc, r))
+                    table[r] = peer.value
+                    opened.append(peer.value)
+            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+            dist.barrier()
+        self._p2p = {"bufs": bufs, "gptrs": gptrs, "pptrs": pptrs, "opened": opened, "rank": rank, "world": world}
+        return self
+
+    def _apply_grads_p2p(self, lr: float):
+        import torch.distributed as dist
+        q = self._p2p
+        if q["world"] > 1:
+            dist.all_reduce(self._flag)               # every rank's gradients are complete (stream-ordered)
+        rc = self._lib.uavnet_p2p_rmsprop(q["gptrs"], q["pptrs"], _ptr(self.ms), self.n_flat, q["rank"], q["world"], lr,
+                                          RMS_DECAY, RMS_EPS, self._stream())
+        if rc:
+            raise RuntimeError("uavnet_p2p_rmsprop failed (%d)" % rc)
+        if q["world"] > 1:
+            dist.all_reduce(self._flag)               # every rank's slice has reached every copy of the parameters
+
+    def close_p2p(self):
+        q = getattr(self, "_p2p", None)
+        if not q:
+            return
+        torch.cuda.synchronize(self.device)
+        for ptr in q["opened"]:
+            self._lib.uavnet_p2p_close(C.c_void_p(ptr))
+        flat, grad = self.flat.clone(), self.grad.clone()
+        self.flat, self.grad = flat, grad
+        self.p = {k: self.flat[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        self.g = {k: self.grad[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        for b in q["bufs"]:
+            self._lib.uavnet_p2p_free(C.c_void_p(b.ptr))
+        self._p2p = None
 
     # ---- on-disk format of the reference (main.py:264-269,314; main_test.py:15-25) ---------------------------
     def actor_params(self):
@@ -273,7 +358,7 @@ class A3CTrainer:
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()
-            if world > 1:
+            if world > 1 and not getattr(net, "_p2p", None):
                 torch.distributed.all_reduce(net.grad)                       # the gradient push, summed over ranks
         net.apply_grads(LR_A, world)
         self.updates += 1

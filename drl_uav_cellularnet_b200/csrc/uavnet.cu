@@ -8,6 +8,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace uavk {
 
@@ -130,6 +131,43 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
     }
 }
 
+// The gradient push fused with the optimiser over NVLink peer memory (main.py:85-86,159-163 on `world` GPUs):
+// rank r owns elements [lo, hi) of the flat buffers.  For each of them it sums the gradient over ALL ranks with peer
+// loads (reduce-scatter), applies the RMSProp step once, and stores the new parameter -- and a zero gradient -- into
+// EVERY rank's buffers with peer stores (all-gather).  One pass over 1/world of the parameters per GPU, no staging
+// buffer, no separate optimiser kernel.  The caller orders it between two tiny stream-ordered collectives.
+struct PeerPtrs {
+    float *g[UAVNET_MAX_PEERS];
+    float *p[UAVNET_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(NET_THREADS) p2p_rmsprop_kernel(const __grid_constant__ PeerPtrs pp, float *__restrict__ ms,
+                                                                  long long lo4, long long hi4, int rank, int world, float lr,
+                                                                  float decay, float eps, float gs) {
+    const float od = 1.f - decay;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = lo4 + (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < hi4; i += (long long)gridDim.x * NET_THREADS) {
+        float4 acc = zero;
+        // fixed summation order (rank 0, 1, ...): every rank computes bit-identical parameters
+        for (int r = 0; r < world; r++) {
+            const float4 v = reinterpret_cast<const float4 *>(pp.g[r])[i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        acc.x *= gs; acc.y *= gs; acc.z *= gs; acc.w *= gs;
+        float4 mv = reinterpret_cast<float4 *>(ms)[i], pv = reinterpret_cast<const float4 *>(pp.p[rank])[i];
+        mv.x = decay * mv.x + od * acc.x * acc.x; mv.y = decay * mv.y + od * acc.y * acc.y;
+        mv.z = decay * mv.z + od * acc.z * acc.z; mv.w = decay * mv.w + od * acc.w * acc.w;
+        pv.x -= lr * acc.x / sqrtf(mv.x + eps); pv.y -= lr * acc.y / sqrtf(mv.y + eps);
+        pv.z -= lr * acc.z / sqrtf(mv.z + eps); pv.w -= lr * acc.w / sqrtf(mv.w + eps);
+        reinterpret_cast<float4 *>(ms)[i] = mv;
+        for (int j = 0; j < world; j++) {
+            const int r = (rank + j) % world;                 // start with the local copy, then walk the peers
+            reinterpret_cast<float4 *>(pp.p[r])[i] = pv;
+            reinterpret_cast<float4 *>(pp.g[r])[i] = zero;
+        }
+    }
+}
+
 int grid_for(long long items) {
     long long g = (items + NET_THREADS - 1) / NET_THREADS;
     const long long cap = 148LL * 8 * 4;          // a few waves of 8 CTAs per SM; the kernels are grid-stride
@@ -168,6 +206,59 @@ int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *
     if (!prob || !a_his || !td || !dz || M < 1 || A < 1) return UAVNET_EINVAL;
     actor_head_bwd_kernel<<<grid_for(M * 32), NET_THREADS, 0, (cudaStream_t)stream>>>(
         prob, (const long long *)a_his, td, M, A, beta, 1.0f / (float)M, dz, loss_row);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_p2p_alloc(int64_t bytes, void **dev_ptr, uint8_t *handle64) {
+    if (bytes < 16 || !dev_ptr || !handle64) return UAVNET_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); return UAVNET_ECUDA; }
+    cudaIpcMemHandle_t hdl;
+    if (cudaMemset(p, 0, (size_t)bytes) != cudaSuccess || cudaIpcGetMemHandle(&hdl, p) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(p);
+        return UAVNET_ECUDA;
+    }
+    memcpy(handle64, &hdl, 64);
+    *dev_ptr = p;
+    return UAVNET_OK;
+}
+
+int uavnet_p2p_open(const uint8_t *handle64, void **dev_ptr) {
+    if (!handle64 || !dev_ptr) return UAVNET_EINVAL;
+    cudaIpcMemHandle_t hdl;
+    memcpy(&hdl, handle64, 64);
+    if (cudaIpcOpenMemHandle(dev_ptr, hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return UAVNET_ECUDA; }
+    return UAVNET_OK;
+}
+
+int uavnet_p2p_close(void *dev_ptr) {
+    if (!dev_ptr) return UAVNET_EINVAL;
+    return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_p2p_free(void *dev_ptr) {
+    if (!dev_ptr) return UAVNET_EINVAL;
+    return cudaFree(dev_ptr) == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_local, int64_t n, int32_t rank, int32_t world,
+                       float lr, float decay, float eps, void *stream) {
+    if (!grads || !params || !ms_local || n < 4 || (n & 3) || world < 1 || world > UAVNET_MAX_PEERS || rank < 0 || rank >= world)
+        return UAVNET_EINVAL;
+    PeerPtrs pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int r = 0; r < world; r++) {
+        if (!grads[r] || !params[r] || !aligned16(grads[r]) || !aligned16(params[r])) return UAVNET_EINVAL;
+        pp.g[r] = grads[r];
+        pp.p[r] = params[r];
+    }
+    const long long n4 = n >> 2, per4 = (n4 + world - 1) / world;
+    const long long lo4 = (long long)rank * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
+    if (lo4 >= hi4) return UAVNET_OK;
+    p2p_rmsprop_kernel<<<grid_for(hi4 - lo4), NET_THREADS, 0, (cudaStream_t)stream>>>(pp, ms_local, lo4, hi4, rank, world, lr,
+                                                                                     decay, eps, 1.0f / (float)world);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 

@@ -20,6 +20,7 @@ extern "C" {
 #endif
 
 enum { UAVNET_OK = 0, UAVNET_EINVAL = -1, UAVNET_ECUDA = -2 };
+#define UAVNET_MAX_PEERS 8
 
 /* First dense layer on a sparse count vector (tf.layers.dense(self.s, 200, relu6), main.py:147,151):
  *   out[m, :] = act( b + sum_k W[idx[m,k], :] ),  act = relu6 (relu6 != 0) or identity.
@@ -45,6 +46,25 @@ int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *
  * over n float32 elements (any n; 16-byte aligned pointers). */
 int uavnet_rmsprop(float *param, float *grad, float *ms, int64_t n, float lr, float decay, float eps, float grad_scale,
                    int32_t zero_grad, void *stream);
+
+/* ---- the gradient push fused with the optimiser over NVLink peer memory (one process per GPU) ----
+ * uavnet_p2p_alloc: cudaMalloc (zeroed) + its 64-byte CUDA IPC handle, to be exchanged between the ranks' processes;
+ * uavnet_p2p_open: map a peer's buffer into this process (peer access over NVLink / NVSwitch is enabled lazily);
+ * uavnet_p2p_close / uavnet_p2p_free: unmap a peer's buffer / free an own one. */
+int uavnet_p2p_alloc(int64_t bytes, void **dev_ptr, uint8_t *handle64);
+int uavnet_p2p_open(const uint8_t *handle64, void **dev_ptr);
+int uavnet_p2p_close(void *dev_ptr);
+int uavnet_p2p_free(void *dev_ptr);
+
+/* One kernel per rank instead of all-reduce + optimiser (main.py:85-86,159-163): rank `rank` of `world` owns the slice
+ * [rank*ceil(n/4/world)*4, ...) of the flat buffers; for each owned element it sums grads[r][i] over all ranks (peer
+ * loads, fixed order), scales by 1/world, applies the TF1 RMSProp step with its local slot ms_local[i], and stores the
+ * new parameter into params[r][i] and 0 into grads[r][i] of EVERY rank (peer stores).  grads / params: HOST arrays of
+ * `world` device pointers (own buffer at index `rank`, peers' mapped with uavnet_p2p_open); n a multiple of 4.
+ * The caller must order the launch after all ranks finished writing their gradients and order the next use of the
+ * parameters after all ranks' launches completed (two stream-ordered collectives, e.g. 4-byte all-reduces). */
+int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_local, int64_t n, int32_t rank, int32_t world,
+                       float lr, float decay, float eps, void *stream);
 
 #ifdef __cplusplus
 }

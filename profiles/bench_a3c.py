@@ -20,6 +20,7 @@ ap.add_argument("--envs", type=int, default=8192)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--tf32", action="store_true", help="TF32 tensor-core GEMMs for the dense layers (default: fp32 SIMT)")
+ap.add_argument("--p2p", action="store_true", help="gradient push as one peer-memory kernel (uavnet_p2p_rmsprop) instead of NCCL all-reduce + RMSProp")
 ap.add_argument("--graph", action="store_true", help="also time the iteration replayed as one CUDA graph")
 args = ap.parse_args()
 rank, world, local = udist.world()
@@ -30,6 +31,8 @@ if args.tf32:
     torch.backends.cuda.matmul.allow_tf32 = True
 env = BatchedMobiEnvironment(args.envs, 4, 40, 100, "group", seed=2026, obs="none", env_offset=rank * args.envs, device=local)
 net = ACNet(env.observation_space_dim, env.action_space_dim, dev)
+if args.p2p:
+    net.enable_p2p()
 tr = A3CTrainer(env, net, seed=100 + rank)
 
 
@@ -65,5 +68,5 @@ if rank == 0:
     print(json.dumps({"metric": "A3C env-steps/sec (rollout + update)", "value": steps / (ms_iter * 1e-3), "n_gpus": world,
                       "envs_per_gpu": args.envs, "rollout_steps": tr.T, "ms_per_iteration": ms_iter, "ms_rollout": ms_roll,
                       "ms_update": ms_upd, "ms_env_step_no_obs": ms_env, "ms_per_iteration_graph": ms_graph,
-                      "value_graph": steps / (ms_graph * 1e-3) if args.graph else None, "tf32": bool(args.tf32), "params": net.n_params,
+                      "value_graph": steps / (ms_graph * 1e-3) if args.graph else None, "tf32": bool(args.tf32), "p2p_push": bool(args.p2p), "params": net.n_params,
                       "allreduce_bytes": net.n_flat * 4 if world > 1 else 0}))

@@ -224,3 +224,45 @@ def test_evaluation_driver_writes_the_reference_files(pkg, tmp_path):
         assert float(r[0]) == out["reward"][t]
         assert np.array_equal(info["ue_xy"][0].cpu().numpy(), out["ue_location"][t]) and np.array_equal(out["ue_location"][t], trace[t])
         assert np.allclose(out["reward"][t], max(out["decomposed_reward"][t].sum(), -1.0), rtol=0, atol=1e-12)
+
+
+def test_p2p_push_world_size_1_equals_rmsprop(pkg):
+    """The peer-memory push (uavnet_p2p_rmsprop) with a single rank is the plain RMSProp step: same parameters bit for
+    bit, gradients zeroed, buffers living in IPC-shareable allocations wrapped as torch tensors."""
+    from drl_uav_cellularnet_b200.a3c import ACNet
+    a, b = ACNet(2000, 25, "cuda:0", hidden=8), ACNet(2000, 25, "cuda:0", hidden=8)
+    b.enable_p2p()
+    assert torch.equal(a.flat, b.flat)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for it in range(3):
+        grad = torch.randn(a.n_flat, device="cuda", generator=g) * 1e-2
+        a.grad.copy_(grad)
+        b.grad.copy_(grad)
+        a.apply_grads(1e-4)
+        b.apply_grads(1e-4)
+        assert torch.equal(a.flat, b.flat) and torch.equal(a.ms, b.ms), it
+        assert float(b.grad.abs().max()) == 0.0
+    idx = _rand_idx(4, 6, 2000, 0)
+    assert torch.equal(a.forward(idx)[0], b.forward(idx)[0])           # the views follow the new buffers
+    b.close_p2p()
+    assert torch.equal(a.flat, b.flat)
+
+
+def test_p2p_push_two_ranks_equals_nccl_path():
+    """Needs two GPUs (skipped on the single-GPU box): torchrun profiles/p2p_check.py -- the fused peer-memory push
+    gives bit-identical parameters to NCCL all-reduce + RMSProp at 2 ranks, on every rank."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", os.path.join(root, "profiles", "p2p_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["world"] == 2 and d["max_abs_param_diff_vs_nccl_path"] == 0.0
+    assert d["param_sums_per_rank"][0] == d["param_sums_per_rank"][1]
