@@ -311,6 +311,7 @@ def main():
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_env,
                          "kernel": "uavk::env_kernel<%d,false,256>" % (4 if N_BS <= 4 else 8 if N_BS <= 8 else 16 if N_BS <= 16 else 32),
                          "launch_us": per_launch_s * 1e6,
+                         "frac_of_spec_8tbs": (achieved / 8000.0) if achieved else None,
                          "write_only_ceiling_gbs": 7030.0,
                          "write_only_ceiling_note": "64 KB bulk-copy zero fill on this pool's B200, profiles/r1/NOTES.md"},
             "clocks": clocks,

@@ -38,9 +38,7 @@ __device__ __forceinline__ void obs_add(float *obs_env, long long lin, float v, 
 #ifdef UAVENV_BOUNDS_CHECK
     if (lin < 0 || lin >= n_cells) { atomicOr(err_flags, ERR_BOUNDS); return; }
 #endif
-#ifndef UAVENV_DBG_NO_RED
     atomicAdd(obs_env + lin, v);
-#endif
 }
 enum { CTR_TICK = 0, CTR_EPOCH = 1, CTR_STEP = 2, CTR_AGG = 3, CTR_DEAGG = 4, CTR_STRIDE = 8 };
 
@@ -706,9 +704,6 @@ __device__ __forceinline__ void issue_zero_stream(float *obs_env, const float *z
 #endif
     bulk_commit();
 }
-#ifdef UAVENV_DBG_NO_ZERO
-#define issue_zero_stream(...) ((void)0)
-#endif
 
 // CTAs per SM the fp32 kernels are compiled for (register budget); the launch plan (uavenv.cu: plan_kernel) keeps
 // (resident CTAs) x (bytes of one env's observation) well inside the 126 MB L2 so that the REDs hit.
