@@ -309,7 +309,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "peak_source": peak_src, "algorithmic_bytes_per_env_step": b_env,
-                         "kernel": "uavk::env_kernel<%d,false,256>" % (4 if N_BS <= 4 else 8 if N_BS <= 8 else 16 if N_BS <= 16 else 32),
+                         "kernel": "uavk::env_kernel<%d,false,256,false>" % (4 if N_BS <= 4 else 8 if N_BS <= 8 else 16 if N_BS <= 16 else 32),
                          "launch_us": per_launch_s * 1e6,
                          "frac_of_spec_8tbs": (achieved / 8000.0) if achieved else None,
                          "write_only_ceiling_gbs": 7030.0,
