@@ -286,3 +286,58 @@ def test_coverage_map_matches_reference_fixture_and_oracle(pkg, golden_dir):
     m = single.channel.GetSinrInArea(single.bsLoc)
     assert m.shape == (100, 100) and m.dtype == np.float64 and float(np.abs(m[0]).max()) == 0.0
     assert float(np.abs(m - orc.sinr_in_area(cfg, single.bsLoc)).max()) < 1e-9
+
+
+@pytest.mark.parametrize("nBS,nUE,G,groups", [(1, 1, 4, [1]), (2, 3, 6, [2, 1]), (5, 33, 12, [11, 11, 11]), (27, 64, 40, [16] * 4)])
+def test_edge_sizes_match_oracle(pkg, nBS, nUE, G, groups):
+    """Smallest legal sizes, ragged groups, a BS count that leaves lanes of the 4-BSs-per-lane mapping empty and the
+    largest BS count whose joint action still fits int64 (5**27 < 2**63): float64 kernels vs the oracle, everything
+    exact, with both action encodings (joint int64 and per-BS digits) giving the same step."""
+    from oracle import mobi_oracle as orc
+    seed, E, T = 17, 3, 12
+    layout = [[1 + (b * 7) % (G - 1), 1 + (b * 3) % (G - 1)] for b in range(nBS)]
+    kw = dict(seed=seed, precision="fp64", group_sizes=groups, init_bs_xy=layout)
+    a = pkg.BatchedMobiEnvironment(E, nBS, nUE, G, "group", **kw)
+    b = pkg.BatchedMobiEnvironment(E, nBS, nUE, G, "group", **kw)
+    cfg = orc.default_cfg(nBS, nUE, G, len(groups))
+    oenvs = [orc.OracleEnv(cfg, group_sizes=groups, init_bs_xy=layout, seed=seed, env_id=e) for e in range(E)]
+    want = np.stack([o.reset() for o in oenvs])
+    assert np.array_equal(_np(a.reset()).astype(np.float64), want)
+    b.reset()
+    rs = np.random.RandomState(3)
+    for t in range(T):
+        digits = rs.randint(0, 5, size=(E, nBS)).astype(np.uint8)
+        joint = np.array([int(sum(int(d) * 5 ** (nBS - 1 - k) for k, d in enumerate(row))) for row in digits], dtype=np.int64)
+        oa, ra, da, ia = a.step(digits)
+        ob, rb, db, ib = b.step(joint)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(ia["serving"], ib["serving"]), t
+        for e in range(E):
+            s, r, d, oi = oenvs[e].step(digits[e].astype(np.int32))
+            assert np.array_equal(_np(oa[e]).astype(np.float64), s), (t, e)
+            assert np.array_equal(_np(ia["serving"][e]), oenvs[e].current_BS), (t, e)
+            assert int(ia["n_out"][e]) == oi["n_out"] and int(ia["n_ho"][e]) == oi["n_ho"], (t, e)
+            assert abs(float(ra[e]) - r) <= 1e-9 * max(1.0, abs(r)), (t, e)
+    assert a.check() == 0 and b.check() == 0
+
+
+def test_joint_action_overflow_and_bad_sizes_are_rejected(pkg):
+    """5**nBS overflows int64 beyond 27 BSs (mobile_env.py:104): joint actions are then rejected by validation (every
+    int64 decodes to at most 27 digits, so any value is a legal action for nBS > 27 only through per-BS digits);
+    impossible sizes fail at creation with ValueError."""
+    env = pkg.BatchedMobiEnvironment(2, 28, 56, 60, "group", seed=1, group_sizes=[14] * 4,
+                                     init_bs_xy=[[2 + 2 * b, 2 + (b * 5) % 50] for b in range(28)])
+    env.reset()
+    env.step(np.array([2 ** 62, 5], dtype=np.int64))                   # decodes into 28 base-5 digits: legal
+    assert env.check() == 0
+    env.step(np.array([-1, 5], dtype=np.int64))
+    with pytest.raises(ValueError):
+        env.check()
+    for bad in (dict(nBS=33), dict(nBS=0), dict(nUE=0), dict(grid_n=3)):
+        args = dict(nBS=4, nUE=40, grid_n=100)
+        args.update(bad)
+        with pytest.raises(ValueError):
+            pkg.BatchedMobiEnvironment(2, args["nBS"], args["nUE"], args["grid_n"], "group")
+    with pytest.raises(ValueError):
+        pkg.BatchedMobiEnvironment(2, 4, 40, 100, "group", group_sizes=[10, 10, 10])      # does not sum to nUE
+    with pytest.raises(ValueError):
+        pkg.BatchedMobiEnvironment(1, 32, 64, 9000, "group", obs="none")                   # (nBS+1) G^2 >= 2^31
