@@ -260,6 +260,7 @@ class ACNet:
             raise RuntimeError("uavnet_p2p_rmsprop failed (%d)" % rc)
         if q["world"] > 1:
             dist.all_reduce(self._flag)               # every rank's slice has reached every copy of the parameters
+            self.grad.zero_()                         # ... and nobody reads this rank's gradients any more
 
     def close_p2p(self):
         q = getattr(self, "_p2p", None)

@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
 // The gradient push fused with the optimiser over NVLink peer memory (main.py:85-86,159-163 on `world` GPUs):
 // rank r owns elements [lo, hi) of the flat buffers.  For each of them it sums the gradient over ALL ranks with peer
 // loads (reduce-scatter), applies the RMSProp step once, and stores the new parameter -- and a zero gradient -- into
-// EVERY rank's buffers with peer stores (all-gather).  One pass over 1/world of the parameters per GPU, no staging
-// buffer, no separate optimiser kernel.  The caller orders it between two tiny stream-ordered collectives.
+// rank's parameter buffer with peer stores (all-gather).  One pass over 1/world of the parameters per GPU, no staging
+// buffer, no separate optimiser kernel.  The caller orders it between two tiny stream-ordered collectives and clears
+// its own gradient buffer afterwards (the peers read the other slices of it during their launches).
 struct PeerPtrs {
     float *g[UAVNET_MAX_PEERS];
     float *p[UAVNET_MAX_PEERS];
@@ -163,8 +164,9 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_rmsprop_kernel(const __grid_c
         for (int j = 0; j < world; j++) {
             const int r = (rank + j) % world;                 // start with the local copy, then walk the peers
             reinterpret_cast<float4 *>(pp.p[r])[i] = pv;
-            reinterpret_cast<float4 *>(pp.g[r])[i] = zero;
         }
+        reinterpret_cast<float4 *>(pp.g[rank])[i] = zero;     // own slice of the own gradient buffer; the rest of it is
+                                                              // still being read by the peers: the caller clears it later
     }
 }
 

@@ -59,7 +59,8 @@ int uavnet_p2p_free(void *dev_ptr);
 /* One kernel per rank instead of all-reduce + optimiser (main.py:85-86,159-163): rank `rank` of `world` owns the slice
  * [rank*ceil(n/4/world)*4, ...) of the flat buffers; for each owned element it sums grads[r][i] over all ranks (peer
  * loads, fixed order), scales by 1/world, applies the TF1 RMSProp step with its local slot ms_local[i], and stores the
- * new parameter into params[r][i] and 0 into grads[r][i] of EVERY rank (peer stores).  grads / params: HOST arrays of
+ * new parameter into params[r][i] of EVERY rank (peer stores).  Only the owned slice of the own gradient buffer is
+ * zeroed; the caller clears the rest after the second collective (the peers are still reading it).  grads / params: HOST arrays of
  * `world` device pointers (own buffer at index `rank`, peers' mapped with uavnet_p2p_open); n a multiple of 4.
  * The caller must order the launch after all ranks finished writing their gradients and order the next use of the
  * parameters after all ranks' launches completed (two stream-ordered collectives, e.g. 4-byte all-reduces). */
