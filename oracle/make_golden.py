@@ -20,6 +20,8 @@ Bundles
   ref_mobility.npz      reference_point_group alone, 3000 ticks from RandomState(seed).rand stream: positions.
   ref_bs_move.npz       BS_move + Decimal_to_Base_N over uniform and biased action sequences (lock-up included).
   ref_dense_channel.npz LTEChannel(2048 UE, 32 BS) + BS_move driven directly for 3 steps (config 4 sizes).
+  ref_free_running_stats.npz  8 free-running reference envs x 1500 steps (group mode, random actions): per-env means of
+                        reward, new outages, handovers, serving SINR, UE movement, outage fraction (distributional pin).
   ref_sinr_area.npz     LTEChannel.GetSinrInArea (the coverage map main_test.py:89 saves) for three BS layouts with all
                         fading draws recorded.
 """
@@ -321,6 +323,36 @@ def golden_dense_channel(n_ue=2048, n_bs=32, n_steps=3, seed=31337):
     print("ref_dense_channel: done")
 
 
+def golden_free_running_stats(n_envs=8, n_steps=1500, seed=1357):
+    """Free-running reference (its own unseeded-style numpy stream, here seeded) in group mode with uniform random
+    actions: per-env summary statistics of the quantities the step produces.  The Philox-driven implementations cannot
+    reproduce the reference's Mersenne-Twister stream draw for draw, so this bundle pins them
+    DISTRIBUTIONALLY: tests compare the oracle's / kernels' statistics over the same number of env-steps."""
+    stats = np.zeros((n_envs, 6))
+    for e in range(n_envs):
+        np.random.seed(seed + e)
+        env = rl.make_reference_env(4, 40, 100, "group")
+        rs = np.random.RandomState(seed + 100 + e)
+        with rl.quiet_stdout():
+            env.reset()
+            prev_cell = np.array(env.ueLoc[:, :2])
+            acc = np.zeros(6)
+            for t in range(n_steps):
+                before = np.array(env.channel.current_BS)
+                s, r, d, info = env.step(int(rs.randint(625)))
+                after = np.array(env.channel.current_BS)
+                cell = np.array(env.ueLoc[:, :2])
+                acc += (r, -info[0][1] * 40, float(np.sum(before != after)), float(np.mean(env.channel.current_BS_sinr)),
+                        float(np.mean(np.abs(cell - prev_cell))), float(np.mean(env.channel.current_BS_sinr <= 0)))
+                prev_cell = cell
+        stats[e] = acc / n_steps
+        print("  free-running env", e, stats[e])
+    np.savez_compressed(os.path.join(OUT, "ref_free_running_stats.npz"), stats=stats, n_steps=n_steps, seed=seed,
+                        columns=np.array(["reward", "new_outages_per_step", "handovers_per_step", "mean_serving_sinr_db",
+                                          "mean_abs_cell_move_per_axis", "fraction_ue_in_outage"]))
+    print("ref_free_running_stats: done", stats.mean(0))
+
+
 def golden_sinr_area(seed=2468):
     """GetSinrInArea (channel.py:411-433) of the UNMODIFIED reference for three BS layouts (the initial one, one after
     random moves, one with two BSs equidistant from many cells), with every fading draw recorded in call order."""
@@ -354,7 +386,9 @@ if __name__ == "__main__":
     if not rl.reference_available():
         sys.exit("reference sources not found; run this in the build container")
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["trace", "group", "mobility", "bs", "dense", "area"]
+    which = sys.argv[1:] or ["trace", "group", "mobility", "bs", "dense", "area", "stats"]
+    if "stats" in which:
+        golden_free_running_stats()
     if "area" in which:
         golden_sinr_area()
     if "bs" in which:

@@ -841,3 +841,36 @@ void orc_philox_area_fading(const orc_cfg *c, uint64_t seed, uint32_t env_id, ui
             for (int k = 0; k < 4 && 4 * q + k < nb; k++) by_bs[(size_t)cell * nb + 4 * q + k] = c->shadow_mean + c->shadow_sd * z[k];
         }
 }
+
+/* ------------------------------------------------------------------------- */
+/* Group-mode run of one env (the training path, env.step): reset, then n_steps steps with the given joint actions,
+ * Philox mobility + fading of env `env_id`, reset again whenever done (main.py:188-190).  Records per step the
+ * new-outage count, handover count, reward and the serving-BS hash, and a hash of the UE cells
+ * (sum_u (u+1) * (x_u * G + y_u + 1)). */
+int orc_group_run(const orc_cfg *c, uint64_t seed, uint32_t env_id, const int64_t *actions, int n_steps,
+                  int32_t *n_out, int32_t *n_ho, double *reward, int64_t *serving_hash, int64_t *cell_hash) {
+    int32_t gs[64];
+    int32_t digits[ORC_MAX_BS];
+    for (int g = 0; g < c->n_groups; g++) gs[g] = c->n_ue / c->n_groups + (g < c->n_ue % c->n_groups ? 1 : 0);
+    orc_env *e = orc_env_create(c, gs, NULL, ORC_MOB_GROUP, ORC_FADE_PHILOX, seed, env_id, 200);
+    orc_env_ctor_channel(e, NULL);
+    orc_env_reset(e, NULL, NULL, NULL);
+    for (int s = 0; s < n_steps; s++) {
+        orc_step_out o;
+        orc_action_digits(actions[s], c->n_act, c->n_bs, digits);
+        orc_env_step(e, digits, NULL, NULL, NULL, &o);
+        n_out[s] = o.n_out; n_ho[s] = o.n_ho; reward[s] = o.reward;
+        const orc_chan *ch = orc_env_chan(e);
+        const int64_t *xy = orc_env_ue_xy(e);
+        int64_t h = 0, hc = 0;
+        for (int u = 0; u < c->n_ue; u++) {
+            h += (int64_t)(u + 1) * (ch->cur[u] + 1);
+            hc += (int64_t)(u + 1) * (xy[2 * u] * c->grid_n + xy[2 * u + 1] + 1);
+        }
+        serving_hash[s] = h;
+        cell_hash[s] = hc;
+        if (o.done) orc_env_reset(e, NULL, NULL, NULL);
+    }
+    orc_env_destroy(e);
+    return 0;
+}

@@ -161,6 +161,8 @@ int orc_replay_run(const orc_cfg *c, const int32_t *trace, int64_t T, uint64_t s
                    const int64_t *actions, int n_steps, int32_t *n_out, int32_t *n_ho, double *reward,
                    int64_t *serving_hash);
 void orc_make_trace(const orc_cfg *c, uint64_t seed, uint32_t env_id, int64_t T, int32_t *trace_out);
+int orc_group_run(const orc_cfg *c, uint64_t seed, uint32_t env_id, const int64_t *actions, int n_steps,
+                  int32_t *n_out, int32_t *n_ho, double *reward, int64_t *serving_hash, int64_t *cell_hash);
 
 #ifdef __cplusplus
 }

@@ -142,6 +142,9 @@ def lib():
     L.orc_replay_run.restype = C.c_int
     L.orc_make_trace.argtypes = [P(OrcCfg), C.c_uint64, C.c_uint32, C.c_int64, P(C.c_int32)]
     L.orc_make_trace.restype = None
+    L.orc_group_run.argtypes = [P(OrcCfg), C.c_uint64, C.c_uint32, P(C.c_int64), C.c_int, P(C.c_int32), P(C.c_int32),
+                                P(C.c_double), P(C.c_int64), P(C.c_int64)]
+    L.orc_group_run.restype = C.c_int
     L.orc_sinr_in_area.argtypes = [P(OrcCfg), P(C.c_int64), P(C.c_double), P(C.c_double), P(C.c_double)]
     L.orc_sinr_in_area.restype = None
     L.orc_philox_area_fading.argtypes = [P(OrcCfg), C.c_uint64, C.c_uint32, C.c_uint32, P(C.c_double)]
@@ -405,3 +408,14 @@ def philox_area_fading(cfg: OrcCfg, seed: int, env_id: int, seq: int):
     out = np.empty(((cfg.grid_n - 1) ** 2, cfg.n_bs), dtype=np.float64)
     lib().orc_philox_area_fading(C.byref(cfg), seed, env_id, seq, _dp(out))
     return out
+
+
+def group_run(cfg: OrcCfg, seed: int, env_id: int, actions):
+    """One group-mode env (Philox), reset + len(actions) steps (+ reset on done):
+    (n_out, n_ho, reward, serving_hash, cell_hash) per step."""
+    act = np.ascontiguousarray(actions, dtype=np.int64)
+    n = len(act)
+    n_out, n_ho = np.empty(n, dtype=np.int32), np.empty(n, dtype=np.int32)
+    rew, hsh, hc = np.empty(n, dtype=np.float64), np.empty(n, dtype=np.int64), np.empty(n, dtype=np.int64)
+    lib().orc_group_run(C.byref(cfg), seed, env_id, _ip64(act), n, _ip32(n_out), _ip32(n_ho), _dp(rew), _ip64(hsh), _ip64(hc))
+    return n_out, n_ho, rew, hsh, hc

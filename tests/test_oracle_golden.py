@@ -211,3 +211,32 @@ def test_sinr_in_area_golden(orc, golden_dir):
     # per-(cell, BS) draws are the same numbers in a different layout
     by_bs = orc.philox_area_fading(cfg, 5, 0, 0)
     assert by_bs.shape == (99 * 99, 4) and abs(by_bs.std() - 2.0) < 0.02 and abs(by_bs.mean()) < 0.02
+
+
+def test_free_running_statistics_match_reference(orc, golden_dir):
+    """Distributional pin: the Philox-driven oracle cannot follow the reference's Mersenne-Twister
+    stream draw for draw, so its free-running statistics -- reward, new outages, handovers, serving SINR, UE movement,
+    outage fraction per step, group mode, uniform random actions -- are compared with 8 free-running runs of the
+    unmodified reference (tests/golden/ref_free_running_stats.npz).  Tolerance: 4 standard errors of the difference of
+    the two means (between-env spread of both samples)."""
+    g = _load(golden_dir, "ref_free_running_stats.npz")
+    ref, T = g["stats"], int(g["n_steps"])
+    n_envs = 24
+    cfg = orc.default_cfg()
+    got = np.zeros((n_envs, 6))
+    for e in range(n_envs):
+        o = orc.OracleEnv(cfg, seed=4321, env_id=e)
+        o.reset()
+        rs = np.random.RandomState(50 + e)
+        prev = o.ue_xy.copy()
+        acc = np.zeros(6)
+        for t in range(T):
+            s, r, d, info = o.step(int(rs.randint(625)), want_state=False)
+            cell = o.ue_xy
+            sinr = o.current_BS_sinr
+            acc += (r, info["n_out"], info["n_ho"], sinr.mean(), np.abs(cell - prev).mean(), (sinr <= 0).mean())
+            prev = cell.copy()
+        got[e] = acc / T
+    for k, name in enumerate(g["columns"]):
+        se = np.sqrt(ref[:, k].var(ddof=1) / len(ref) + got[:, k].var(ddof=1) / n_envs)
+        assert abs(ref[:, k].mean() - got[:, k].mean()) < 4 * se, (str(name), ref[:, k].mean(), got[:, k].mean(), se)
