@@ -72,7 +72,7 @@ struct DevCfg {
     float f_db_k;           // 10 log10(2):             10 log10(x) = f_db_k * log2(x)
     float f_N, f_sh_mean, f_sh_sd;
     // persistent state (device)
-    double *x, *y;          // [E,nUE] float UE positions                      (ue_mobility.py:434-435)
+    double2 *xy;            // [E,nUE] float UE positions (x, y): one 16-byte load (ue_mobility.py:434-435)
     double *th_u;           // [E,nUE] last theta uniform, injected-mobility runs only
     double *grp;            // [E,6,nG] g_x g_y g_fl g_v g_cos g_sin           (ue_mobility.py:442-448)
     int32_t *ctr;           // [E,8]   tick, epoch, step_n, aggregating, deaggregating
@@ -152,6 +152,14 @@ __device__ __forceinline__ void stk(double *a, double v, uint64_t pol) {
 __device__ __forceinline__ void stk(uint32_t *a, uint32_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(a), "r"(v), "l"(pol) : "memory");
 }
+__device__ __forceinline__ double2 ldk(const double2 *a, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void stk(double2 *a, double2 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void stk(float *a, float v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
 }
@@ -165,6 +173,8 @@ __device__ __forceinline__ void stk(uint8_t *a, uint8_t v, uint64_t pol) {
 __device__ __forceinline__ void stk(float *a, float v, uint64_t) { *a = v; }
 __device__ __forceinline__ void stk(int32_t *a, int32_t v, uint64_t) { *a = v; }
 __device__ __forceinline__ void stk(uint8_t *a, uint8_t v, uint64_t) { *a = v; }
+__device__ __forceinline__ double2 ldk(const double2 *a, uint64_t) { return *a; }
+__device__ __forceinline__ void stk(double2 *a, double2 v, uint64_t) { *a = v; }
 __device__ __forceinline__ double ldk(const double *a, uint64_t) { return *a; }
 __device__ __forceinline__ uint32_t ldk(const uint32_t *a, uint64_t) { return *a; }
 __device__ __forceinline__ void stk(double *a, double v, uint64_t) { *a = v; }
@@ -239,8 +249,7 @@ __device__ __forceinline__ short2 mob_ue_move(const DevCfg &c, EnvShared &s, int
     if (x > c.max_xy) { x = __dadd_rn(__dmul_rn(2.0, c.max_xy), -x); s.refl[1][g] = 1; }
     if (y < 0.0) { y = -y; s.refl[2][g] = 1; }
     if (y > c.max_xy) { y = __dadd_rn(__dmul_rn(2.0, c.max_xy), -y); s.refl[3][g] = 1; }
-    stk(c.x + i, x, keep);
-    stk(c.y + i, y, keep);
+    stk(c.xy + i, make_double2(x, y), keep);
     if (inj) stk(c.th_u + i, inj[u], keep);
     // np.concatenate(...).astype(int): truncation toward zero (mobile_env.py:154-155).  A UE exactly on the far
     // wall would index cell G (IndexError in the reference, ue_mobility.py:186): clamp + flag.
@@ -308,8 +317,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_cons
     for (int u = tid; u < c.nUE; u += blockDim.x) {
         double a, b;
         philox_uniform2(c.k0, c.k1, genv, (uint32_t)u, 0u, DOM_INIT_XY, a, b);
-        c.x[(size_t)e * c.nUE + u] = U_(0.0, c.max_xy, a);
-        c.y[(size_t)e * c.nUE + u] = U_(0.0, c.max_xy, b);
+        c.xy[(size_t)e * c.nUE + u] = make_double2(U_(0.0, c.max_xy, a), U_(0.0, c.max_xy, b));
     }
     if (tid < c.nG) {
         double *grp = c.grp + (size_t)e * 6 * c.nG;
@@ -333,7 +341,8 @@ __global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_cons
         __syncthreads();
         for (int u = tid; u < c.nUE; u += blockDim.x) {
             const size_t i = (size_t)e * c.nUE + u;
-            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u, c.x[i], c.y[i], 0.0, keep);
+            const double2 p = c.xy[i];
+            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u, p.x, p.y, 0.0, keep);
             if (t == warmup) reinterpret_cast<short2 *>(c.ue_cell)[(size_t)e * c.nUE + u] = cell;
         }
         mob_phase_advance(c, agg, deagg);
@@ -842,8 +851,10 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 // the cell of the previous step leaves its association plane
                 obs_add(obs_env, (long long)(((size_t)(1 + (ldk(c.ho + i, keep) & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
             }
-            if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, ldk(c.x + i, keep), ldk(c.y + i, keep),
-                                               inj ? ldk(c.th_u + i, keep) : 0.0, keep);
+            if (group_tick) {
+                const double2 p = ldk(c.xy + i, keep);
+                cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, inj ? ldk(c.th_u + i, keep) : 0.0, keep);
+            }
             else if (tr) {
                 const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
                 cell = make_short2((short)xy.x, (short)xy.y);
@@ -889,9 +900,10 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             // the cell of the previous step leaves its association plane
             obs_add(obs_env, (long long)(((size_t)(1 + (word & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
         }
-        if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, ldk(c.x + i, keep), ldk(c.y + i, keep),
-                                           inj ? ldk(c.th_u + i, keep) : 0.0, keep);
-        else if (tr) {
+        if (group_tick) {
+            const double2 p = ldk(c.xy + i, keep);
+            cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, inj ? ldk(c.th_u + i, keep) : 0.0, keep);
+        } else if (tr) {
             const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
             cell = make_short2((short)xy.x, (short)xy.y);
         }

@@ -16,7 +16,7 @@ using namespace uavk;
 
 namespace {
 
-enum { F_X = 0, F_Y, F_THU, F_GRP, F_CTR, F_BS, F_CELL, F_HO, F_COUNT };
+enum { F_XY = 0, F_THU, F_GRP, F_CTR, F_BS, F_CELL, F_HO, F_COUNT };
 
 struct Field {
     void **dev;
@@ -32,7 +32,7 @@ struct uavenv {
     char err[512];
     int64_t launches;
     // device allocations
-    void *x, *y, *th_u, *grp, *ctr, *bs_xy, *ue_cell, *ho, *init_bs, *ue_group, *trace, *err_flags;
+    void *xy, *th_u, *grp, *ctr, *bs_xy, *ue_cell, *ho, *init_bs, *ue_group, *trace, *err_flags;
     // step_host staging (device)
     void *h_action, *h_reward, *h_mean, *h_nout, *h_done;
     Field fields[F_COUNT];
@@ -292,7 +292,7 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
 
     const int64_t nu = (int64_t)E * nUE;
     Field f[F_COUNT] = {
-        {&h->x, nu * 8}, {&h->y, nu * 8}, {&h->th_u, nu * 8}, {&h->grp, (int64_t)E * 6 * nG * 8},
+        {&h->xy, nu * 16}, {&h->th_u, nu * 8}, {&h->grp, (int64_t)E * 6 * nG * 8},
         {&h->ctr, (int64_t)E * CTR_STRIDE * 4}, {&h->bs_xy, (int64_t)E * nBS * 4}, {&h->ue_cell, nu * 4}, {&h->ho, nu * 4}};
     for (int i = 0; i < F_COUNT; i++) {
         h->fields[i] = f[i];
@@ -338,7 +338,7 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
         free(gr);
         CU(h, ce);
     }
-    d.x = (double *)h->x; d.y = (double *)h->y; d.th_u = (double *)h->th_u; d.grp = (double *)h->grp;
+    d.xy = (double2 *)h->xy; d.th_u = (double *)h->th_u; d.grp = (double *)h->grp;
     d.ctr = (int32_t *)h->ctr; d.bs_xy = (int16_t *)h->bs_xy; d.ue_cell = (int16_t *)h->ue_cell; d.ho = (uint32_t *)h->ho;
     d.init_bs = (const int16_t *)h->init_bs; d.ue_group = (const uint8_t *)h->ue_group;
     d.trace = nullptr; d.trace_T = 0; d.trace_per_env = 0;
@@ -370,7 +370,7 @@ void uavenv_destroy(uavenv_t *h) {
     int cur = -1;
     cudaGetDevice(&cur);
     if (cur != h->device) cudaSetDevice(h->device);
-    void *p[] = {h->x, h->y, h->th_u, h->grp, h->ctr, h->bs_xy, h->ue_cell, h->ho, h->init_bs, h->ue_group,
+    void *p[] = {h->xy, h->th_u, h->grp, h->ctr, h->bs_xy, h->ue_cell, h->ho, h->init_bs, h->ue_group,
                  h->trace, h->err_flags, h->h_action, h->h_reward, h->h_mean, h->h_nout, h->h_done};
     for (void *q : p) if (q) cudaFree(q);
     delete h;

@@ -31,7 +31,7 @@ _MOBILITY = {"group": N.MOB_GROUP, "read_trace": N.MOB_TRACE}
 _FADING = {"philox": N.FADE_PHILOX, "injected": N.FADE_INJECTED, "none": N.FADE_NONE}
 _PRECISION = {"fp32": N.PREC_FP32_FAST, "fp64": N.PREC_FP64_PARITY}
 _OBS = {"none": N.OBS_NONE, "f32": N.OBS_F32, "f32_incremental": N.OBS_F32_INCREMENTAL}
-_STATE_FIELDS = [("x", np.float64), ("y", np.float64), ("theta_u", np.float64), ("group", np.float64),
+_STATE_FIELDS = [("xy", np.float64), ("theta_u", np.float64), ("group", np.float64),
                  ("counters", np.int32), ("bs_xy", np.int16), ("ue_cell", np.int16), ("ho_word", np.uint32)]
 
 
@@ -290,7 +290,7 @@ class BatchedMobiEnvironment:
     # -- state blob (copy.deepcopy(env) in gradient.py:15; checkpoint) -------------------------------------
     def _field_shapes(self):
         E, nBS, nUE, nG = self.n_envs, self.nBS, self.nUE, self.cfg.n_groups
-        return [(E, nUE), (E, nUE), (E, nUE), (E, 6, nG), (E, 8), (E, nBS, 2), (E, nUE, 2), (E, nUE)]
+        return [(E, nUE, 2), (E, nUE), (E, 6, nG), (E, 8), (E, nBS, 2), (E, nUE, 2), (E, nUE)]
 
     def get_state(self) -> dict:
         n = self._lib.uavenv_state_bytes(self._h)

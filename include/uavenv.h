@@ -146,7 +146,7 @@ int uavenv_coverage_map(uavenv_t *h, const int16_t *bs_xy_dev, const double *fad
 
 /* State blob (copy.deepcopy(env), gradient.py:15; checkpoint).  Host buffer; layout in DESIGN.md. Synchronises. */
 int64_t uavenv_state_bytes(const uavenv_t *h);
-/* byte offset / size inside the blob of field 0..7: x f64[E,nUE], y f64[E,nUE], theta_u f64[E,nUE],
+/* byte offset / size inside the blob of field 0..6: xy f64[E,nUE,2] (float UE positions), theta_u f64[E,nUE],
  * group f64[E,6,nG] (g_x g_y g_fl g_v g_cos g_sin), counters i32[E,8] (tick, epoch, step_n, aggregating,
  * deaggregating), bs_xy i16[E,nBS,2], ue_cell i16[E,nUE,2], ho_word u32[E,nUE] */
 int uavenv_state_field(const uavenv_t *h, int32_t field, int64_t *offset, int64_t *bytes);

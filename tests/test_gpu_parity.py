@@ -128,7 +128,7 @@ def test_group_mobility_matches_reference_fixture(pkg, orc, golden_dir):
     k += 5 * ng
     env = pkg.BatchedMobiEnvironment(1, 4, 40, 100, "group", fading="injected", precision="fp64", warmup_ticks=-1)
     st = env.get_state()
-    st["x"][0], st["y"][0], st["theta_u"][0] = x0, y0, th0
+    st["xy"][0, :, 0], st["xy"][0, :, 1], st["theta_u"][0] = x0, y0, th0
     st["group"][0] = np.stack([gx, gy, gfl, gv, np.cos(gth), np.sin(gth)])
     st["counters"][0, :5] = [0, 0, 0, 200, 100]                    # tick, epoch, step_n, aggregating, deaggregating
     env.set_state(st)
@@ -143,7 +143,7 @@ def test_group_mobility_matches_reference_fixture(pkg, orc, golden_dir):
         k += used
         if tick % 25 == 0 or tick == 200:
             s = env.get_state()
-            assert np.max(np.abs(s["x"][0] - xy[:, 0])) < 1e-9 and np.max(np.abs(s["y"][0] - xy[:, 1])) < 1e-9, tick
+            assert np.max(np.abs(s["xy"][0] - xy)) < 1e-9, tick
     assert k == u.size
     assert np.array_equal(env.get_state()["ue_cell"][0], g["ue0"])
     # constructor channel pass, then reset + steps with the recorded fading / uniforms
