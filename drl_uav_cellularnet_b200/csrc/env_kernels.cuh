@@ -843,15 +843,17 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     int cnt_out = 0, cnt_ho = 0;
     const uint64_t keep = l2_policy_evict_last();                      // the env's own state stays in L2 under the stream
     if constexpr (!F64 && NB > 4) {
-        // ---- more than 4 BSs, fp32: two mappings.  (A) thread = UE: movement; cells staged through shared memory.
-        short2 *cells = a.cells_off >= 0 ? reinterpret_cast<short2 *>(dyn_smem + a.cells_off)
-                                         : reinterpret_cast<short2 *>(c.ue_cell) + (size_t)e * nUE;
+        // ---- more than 4 BSs, fp32: two mappings.  (A) thread = UE: movement.  Each UE's (cell, handover word) is
+        // staged through shared memory (coalesced HBM loads here, no global load left in pass B); if the env's UEs do
+        // not fit, HBM is the staging area.
+        int2 *stage = a.cells_off >= 0 ? reinterpret_cast<int2 *>(dyn_smem + a.cells_off) : nullptr;
         for (int u = tid; u < nUE; u += NT) {
             const size_t i = (size_t)e * nUE + u;
             short2 cell = ldk_cell(c.ue_cell, i, keep);
+            const uint32_t word0 = (mode == MODE_STEP || incremental) ? ldk(c.ho + i, keep) : 0u;
             if (incremental) {
                 // the cell of the previous step leaves its association plane
-                obs_add(obs_env, (long long)(((size_t)(1 + (ldk(c.ho + i, keep) & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
+                obs_add(obs_env, (long long)(((size_t)(1 + (word0 & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
             }
             if (group_tick) {
                 const double2 p = ldk(c.xy + i, keep);
@@ -862,7 +864,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 cell = make_short2((short)xy.x, (short)xy.y);
             }
             if (mode != MODE_CTOR || c.mobility == MOB_TRACE) stk_cell(c.ue_cell, i, cell, keep);
-            if (a.cells_off >= 0) cells[u] = cell;
+            if (stage) stage[u] = make_int2((int)((uint32_t)(uint16_t)cell.x | ((uint32_t)(uint16_t)cell.y << 16)), (int)word0);
             if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
         }
         __syncthreads();
@@ -875,14 +877,24 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             const bool live = uu < nUE;
             const int u = live ? uu : nUE - 1;
             const size_t i = (size_t)e * nUE + u;
-            const short2 cell = cells[u];
-            uint32_t word = mode == MODE_STEP ? ldk(c.ho + i, keep) : 0u;
+            short2 cell;
+            uint32_t word;
+            if (stage) {
+                const int2 sv = stage[u];
+                cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
+                word = (uint32_t)sv.y;
+            } else {
+                cell = ldk_cell(c.ue_cell, i, keep);
+                word = ldk(c.ho + i, keep);
+            }
+            if (mode != MODE_STEP) word = 0u;
             int new_out, did_ho;
             const float curS = full_bs
                 ? ue_channel_quad<NB, DIAG, true>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho)
                 : ue_channel_quad<NB, DIAG, false>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho);
             if (live && q == 0) {
                 stk(c.ho + i, word, keep);
+                if (stage) stage[u].y = (int)word;                     // the count REDs below read (cell, serving) from here
                 sum_sinr += (double)curS;
                 cnt_out += new_out;
                 cnt_ho += did_ho;
@@ -943,10 +955,19 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     if (warp == WARP_GRP && group_tick) mob_group_finish(c, s, e, genv, tick - 1, inj, lane);
     if (full_obs) {
         // non-zero cells: UEs on the plane of their (post-handover) serving BS, BSs on plane 0
+        const int2 *stage = (!F64 && NB > 4 && a.cells_off >= 0) ? reinterpret_cast<const int2 *>(dyn_smem + a.cells_off) : nullptr;
         for (int u = tid; u < nUE; u += NT) {
             const size_t i = (size_t)e * nUE + u;
-            const short2 cell = ldk_cell(c.ue_cell, i, keep);
-            const int srv = ldk(c.ho + i, keep) & 31;
+            short2 cell;
+            int srv;
+            if (stage) {
+                const int2 sv = stage[u];
+                cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
+                srv = sv.y & 31;
+            } else {
+                cell = ldk_cell(c.ue_cell, i, keep);
+                srv = ldk(c.ho + i, keep) & 31;
+            }
             obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
         }
         if (tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);

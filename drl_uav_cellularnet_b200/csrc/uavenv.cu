@@ -111,7 +111,7 @@ int plan_kernel(uavenv_t *h) {
     h->tile_bytes = h->tiles_ok ? (int)tile : 0;
     /* fp32 kernels with more than 4 BSs stage the env's UE cells in shared memory between the movement pass
      * (thread = UE) and the channel pass (lane = 4 BSs of a UE); if they do not fit, HBM is the staging area */
-    const int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 4 + 127) & ~(int64_t)127) : 0;
+    const int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 8 + 127) & ~(int64_t)127) : 0;   /* (cell, handover word) per UE */
     h->cells_off = -1;
     if (cells_bytes && cells_bytes <= 32768) {
         if (h->tile_bytes + cells_bytes + (int64_t)fa.sharedSizeBytes + 1024 > dev_smem) {
