@@ -847,18 +847,35 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // staged through shared memory (coalesced HBM loads here, no global load left in pass B); if the env's UEs do
         // not fit, HBM is the staging area.
         int2 *stage = a.cells_off >= 0 ? reinterpret_cast<int2 *>(dyn_smem + a.cells_off) : nullptr;
+        // software-pipelined: the next UE's state is requested before the current one is computed
+        const bool need_word = mode == MODE_STEP || incremental;
+        size_t i_n = (size_t)e * nUE + tid;
+        short2 cell_n = make_short2(0, 0);
+        uint32_t word_n = 0u;
+        double2 p_n = make_double2(0.0, 0.0);
+        double thu_n = 0.0;
+        if (tid < nUE) {
+            cell_n = ldk_cell(c.ue_cell, i_n, keep);
+            if (need_word) word_n = ldk(c.ho + i_n, keep);
+            if (group_tick) { p_n = ldk(c.xy + i_n, keep); if (inj) thu_n = ldk(c.th_u + i_n, keep); }
+        }
         for (int u = tid; u < nUE; u += NT) {
-            const size_t i = (size_t)e * nUE + u;
-            short2 cell = ldk_cell(c.ue_cell, i, keep);
-            const uint32_t word0 = (mode == MODE_STEP || incremental) ? ldk(c.ho + i, keep) : 0u;
+            const size_t i = i_n;
+            short2 cell = cell_n;
+            const uint32_t word0 = word_n;
+            const double2 p = p_n;
+            const double thu = thu_n;
+            if (u + NT < nUE) {
+                i_n = i + NT;
+                cell_n = ldk_cell(c.ue_cell, i_n, keep);
+                if (need_word) word_n = ldk(c.ho + i_n, keep);
+                if (group_tick) { p_n = ldk(c.xy + i_n, keep); if (inj) thu_n = ldk(c.th_u + i_n, keep); }
+            }
             if (incremental) {
                 // the cell of the previous step leaves its association plane
                 obs_add(obs_env, (long long)(((size_t)(1 + (word0 & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
             }
-            if (group_tick) {
-                const double2 p = ldk(c.xy + i, keep);
-                cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, inj ? ldk(c.th_u + i, keep) : 0.0, keep);
-            }
+            if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, thu, keep);
             else if (tr) {
                 const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
                 cell = make_short2((short)xy.x, (short)xy.y);
