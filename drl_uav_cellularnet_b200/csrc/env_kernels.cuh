@@ -846,7 +846,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // ---- more than 4 BSs, fp32: two mappings.  (A) thread = UE: movement.  Each UE's (cell, handover word) is
         // staged through shared memory (coalesced HBM loads here, no global load left in pass B); if the env's UEs do
         // not fit, HBM is the staging area.
-        int2 *stage = a.cells_off >= 0 ? reinterpret_cast<int2 *>(dyn_smem + a.cells_off) : nullptr;
+        int4 *stage = a.cells_off >= 0 ? reinterpret_cast<int4 *>(dyn_smem + a.cells_off) : nullptr;
         // software-pipelined: the next UE's state is requested before the current one is computed
         const bool need_word = mode == MODE_STEP || incremental;
         size_t i_n = (size_t)e * nUE + tid;
@@ -881,7 +881,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 cell = make_short2((short)xy.x, (short)xy.y);
             }
             if (mode != MODE_CTOR || c.mobility == MOB_TRACE) stk_cell(c.ue_cell, i, cell, keep);
-            if (stage) stage[u] = make_int2((int)((uint32_t)(uint16_t)cell.x | ((uint32_t)(uint16_t)cell.y << 16)), (int)word0);
+            if (stage) stage[u] = make_int4((int)((uint32_t)(uint16_t)cell.x | ((uint32_t)(uint16_t)cell.y << 16)), (int)word0, 0, 0);
             if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
         }
         __syncthreads();
@@ -897,7 +897,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             short2 cell;
             uint32_t word;
             if (stage) {
-                const int2 sv = stage[u];
+                const int2 sv = *reinterpret_cast<const int2 *>(stage + u);
                 cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
                 word = (uint32_t)sv.y;
             } else {
@@ -910,16 +910,21 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 ? ue_channel_quad<NB, DIAG, true>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho)
                 : ue_channel_quad<NB, DIAG, false>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho);
             if (live && q == 0) {
-                stk(c.ho + i, word, keep);
-                if (stage) stage[u].y = (int)word;                     // the count REDs below read (cell, serving) from here
                 sum_sinr += (double)curS;
                 cnt_out += new_out;
                 cnt_ho += did_ho;
-                const int srv = word & 31;
-                if (a.serving) a.serving[i] = (uint8_t)srv;
-                if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = curS;
-                if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
-                if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
+                if (stage) {
+                    // results go back to the staging area; the per-UE outputs are written coalesced after barrier 2
+                    reinterpret_cast<int2 *>(stage + u)[0].y = (int)word;
+                    stage[u].z = __float_as_int(curS);
+                } else {
+                    const int srv = word & 31;
+                    stk(c.ho + i, word, keep);
+                    if (a.serving) a.serving[i] = (uint8_t)srv;
+                    if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = curS;
+                    if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
+                    if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
+                }
             }
         }
     } else {
@@ -970,24 +975,33 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     __syncthreads();                                                   // barrier 2
 
     if (warp == WARP_GRP && group_tick) mob_group_finish(c, s, e, genv, tick - 1, inj, lane);
-    if (full_obs) {
-        // non-zero cells: UEs on the plane of their (post-handover) serving BS, BSs on plane 0
-        const int2 *stage = (!F64 && NB > 4 && a.cells_off >= 0) ? reinterpret_cast<const int2 *>(dyn_smem + a.cells_off) : nullptr;
-        for (int u = tid; u < nUE; u += NT) {
-            const size_t i = (size_t)e * nUE + u;
-            short2 cell;
-            int srv;
-            if (stage) {
-                const int2 sv = stage[u];
-                cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
-                srv = sv.y & 31;
-            } else {
-                cell = ldk_cell(c.ue_cell, i, keep);
-                srv = ldk(c.ho + i, keep) & 31;
+    {
+        // per-UE epilogue, thread = UE: the staged results of the 4-BSs-per-lane pass go to HBM coalesced, and the dense
+        // observation gets its non-zero cells (UEs on the plane of their post-handover serving BS, BSs on plane 0)
+        const int4 *stage = (!F64 && NB > 4 && a.cells_off >= 0) ? reinterpret_cast<const int4 *>(dyn_smem + a.cells_off) : nullptr;
+        if (stage || full_obs) {
+            for (int u = tid; u < nUE; u += NT) {
+                const size_t i = (size_t)e * nUE + u;
+                short2 cell;
+                int srv;
+                if (stage) {
+                    const int4 sv = stage[u];
+                    cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
+                    srv = sv.y & 31;
+                    const int lin = ((1 + srv) * G + cell.x) * G + cell.y;
+                    stk(c.ho + i, (uint32_t)sv.y, keep);
+                    if (a.serving) a.serving[i] = (uint8_t)srv;
+                    if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = __int_as_float(sv.z);
+                    if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = lin;
+                    if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
+                } else {
+                    cell = ldk_cell(c.ue_cell, i, keep);
+                    srv = ldk(c.ho + i, keep) & 31;
+                }
+                if (full_obs) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
             }
-            obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
         }
-        if (tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);
+        if (full_obs && tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);
     }
     if (tid == 0) {
         double tot = 0.0;

@@ -111,9 +111,9 @@ int plan_kernel(uavenv_t *h) {
     h->tile_bytes = h->tiles_ok ? (int)tile : 0;
     /* fp32 kernels with more than 4 BSs stage the env's UE cells in shared memory between the movement pass
      * (thread = UE) and the channel pass (lane = 4 BSs of a UE); if they do not fit, HBM is the staging area */
-    const int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 8 + 127) & ~(int64_t)127) : 0;   /* (cell, handover word) per UE */
+    const int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 16 + 127) & ~(int64_t)127) : 0;   /* (cell, handover word, serving SINR, -) per UE */
     h->cells_off = -1;
-    if (cells_bytes && cells_bytes <= 32768) {
+    if (cells_bytes && cells_bytes <= 49152) {
         if (h->tile_bytes + cells_bytes + (int64_t)fa.sharedSizeBytes + 1024 > dev_smem) {
             /* shrink the tile (re-balanced) to make room */
             const int64_t total = n_cells * 4, room = (dev_smem - (int64_t)fa.sharedSizeBytes - 1024 - cells_bytes) / 128 * 128;
