@@ -722,7 +722,10 @@ __device__ __forceinline__ void issue_zero_stream(float *obs_env, const float *z
 #define UAVENV_MINB 3
 #endif
 constexpr int NT_SMALL = 128;   // CTA size for handles without a dense observation stream and <= 64 UEs per env
-constexpr int min_blocks(int nb, bool f64, int nt) { return (f64 || nb > 8) ? 1 : (nt == NT_SMALL ? 6 : UAVENV_MINB); }
+#ifndef UAVENV_MINB_WIDE
+#define UAVENV_MINB_WIDE 3
+#endif
+constexpr int min_blocks(int nb, bool f64, int nt) { return f64 ? 1 : (nb > 8 ? UAVENV_MINB_WIDE : (nt == NT_SMALL ? 6 : UAVENV_MINB)); }
 
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
 //   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move

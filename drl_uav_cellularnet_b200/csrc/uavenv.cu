@@ -101,27 +101,31 @@ int plan_kernel(uavenv_t *h) {
     CU(h, cudaFuncGetAttributes(&fa, (const void *)h->kernel));
     /* the TMA path needs whole float4s per env and 32-bit byte offsets */
     h->tiles_ok = h->cfg.obs_mode == UAVENV_OBS_F32 && (n_cells & 3) == 0 && n_cells * 4 < 0x7fffffffLL;
+    /* fp32 kernels with more than 4 BSs stage every UE's (cell, handover word, serving SINR) in shared memory between
+     * the movement pass (thread = UE) and the channel pass (lane = 4 BSs of a UE); if it does not fit, HBM is the
+     * staging area */
+    int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 16 + 127) & ~(int64_t)127) : 0;
+    if (cells_bytes > 49152) cells_bytes = 0;
+    /* Shared-memory budget per CTA for three resident CTAs per SM (what the fp32 kernels are compiled for and what
+     * measured best: NOTES.md); the zero tile takes what the staging area leaves, in equal copies of <= TILE_BYTES. */
+    int sm_smem = 0;
+    CU(h, cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
+    const int64_t fixed = (int64_t)fa.sharedSizeBytes + 1024;               /* static + per-CTA reservation */
+    int64_t budget = f64 ? dev_smem - fixed : sm_smem / 3 - fixed;
+    if (budget > dev_smem - fixed) budget = dev_smem - fixed;
     int64_t tile = TILE_BYTES;
     if (const char *ev = getenv("UAVENV_TILE_BYTES")) { const long v = atol(ev); if (v >= 128 && v % 128 == 0) tile = v; }
+    if (tile > budget - cells_bytes) tile = (budget - cells_bytes) / 128 * 128;
+    if (tile < 16384) {                                                     /* no room at 3 CTAs/SM: fewer, larger CTAs */
+        tile = TILE_BYTES;
+        if (tile > dev_smem - fixed - cells_bytes) tile = (dev_smem - fixed - cells_bytes) / 128 * 128;
+    }
     {   /* equal copies: ceil(total / tile) of them, each rounded up to 128 B (reference sizes: 3 x 66 688 B) */
         const int64_t total = n_cells * 4, n_ops = (total + tile - 1) / tile;
         tile = ((total + n_ops - 1) / n_ops + 127) / 128 * 128;
     }
-    if (tile + (int64_t)fa.sharedSizeBytes + 1024 > dev_smem) tile = (dev_smem - (int64_t)fa.sharedSizeBytes - 1024) / 128 * 128;
     h->tile_bytes = h->tiles_ok ? (int)tile : 0;
-    /* fp32 kernels with more than 4 BSs stage the env's UE cells in shared memory between the movement pass
-     * (thread = UE) and the channel pass (lane = 4 BSs of a UE); if they do not fit, HBM is the staging area */
-    const int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 16 + 127) & ~(int64_t)127) : 0;   /* (cell, handover word, serving SINR, -) per UE */
-    h->cells_off = -1;
-    if (cells_bytes && cells_bytes <= 49152) {
-        if (h->tile_bytes + cells_bytes + (int64_t)fa.sharedSizeBytes + 1024 > dev_smem) {
-            /* shrink the tile (re-balanced) to make room */
-            const int64_t total = n_cells * 4, room = (dev_smem - (int64_t)fa.sharedSizeBytes - 1024 - cells_bytes) / 128 * 128;
-            const int64_t n_ops = (total + room - 1) / room;
-            h->tile_bytes = h->tiles_ok ? (int)(((total + n_ops - 1) / n_ops + 127) / 128 * 128) : 0;
-        }
-        h->cells_off = h->tile_bytes;
-    }
+    h->cells_off = cells_bytes ? h->tile_bytes : -1;
     h->dyn_smem = (size_t)h->tile_bytes + (h->cells_off >= 0 ? (size_t)cells_bytes : 0);
     if (h->dyn_smem) {
         CU(h, cudaFuncSetAttribute((const void *)h->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
