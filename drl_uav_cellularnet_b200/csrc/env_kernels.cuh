@@ -566,12 +566,12 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 // its 4 fading normals), so a warp runs 32/(NB/4) UEs at once with small register arrays.  The exclude-self
 // interference sum is (the other three of my four) + (the quad sums of the other lanes, gathered with shuffles) --
 // never total - own; the best server is a shuffle argmax with lowest-index tie break.  All lanes of a
-// group end up with the same decision; the caller lets lane q == 0 write it.  `u` must be clamped to a valid UE on
-// every lane (shuffles need the whole warp).
+// group end up with the same (best server, its SINR, SINR of the current cell); the handover / outage decisions are
+// taken by the caller, once per UE.  `u` must be clamped to a valid UE on every lane (shuffles need the whole warp).
 template <int NB, bool DIAG, bool FULL>
 __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs &a, const EnvShared &s, int e,
-                                                 uint32_t genv, int u, int cx, int cy, uint32_t epoch, int mode,
-                                                 uint32_t &word, int &new_out, int &did_ho) {
+                                                 uint32_t genv, int u, int cx, int cy, uint32_t epoch, uint32_t word,
+                                                 int &best_out, float &bestS_out) {
     constexpr int LPU = NB / 4;                                        // lanes per UE
     static_assert(NB == 8 || NB == 16 || NB == 32, "quad mapping");
     const int lane = threadIdx.x & 31, q = lane & (LPU - 1), gbase = lane & ~(LPU - 1);
@@ -645,7 +645,9 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
     const int cur = word & 31, ks = cur & 3;
     const float mineS = ks == 0 ? S0 : (ks == 1 ? S1 : (ks == 2 ? S2 : S3));
     const float curS = __shfl_sync(0xffffffffu, mineS, gbase | ((cur >> 2) & (LPU - 1)));
-    return ho_decide<float>(c, mode, best, bestS, curS, word, new_out, did_ho);
+    best_out = best;
+    bestS_out = bestS;
+    return curS;                                                       // the decisions (ho_decide) are the caller's
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -908,26 +910,55 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 word = ldk(c.ho + i, keep);
             }
             if (mode != MODE_STEP) word = 0u;
-            int new_out, did_ho;
+            int best;
+            float bestS;
             const float curS = full_bs
-                ? ue_channel_quad<NB, DIAG, true>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho)
-                : ue_channel_quad<NB, DIAG, false>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word, new_out, did_ho);
-            if (live && q == 0) {
-                sum_sinr += (double)curS;
-                cnt_out += new_out;
-                cnt_ho += did_ho;
-                if (stage) {
-                    // results go back to the staging area; the per-UE outputs are written coalesced after barrier 2
-                    reinterpret_cast<int2 *>(stage + u)[0].y = (int)word;
-                    stage[u].z = __float_as_int(curS);
-                } else {
+                ? ue_channel_quad<NB, DIAG, true>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS)
+                : ue_channel_quad<NB, DIAG, false>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS);
+            if (stage) {
+                // hand (best server, its SINR, current-cell SINR) to the per-UE decision pass below
+                if (live && q == 0) {
+                    reinterpret_cast<int2 *>(stage + u)[0].y = (int)(word | ((uint32_t)best << 23));
+                    reinterpret_cast<int2 *>(stage + u)[1] = make_int2(__float_as_int(bestS), __float_as_int(curS));
+                }
+            } else {
+                int new_out, did_ho;
+                const float srvS = ho_decide<float>(c, mode, best, bestS, curS, word, new_out, did_ho);
+                if (live && q == 0) {
+                    sum_sinr += (double)srvS;
+                    cnt_out += new_out;
+                    cnt_ho += did_ho;
                     const int srv = word & 31;
                     stk(c.ho + i, word, keep);
                     if (a.serving) a.serving[i] = (uint8_t)srv;
-                    if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = curS;
+                    if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = srvS;
                     if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
                     if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
                 }
+            }
+        }
+        if (stage) {
+            // ---- (C) thread = UE again: handover / outage decisions once per UE, per-UE outputs coalesced
+            __syncthreads();
+            for (int u = tid; u < nUE; u += NT) {
+                const size_t i = (size_t)e * nUE + u;
+                const int4 sv = stage[u];
+                const short2 cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
+                uint32_t word = (uint32_t)sv.y & 0x7fffffu;
+                const int best = ((uint32_t)sv.y >> 23) & 31;
+                int new_out, did_ho;
+                const float srvS = ho_decide<float>(c, mode, best, __int_as_float(sv.z), __int_as_float(sv.w), word, new_out, did_ho);
+                sum_sinr += (double)srvS;
+                cnt_out += new_out;
+                cnt_ho += did_ho;
+                const int srv = word & 31;
+                const int lin = ((1 + srv) * G + cell.x) * G + cell.y;
+                stk(c.ho + i, word, keep);
+                reinterpret_cast<int2 *>(stage + u)[0].y = (int)word;       // the count REDs after barrier 2 read (cell, serving)
+                if (a.serving) a.serving[i] = (uint8_t)srv;
+                if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = srvS;
+                if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = lin;
+                if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
             }
         }
     } else {
@@ -979,29 +1010,23 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
 
     if (warp == WARP_GRP && group_tick) mob_group_finish(c, s, e, genv, tick - 1, inj, lane);
     {
-        // per-UE epilogue, thread = UE: the staged results of the 4-BSs-per-lane pass go to HBM coalesced, and the dense
-        // observation gets its non-zero cells (UEs on the plane of their post-handover serving BS, BSs on plane 0)
+        // the dense observation gets its non-zero cells (UEs on the plane of their post-handover serving BS, BSs on
+        // plane 0); thread = UE, (cell, serving) from the staging area when there is one
         const int4 *stage = (!F64 && NB > 4 && a.cells_off >= 0) ? reinterpret_cast<const int4 *>(dyn_smem + a.cells_off) : nullptr;
-        if (stage || full_obs) {
+        if (full_obs) {
             for (int u = tid; u < nUE; u += NT) {
                 const size_t i = (size_t)e * nUE + u;
                 short2 cell;
                 int srv;
                 if (stage) {
-                    const int4 sv = stage[u];
+                    const int2 sv = *reinterpret_cast<const int2 *>(stage + u);
                     cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
                     srv = sv.y & 31;
-                    const int lin = ((1 + srv) * G + cell.x) * G + cell.y;
-                    stk(c.ho + i, (uint32_t)sv.y, keep);
-                    if (a.serving) a.serving[i] = (uint8_t)srv;
-                    if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = __int_as_float(sv.z);
-                    if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = lin;
-                    if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
                 } else {
                     cell = ldk_cell(c.ue_cell, i, keep);
                     srv = ldk(c.ho + i, keep) & 31;
                 }
-                if (full_obs) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
+                obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
             }
         }
         if (full_obs && tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);
