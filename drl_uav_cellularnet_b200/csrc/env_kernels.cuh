@@ -2,17 +2,21 @@
 //
 // One CTA owns one environment for the whole call: UE mobility tick -> BS move -> UE x BS channel pass ->
 // best server / time-to-trigger handover / new-outage count -> reward -> observation.  Nothing is exchanged
-// between environments (reference: one env object per worker, main.py:173), so the grid is E CTAs.
+// between environments (reference: one env object per worker, main.py:173), so the grid is E CTAs.  The dense
+// observation -- 99 % of the bytes a step moves -- is streamed by the TMA engine (cp.async.bulk copies of one zeroed
+// shared-memory tile) while the warps compute; DESIGN.md section 3 explains the shape and profiles/r1/NOTES.md the
+// measurements behind it.
 //
 // Reference semantics restated here (file:line into the reference repo):
 //   mobile_env.py:150-194 / 196-233  step / step_test          -> env_kernel<.., MODE_STEP>
 //   mobile_env.py:115-148            reset                     -> MODE_RESET
 //   mobile_env.py:100 + channel.py:92-93,110  LTEChannel ctor  -> MODE_CTOR
 //   ue_mobility.py:409-523           reference_point_group     -> mob_group_load / mob_ue_move / mob_group_finish
-//   ue_mobility.py:191-271,310-336   BS_move, Decimal_to_Base_N-> decode_action / bs_move_warp
-//   channel.py:220-269               gain / SINR               -> ue_channel_pass
-//   channel.py:138-176,216           UpdateDroneNet            -> ue_channel_pass (handover word)
-//   channel.py:387-409, ue_mobility.py:173-188  association / BS grid map -> obs_* functions
+//   ue_mobility.py:191-271,310-336   BS_move, Decimal_to_Base_N-> the BS warp of env_kernel / bs_move_warp
+//   channel.py:220-269               gain / SINR               -> ue_channel_pass (thread = UE), ue_channel_quad (lane = 4 BSs)
+//   channel.py:138-176,216           UpdateDroneNet            -> ho_decide (handover word)
+//   channel.py:387-409, ue_mobility.py:173-188  association / BS grid map -> issue_zero_stream + obs_add
+//   channel.py:411-433               GetSinrInArea             -> coverage_kernel
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,6 +44,7 @@ __device__ __forceinline__ void obs_add(float *obs_env, long long lin, float v, 
 #endif
     atomicAdd(obs_env + lin, v);
 }
+
 enum { CTR_TICK = 0, CTR_EPOCH = 1, CTR_STEP = 2, CTR_AGG = 3, CTR_DEAGG = 4, CTR_STRIDE = 8 };
 
 // handover word, one per UE (channel.py:75-81,92-93): current_BS, the <=3 rows of bestBS_buf, its depth, and
