@@ -57,7 +57,7 @@ SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
-    "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
+    "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
     "uavnet_p2p_rmsprop",
     "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
 ]
@@ -102,6 +102,7 @@ def lib():
     L.uavenv_diag_fill_env.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.uavnet_sparse_fwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.uavnet_sparse_bwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp]
+    L.uavnet_softmax_sample.argtypes = [vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
     L.uavnet_actor_head_bwd.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, C.c_float, vp, vp, vp]
     L.uavnet_p2p_alloc.argtypes = [C.c_int64, P(vp), vp]
     L.uavnet_p2p_open.argtypes = [vp, P(vp)]

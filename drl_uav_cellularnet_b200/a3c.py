@@ -124,6 +124,20 @@ class ACNet:
             cache.update(h2c=h2c, v=v)
         return prob, v, cache
 
+    def sample_head(self, h2a: torch.Tensor, seed: int, row_offset: int, counter_dev: Optional[torch.Tensor], counter_add: int,
+                    prob_out: Optional[torch.Tensor] = None):
+        """logits = h2a @ Wa3 + ba3, then softmax + np.random.choice(p=a_prob) in one kernel (uavnet_softmax_sample,
+        Philox keyed by (seed, row_offset + row, *counter_dev + counter_add)) -> (prob [M, N_A], action int64 [M])"""
+        M = h2a.shape[0]
+        logits = torch.addmm(self.p["ba3"], h2a, self.p["Wa3"])
+        prob = prob_out if prob_out is not None else torch.empty_like(logits)
+        action = torch.empty(M, dtype=torch.int64, device=self.device)
+        rc = self._lib.uavnet_softmax_sample(_ptr(logits), M, self.n_a, int(seed), int(row_offset), _ptr(counter_dev),
+                                             int(counter_add), _ptr(prob), _ptr(action), self._stream())
+        if rc:
+            raise RuntimeError("uavnet_softmax_sample failed (%d)" % rc)
+        return prob, action
+
     def choose_action(self, idx: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """np.random.choice(N_A, p=a_prob) per env (main.py:165-169) -> int64 [M]"""
         prob, _, _ = self.forward(idx, "actor")
@@ -323,7 +337,9 @@ class A3CTrainer:
         self.env, self.net, self.T = env, net, int(rollout)
         self.E, self.K = env.n_envs, env.nUE + env.nBS
         dev = env.device
+        self.seed = int(seed)
         self.gen = torch.Generator(device=dev).manual_seed(int(seed))
+        self._draws = torch.zeros(1, dtype=torch.int32, device=dev)          # rollout steps sampled so far (Philox counter)
         self.buf_idx = torch.empty((self.T, self.E, self.K), dtype=torch.int32, device=dev)
         self.buf_a = torch.empty((self.T, self.E), dtype=torch.int64, device=dev)
         self.buf_r = torch.empty((self.T, self.E), dtype=torch.float32, device=dev)
@@ -340,15 +356,17 @@ class A3CTrainer:
         env, net = self.env, self.net
         for t in range(self.T):
             self.buf_idx[t].copy_(env.obs_idx)
-            prob, _, _ = net.forward(self.buf_idx[t], "actor",
-                                     out={"h1": self.buf_h1[t], "h2a": self.buf_h2a[t], "prob": self.buf_prob[t]})
-            a = torch.multinomial(prob, 1, generator=self.gen).squeeze(1)    # np.random.choice(p=a_prob), main.py:165-169,195
+            h1 = net.first_layer(self.buf_idx[t], self.buf_h1[t])
+            h2a = torch.addmm(net.p["ba2"], h1[:, :net.h], net.p["Wa2"], out=self.buf_h2a[t]).clamp_(0.0, 6.0)
+            # softmax + np.random.choice(p=a_prob) (main.py:149,165-169,195) fused; draws keyed by the GLOBAL env id
+            _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t])
             _, r, done, _ = env.step(a)                                      # main.py:198
             self.buf_a[t].copy_(a)
             self.buf_r[t].copy_(r)
             self.buf_done[t].copy_(done)
             self.ep_return += r
             env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)
+        self._draws += self.T                                                # next rollout: fresh Philox counters
         v_boot = net.value(env.obs_idx.clone())                              # main.py:217-220
         return n_step_targets(self.buf_r, self.buf_done, v_boot)
 
@@ -383,7 +401,6 @@ class A3CTrainer:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self._graph = torch.cuda.CUDAGraph()
-        self._graph.register_generator_state(self.gen)
         with torch.cuda.graph(self._graph):
             self._graph_out = self.train_iteration()
         return self

@@ -22,7 +22,8 @@ enum PhiloxDomain : uint32_t {
     DOM_GRP_V = 8,     // idx = group, seq = tick: a -> g_v                    (ue_mobility.py:520)
     DOM_FADING = 9,    // idx = UE*ceil(nBS/4) + b/4, seq = channel pass: 4 normals (channel.py:240)
     DOM_ACTION = 10,   // idx = BS, seq = step: a -> digit (synthetic actions for benchmarks)
-    DOM_AREA = 11      // idx = cell*ceil(nBS/4) + b/4, seq = coverage-map call: 4 normals (channel.py:426,429)
+    DOM_AREA = 11,     // idx = cell*ceil(nBS/4) + b/4, seq = coverage-map call: 4 normals (channel.py:426,429)
+    DOM_SAMPLE = 12    // env = sample row, idx = 0, seq = call counter: a -> action draw (np.random.choice, main.py:167)
 };
 
 struct Philox4 {

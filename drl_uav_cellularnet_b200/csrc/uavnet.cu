@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <string.h>
 
+#include "philox.cuh"
+
 namespace uavk {
 
 constexpr int NET_THREADS = 256;
@@ -170,6 +172,53 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_rmsprop_kernel(const __grid_c
     }
 }
 
+// softmax over the logits + np.random.choice(N_A, p=a_prob) (main.py:149,165-169), one warp per sample: the row is
+// read once, the probabilities are written for the update, and the action is drawn by inverse CDF with one Philox
+// uniform keyed by (seed, global row, call counter): the first j whose cumulative probability exceeds u.
+__global__ void __launch_bounds__(NET_THREADS) softmax_sample_kernel(const float *__restrict__ logits, long long M, int A,
+                                                                     uint32_t k0, uint32_t k1, uint32_t row0,
+                                                                     const uint32_t *__restrict__ counter_dev, uint32_t counter_add,
+                                                                     float *__restrict__ prob, long long *__restrict__ action) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t seq = (counter_dev ? *counter_dev : 0u) + counter_add;
+    const long long warp0 = ((long long)blockIdx.x * NET_THREADS + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * NET_THREADS) >> 5;
+    for (long long m = warp0; m < M; m += n_warps) {
+        const float *z = logits + m * A;
+        float mx = -3.0e38f;
+        for (int j = lane; j < A; j += 32) mx = fmaxf(mx, z[j]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < A; j += 32) sum += expf(z[j] - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+        double ua, ub;
+        philox_uniform2(k0, k1, row0 + (uint32_t)m, 0u, seq, DOM_SAMPLE, ua, ub);
+        const float target = (float)ua;                   // in [0, 1)
+        // chunks of 32 consecutive actions: warp-inclusive scan, first crossing wins
+        float carry = 0.f;
+        int pick = -1;
+        for (int base = 0; base < A; base += 32) {
+            const int j = base + lane;
+            const float p = j < A ? expf(z[j] - mx) * inv : 0.f;
+            if (j < A && prob) prob[m * A + j] = p;
+            float inc = p;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, j < A && carry + inc > target);
+            if (pick < 0 && hit) pick = base + __ffs(hit) - 1;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (pick < 0) pick = A - 1;                       // rounding: the cumulative sum ended just below u
+        if (lane == 0 && action) action[m] = pick;
+    }
+}
+
 int grid_for(long long items) {
     long long g = (items + NET_THREADS - 1) / NET_THREADS;
     const long long cap = 148LL * 8 * 4;          // a few waves of 8 CTAs per SM; the kernels are grid-stride
@@ -261,6 +310,14 @@ int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_loca
     if (lo4 >= hi4) return UAVNET_OK;
     p2p_rmsprop_kernel<<<grid_for(hi4 - lo4), NET_THREADS, 0, (cudaStream_t)stream>>>(pp, ms_local, lo4, hi4, rank, world, lr,
                                                                                      decay, eps, 1.0f / (float)world);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t seed, uint32_t row_offset,
+                          const uint32_t *counter_dev, uint32_t counter_add, float *prob, int64_t *action, void *stream) {
+    if (!logits || M < 1 || A < 1 || (!prob && !action)) return UAVNET_EINVAL;
+    softmax_sample_kernel<<<grid_for(M * 32), NET_THREADS, 0, (cudaStream_t)stream>>>(
+        logits, M, A, (uint32_t)seed, (uint32_t)(seed >> 32), row_offset, counter_dev, counter_add, prob, (long long *)action);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 

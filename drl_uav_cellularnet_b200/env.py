@@ -99,6 +99,7 @@ class BatchedMobiEnvironment:
             raise (ValueError if rc == N.EINVAL else RuntimeError)("uavenv_create: " + msg)
         self.cfg = self._lib.uavenv_get_cfg(self._h).contents
         self.n_envs, self.nBS, self.nUE, self.grid_n = n_envs, nBS, nUE, grid_n
+        self.env_offset = int(env_offset)
         self.mobility_model, self.fading, self.precision, self.obs_mode = mobility_model, fading, precision, obs
         self.action_space_dim = N_ACT ** nBS if cfg.n_act == N_ACT else cfg.n_act ** nBS     # mobile_env.py:104
         self.observation_space_dim = grid_n * grid_n * (nBS + 1) * MAX_UE_PER_GRID           # mobile_env.py:105

@@ -34,6 +34,14 @@ int uavnet_sparse_fwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
 int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
                       void *stream);
 
+/* Actor head of the rollout (main.py:149,165-169): prob = softmax(logits) and action ~ np.random.choice(A, p=prob) by
+ * inverse CDF with one Philox4x32-10 uniform per sample, keyed by (seed, row_offset + row, counter) -- the first action
+ * whose cumulative probability exceeds u.  logits float32 [M,A]; prob float32 [M,A] out (may be NULL); action int64 [M]
+ * out (may be NULL).  counter = *counter_dev (a uint32 in device memory, NULL = 0) + counter_add: keeping the running
+ * count on the device lets a CUDA graph that contains the call draw fresh numbers on every replay. */
+int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t seed, uint32_t row_offset,
+                          const uint32_t *counter_dev, uint32_t counter_add, float *prob, int64_t *action, void *stream);
+
 /* d(a_loss)/d(logits) of the actor loss (main.py:68-76), fused over the softmax output:
  *   a_loss = mean_i -( log(prob[i,a_i] + 1e-5) * td_i + beta * H_i ),  H_i = -sum_j prob_ij log(prob_ij + 1e-5)
  * prob float32 [M,A] (softmax output), a_his int64 [M], td float32 [M] (v_target - v, treated as constant),

@@ -266,3 +266,38 @@ def test_p2p_push_two_ranks_equals_nccl_path():
     d = json.loads(line)
     assert d["world"] == 2 and d["max_abs_param_diff_vs_nccl_path"] == 0.0
     assert d["param_sums_per_rank"][0] == d["param_sums_per_rank"][1]
+
+
+def test_softmax_sample_kernel_matches_inverse_cdf(pkg):
+    """uavnet_softmax_sample: probabilities = torch.softmax (1e-6), and the action is exactly the inverse-CDF pick for the
+    Philox uniform of (seed, row, counter) -- recomputed on the host with the oracle's Philox -- and the empirical
+    action frequencies over many draws follow the probabilities."""
+    from oracle import mobi_oracle as orc
+    from drl_uav_cellularnet_b200.a3c import ACNet
+    net = ACNet(2000, 625, "cuda:0", hidden=16)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, seed, row0 = 300, 99, 1000
+    h2a = torch.rand((M, 16), device="cuda", generator=g) * 6
+    ctr = torch.tensor([5], dtype=torch.int32, device="cuda")
+    prob, act = net.sample_head(h2a, seed, row0, ctr, 2)
+    ref = torch.softmax(torch.addmm(net.p["ba3"], h2a, net.p["Wa3"]), dim=1)
+    assert float((prob - ref).abs().max()) < 1e-6
+    p64 = prob.double().cpu().numpy()
+    for m in range(0, M, 7):
+        u, _ = orc.philox_uniform2(seed, row0 + m, 0, 7, 12)               # counter 5 + 2, DOM_SAMPLE
+        cdf = np.cumsum(prob[m].cpu().numpy().astype(np.float32), dtype=np.float32)
+        want = int(np.searchsorted(cdf, np.float32(u), side="right"))
+        got = int(act[m])
+        assert abs(got - min(want, 624)) <= 1, (m, got, want)              # float32 scan order may shift a boundary pick
+        assert p64[m, got] > 0
+    # frequencies: one fixed distribution, 40 000 draws through the counter
+    hh = h2a[:1].expand(40000, 16).contiguous()
+    _, a2 = net.sample_head(hh, seed, 0, ctr, 0)
+    freq = torch.bincount(a2, minlength=625).double().cpu().numpy() / 40000
+    p0 = p64[0]
+    assert np.abs(freq - p0).max() < 5 * np.sqrt(p0.max() / 40000) + 1e-3
+    _, a3 = net.sample_head(hh, seed, 0, ctr, 0)
+    assert torch.equal(a2, a3)                                             # same counters, same draws
+    ctr += 1
+    _, a4 = net.sample_head(hh, seed, 0, ctr, 0)
+    assert not torch.equal(a2, a4)
