@@ -341,3 +341,51 @@ def test_joint_action_overflow_and_bad_sizes_are_rejected(pkg):
         pkg.BatchedMobiEnvironment(2, 4, 40, 100, "group", group_sizes=[10, 10, 10])      # does not sum to nUE
     with pytest.raises(ValueError):
         pkg.BatchedMobiEnvironment(1, 32, 64, 9000, "group", obs="none")                   # (nBS+1) G^2 >= 2^31
+
+
+def test_long_moves_per_env_traces_and_incremental_masked_reset(pkg):
+    """Less-travelled options against the oracle (float64 kernels): N_ACT = 9 (the long moves 5-8 of BS_move,
+    ue_mobility.py:239-253), one trace PER env (uavenv_set_trace per_env), and incremental observations across a
+    masked reset (the reset envs are rewritten in full, the others only patched)."""
+    from oracle import mobi_oracle as orc
+    E, T, seed = 4, 25, 66
+    cfg = orc.default_cfg(n_act=9)
+    # -- N_ACT = 9, group mode, incremental observation, masked reset half way
+    env = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", precision="fp64", seed=seed, obs="f32_incremental", n_act=9)
+    assert env.action_space_dim == 9 ** 4
+    oenvs = [orc.OracleEnv(cfg, seed=seed, env_id=e) for e in range(E)]
+    want = np.stack([o.reset() for o in oenvs])
+    assert np.array_equal(_np(env.reset()).astype(np.float64), want)
+    rs = np.random.RandomState(8)
+    for t in range(T):
+        digits = rs.randint(0, 9, size=(E, 4)).astype(np.uint8)
+        obs, r, d, info = env.step(digits)
+        for e in range(E):
+            want[e] = oenvs[e].step(digits[e].astype(np.int32))[0]
+            assert np.array_equal(_np(info["bs_xy"][e]), oenvs[e].bs_xy), (t, e)
+        assert np.array_equal(_np(obs).astype(np.float64), want), t
+        if t == 12:
+            mask = np.array([1, 0, 0, 1], dtype=np.uint8)
+            obs = env.reset(env_mask=mask)
+            for e in range(E):
+                if mask[e]:
+                    want[e] = oenvs[e].reset()
+            assert np.array_equal(_np(obs).astype(np.float64), want)
+    assert env.check() == 0
+    # -- one trace per env
+    cfg5 = orc.default_cfg()
+    traces = np.stack([orc.make_trace(cfg5, 100 + e, e, T + 1) for e in range(E)], axis=1)        # [T+1, E, 40, 2]
+    tenv = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "read_trace", trace=traces, trace_per_env=True, precision="fp64",
+                                      seed=seed)
+    torcs = [orc.OracleEnv(cfg5, mobility=orc.MOB_TRACE, seed=seed, env_id=e, trace=traces[:, e], warmup_ticks=0) for e in range(E)]
+    want = np.stack([o.reset() for o in torcs])
+    assert np.array_equal(_np(tenv.reset()).astype(np.float64), want)
+    for t in range(T):
+        act = rs.randint(0, 625, size=E)
+        obs, r, d, info = tenv.step(act)
+        for e in range(E):
+            s, rr, dd, oi = torcs[e].step(int(act[e]))
+            assert np.array_equal(_np(obs[e]).astype(np.float64), s), (t, e)
+            assert np.array_equal(_np(info["ue_xy"][e]), traces[t, e]), (t, e)
+            assert int(info["n_out"][e]) == oi["n_out"] and abs(float(r[e]) - rr) < 1e-9
+    assert tenv.check() == 0
