@@ -97,39 +97,62 @@ __global__ void __launch_bounds__(NET_THREADS) rmsprop_kernel(float *__restrict_
 //   g_ij = dL/dp_ij = (beta/M) (log(p_ij + 1e-5) + p_ij / (p_ij + 1e-5)) - [j = a_i] td_i / (M (p_i,a_i + 1e-5))
 //   dz_ij = p_ij (g_ij - sum_k p_ik g_ik)
 // One read of the probabilities (the second pass hits L1), one write of dz, and the sample's loss term.
+template <int PL>   // PL = ceil(A / 32) register slots per lane; 0 = any A, probabilities re-read for the second pass
 __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float *__restrict__ prob, const long long *__restrict__ a_his,
                                                                      const float *__restrict__ td, long long M, int A, float beta,
                                                                      float inv_m, float *__restrict__ dz, float *__restrict__ loss_row) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * NET_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * NET_THREADS) >> 5;
+    const float bm = beta * inv_m;
     for (long long m = warp0; m < M; m += n_warps) {
         const float *pr = prob + m * A;
         const int a = (int)a_his[m];
         const float t = td[m];
         const float pa = pr[a];
         const float ga = -t * inv_m / (pa + 1e-5f);
-        float ent = 0.f, dot = 0.f;                       // -H/1 accumulators: sum p*lp, sum p*g
-        for (int j = lane; j < A; j += 32) {
-            const float p = pr[j];
-            const float lp = logf(p + 1e-5f);
-            const float g = beta * inv_m * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f);
-            ent += p * lp;
-            dot += p * g;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ent += __shfl_xor_sync(0xffffffffu, ent, o);
-            dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        }
+        float ent = 0.f, dot = 0.f;                       // sum p*lp (= -H), sum p*g
         float *dr = dz + m * A;
-        for (int j = lane; j < A; j += 32) {
-            const float p = pr[j];
-            const float lp = logf(p + 1e-5f);
-            const float g = beta * inv_m * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f);
-            dr[j] = p * (g - dot);
+        if constexpr (PL > 0) {
+            float pv[PL], gv[PL];                         // the row lives in registers between the two passes
+#pragma unroll
+            for (int k = 0; k < PL; k++) {
+                const int j = lane + 32 * k;
+                pv[k] = j < A ? pr[j] : 0.f;
+                const float lp = __logf(pv[k] + 1e-5f);
+                gv[k] = bm * (lp + pv[k] / (pv[k] + 1e-5f)) + (j == a ? ga : 0.f);
+                ent += pv[k] * lp;
+                dot += pv[k] * gv[k];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ent += __shfl_xor_sync(0xffffffffu, ent, o);
+                dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            }
+#pragma unroll
+            for (int k = 0; k < PL; k++) {
+                const int j = lane + 32 * k;
+                if (j < A) dr[j] = pv[k] * (gv[k] - dot);
+            }
+        } else {
+            for (int j = lane; j < A; j += 32) {
+                const float p = pr[j];
+                const float lp = __logf(p + 1e-5f);
+                ent += p * lp;
+                dot += p * (bm * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ent += __shfl_xor_sync(0xffffffffu, ent, o);
+                dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            }
+            for (int j = lane; j < A; j += 32) {
+                const float p = pr[j];
+                const float lp = __logf(p + 1e-5f);
+                dr[j] = p * ((bm * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f)) - dot);
+            }
         }
-        if (lane == 0 && loss_row) loss_row[m] = -(logf(pa + 1e-5f) * t - beta * ent);
+        if (lane == 0 && loss_row) loss_row[m] = -(__logf(pa + 1e-5f) * t - beta * ent);
     }
 }
 
@@ -255,8 +278,14 @@ int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
 int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
                           float *dz, float *loss_row, void *stream) {
     if (!prob || !a_his || !td || !dz || M < 1 || A < 1) return UAVNET_EINVAL;
-    actor_head_bwd_kernel<<<grid_for(M * 32), NET_THREADS, 0, (cudaStream_t)stream>>>(
-        prob, (const long long *)a_his, td, M, A, beta, 1.0f / (float)M, dz, loss_row);
+    const int grid = grid_for(M * 32);
+    const float inv_m = 1.0f / (float)M;
+    const long long *ah = (const long long *)a_his;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (A <= 256) actor_head_bwd_kernel<8><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
+    else if (A <= 640) actor_head_bwd_kernel<20><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
+    else if (A <= 1024) actor_head_bwd_kernel<32><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
+    else actor_head_bwd_kernel<0><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
