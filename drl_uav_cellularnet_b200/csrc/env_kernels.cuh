@@ -835,6 +835,18 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         if (lane == 0) s.ok = ok;
     }
     if (warp == WARP_GRP && group_tick && lane < c.nG) mob_group_load(s, group_row_load(c, e, lane), lane);
+    // the state of this thread's first UE is requested before the barrier: its HBM / L2 latency overlaps the BS warp's
+    const uint64_t keep = l2_policy_evict_last();                      // the env's own state stays in L2 under the stream
+    short2 cell_0 = make_short2(0, 0);
+    uint32_t word_0 = 0u;
+    double2 p_0 = make_double2(0.0, 0.0);
+    double thu_0 = 0.0;
+    if (tid < nUE) {
+        const size_t i0 = (size_t)e * nUE + tid;
+        cell_0 = ldk_cell(c.ue_cell, i0, keep);
+        word_0 = ldk(c.ho + i0, keep);
+        if (group_tick) { p_0 = ldk(c.xy + i0, keep); if (inj) thu_0 = ldk(c.th_u + i0, keep); }
+    }
     __syncthreads();                                                   // barrier 1
     if (!s.ok) {                                                       // the env's state is left untouched
         if (bulk_ok && warp == WARP_TMA) bulk_wait_read_all();         // the tile must outlive the copies' reads
@@ -851,7 +863,6 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     }
     double sum_sinr = 0.0;
     int cnt_out = 0, cnt_ho = 0;
-    const uint64_t keep = l2_policy_evict_last();                      // the env's own state stays in L2 under the stream
     if constexpr (!F64 && NB > 4) {
         // ---- more than 4 BSs, fp32: two mappings.  (A) thread = UE: movement.  Each UE's (cell, handover word) is
         // staged through shared memory (coalesced HBM loads here, no global load left in pass B); if the env's UEs do
@@ -860,15 +871,10 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // software-pipelined: the next UE's state is requested before the current one is computed
         const bool need_word = mode == MODE_STEP || incremental;
         size_t i_n = (size_t)e * nUE + tid;
-        short2 cell_n = make_short2(0, 0);
-        uint32_t word_n = 0u;
-        double2 p_n = make_double2(0.0, 0.0);
-        double thu_n = 0.0;
-        if (tid < nUE) {
-            cell_n = ldk_cell(c.ue_cell, i_n, keep);
-            if (need_word) word_n = ldk(c.ho + i_n, keep);
-            if (group_tick) { p_n = ldk(c.xy + i_n, keep); if (inj) thu_n = ldk(c.th_u + i_n, keep); }
-        }
+        short2 cell_n = cell_0;                                         // first stage: requested before barrier 1
+        uint32_t word_n = need_word ? word_0 : 0u;
+        double2 p_n = p_0;
+        double thu_n = thu_0;
         for (int u = tid; u < nUE; u += NT) {
             const size_t i = i_n;
             short2 cell = cell_n;
@@ -969,15 +975,17 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     } else {
     for (int u = tid; u < nUE; u += NT) {
         const size_t i = (size_t)e * nUE + u;
-        short2 cell = ldk_cell(c.ue_cell, i, keep);
-        uint32_t word = ldk(c.ho + i, keep);
+        const bool first = u == tid;                                   // requested before barrier 1
+        short2 cell = first ? cell_0 : ldk_cell(c.ue_cell, i, keep);
+        uint32_t word = first ? word_0 : ldk(c.ho + i, keep);
         if (incremental) {
             // the cell of the previous step leaves its association plane
             obs_add(obs_env, (long long)(((size_t)(1 + (word & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
         }
         if (group_tick) {
-            const double2 p = ldk(c.xy + i, keep);
-            cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, inj ? ldk(c.th_u + i, keep) : 0.0, keep);
+            const double2 p = first ? p_0 : ldk(c.xy + i, keep);
+            const double thu = inj ? (first ? thu_0 : ldk(c.th_u + i, keep)) : 0.0;
+            cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, thu, keep);
         } else if (tr) {
             const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
             cell = make_short2((short)xy.x, (short)xy.y);
