@@ -52,13 +52,29 @@ class Out(C.Structure):
                 ("obs_idx", C.c_void_p)]
 
 
-# every symbol include/uavenv.h declares
+class GemmDesc(C.Structure):
+    """uavnet_gemm_desc (include/uavnet.h)"""
+    _fields_ = [("A", C.c_void_p), ("lda", C.c_int64), ("a_trans", C.c_int32),
+                ("B", C.c_void_p), ("ldb", C.c_int64), ("b_trans", C.c_int32),
+                ("D", C.c_void_p), ("ldd", C.c_int64),
+                ("M", C.c_int64), ("N", C.c_int32), ("K", C.c_int64),
+                ("bias", C.c_void_p), ("relu6", C.c_int32),
+                ("mask_src", C.c_void_p), ("ld_mask", C.c_int64),
+                ("accumulate", C.c_int32), ("split_k", C.c_int32),
+                ("colsum", C.c_void_p),
+                ("dot_w", C.c_void_p), ("dot_b", C.c_void_p), ("dot_out", C.c_void_p),
+                ("precision", C.c_int32)]
+
+
+GEMM_TF32, GEMM_3XTF32 = 0, 1
+
+# every symbol include/uavenv.h and include/uavnet.h declare
 SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
     "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
-    "uavnet_p2p_rmsprop",
+    "uavnet_p2p_rmsprop", "uavnet_gemm", "uavnet_gemm_check",
     "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
 ]
 
@@ -103,7 +119,7 @@ def lib():
     L.uavnet_sparse_fwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.uavnet_sparse_bwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp]
     L.uavnet_softmax_sample.argtypes = [vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
-    L.uavnet_actor_head_bwd.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, C.c_float, vp, vp, vp]
+    L.uavnet_actor_head_bwd.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, C.c_float, vp, C.c_int64, vp, vp]
     L.uavnet_p2p_alloc.argtypes = [C.c_int64, P(vp), vp]
     L.uavnet_p2p_open.argtypes = [vp, P(vp)]
     L.uavnet_p2p_close.argtypes = [vp]
@@ -111,5 +127,7 @@ def lib():
     L.uavnet_p2p_rmsprop.argtypes = [P(vp), P(vp), vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp]
     L.uavnet_rmsprop.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, vp]
     L.uavenv_diag_fill.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp]
+    L.uavnet_gemm.argtypes = [P(GemmDesc), vp]
+    L.uavnet_gemm_check.argtypes = []
     _lib = L
     return L

@@ -5,7 +5,9 @@ What changes against the reference
   * The first layer never sees the dense 50 000-wide observation: the env kernel emits the ~44 non-zero cells as flat
     indices (``obs_idx``) and ``uavnet_sparse_fwd`` / ``uavnet_sparse_bwd`` (include/uavnet.h) do the gather-sum and
     the scatter-add.  Actor and critic first layers are stored side by side in one ``[N_S, 2*200]`` matrix so that one
-    gather feeds both.  The 200x200 / 200x625 / 200x1 layers are plain library GEMMs (torch.matmul).
+    gather feeds both.  The 200x200 / 200x625 / 200x1 layers and all their gradients run on the tcgen05 tensor cores
+    through ``uavnet_gemm`` (dense.py, csrc/tc_gemm.cuh) with bias / relu6 / relu6' / value-head / bias-gradient
+    epilogues fused in; ``precision='fp32'`` is 3xTF32 (fp32-class accuracy), ``'tf32'`` one MMA per k-step.
   * Four asynchronous worker threads pushing gradients into a shared net (Hogwild, main.py:85-86,159-163) become one
     synchronous batch: every rank rolls its E envs UPDATE_GLOBAL_ITER steps, the loss is the mean over all samples
     (like the reference's own synchronous variant, a2c_single_thread.py:153-186), gradients are summed over ranks with
@@ -22,6 +24,7 @@ import numpy as np
 import torch
 
 from . import _native as N
+from . import dense
 
 # the reference's hyper-parameters (main.py:19-27)
 UPDATE_GLOBAL_ITER = 10
@@ -60,8 +63,12 @@ class ACNet:
         | Wc2 [H,H] | bc2 [H] | Wc3 [H,1] | bc3 [1]
     """
 
-    def __init__(self, n_s: int, n_a: int, device, hidden: int = HIDDEN, seed: int = TENSOR_SEED):
+    def __init__(self, n_s: int, n_a: int, device, hidden: int = HIDDEN, seed: int = TENSOR_SEED, precision: str = "fp32"):
         self.n_s, self.n_a, self.h = int(n_s), int(n_a), int(hidden)
+        if precision not in dense.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(dense.PRECISIONS))
+        self.precision = precision
+        self.ld_a = (self.n_a + 3) // 4 * 4          # rows of Wa3 / dz padded to 16 bytes (625 -> 628): vector staging
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("ACNet needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -71,21 +78,42 @@ class ACNet:
                   ("Wc2", (H, H)), ("bc2", (H,)), ("Wc3", (H, 1)), ("bc3", (1,))]
         self.segments, off = {}, 0
         for name, shp in shapes:
-            n = int(np.prod(shp))
-            self.segments[name] = (off, n, shp)
+            stored = (shp[0], self.ld_a) if name == "Wa3" else shp          # padding columns stay zero for ever
+            n = int(np.prod(stored))
+            self.segments[name] = (off, n, stored, shp)
             off += (n + 3) // 4 * 4
         self.n_flat = off
         self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
         self.grad = torch.zeros_like(self.flat)
         self.ms = torch.ones_like(self.flat)                # TF1 RMSProp: rms slot initialised to ones
-        self.p = {k: self.flat[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
-        self.g = {k: self.grad[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        self._bind_views()
         # tf.random_normal_initializer(0., .1, seed) kernels, zero biases (main.py:145-153).  The TF stream itself is
         # not reproducible here (TensorFlow absent); the distribution is.
         gen = torch.Generator(device="cpu").manual_seed(int(seed))
         for k in ("W1", "Wa2", "Wa3", "Wc2", "Wc3"):
-            self.p[k].copy_(torch.randn(self.segments[k][2], generator=gen) * 0.1)
-        self.n_params = sum(n for _, n, _ in self.segments.values())
+            self.p[k].copy_(torch.randn(self.segments[k][3], generator=gen) * 0.1)
+        self.n_params = sum(int(np.prod(shp)) for _, _, _, shp in self.segments.values())
+        self._scratch = {}
+
+    def _bind_views(self):
+        def views(buf):
+            out = {}
+            for k, (o, n, stored, shp) in self.segments.items():
+                v = buf[o:o + n].view(stored)
+                out[k] = v[:, :shp[1]] if stored != shp else v
+            return out
+        self.p, self.g = views(self.flat), views(self.grad)
+
+    def _buf(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """persistent scratch (stable pointers: CUDA-graph friendly, no allocator traffic per step)"""
+        key = (name, tuple(shape), dtype)
+        t = self._scratch.get(key)
+        if t is None:
+            t = self._scratch[key] = torch.empty(shape, dtype=dtype, device=self.device)
+        return t
+
+    def _gemm(self, A, B, out=None, **kw):
+        return dense.gemm(A, B, out, precision=self.precision, **kw)
 
     # ---- forward ------------------------------------------------------------------------------------------
     def _stream(self):
@@ -111,25 +139,31 @@ class ACNet:
         cache = {"idx": idx, "h1": h1}
         prob = v = None
         if want in ("both", "actor"):
-            if out is None:
-                h2a = _relu6(torch.addmm(p["ba2"], h1[:, :H], p["Wa2"]))
-                prob = torch.softmax(torch.addmm(p["ba3"], h2a, p["Wa3"]), dim=1)
-            else:
-                h2a = torch.addmm(p["ba2"], h1[:, :H], p["Wa2"], out=out["h2a"]).clamp_(0.0, 6.0)
-                prob = torch.softmax(torch.addmm(p["ba3"], h2a, p["Wa3"]), dim=1, out=out["prob"])
+            h2a = self._gemm(h1[:, :H], p["Wa2"], None if out is None else out["h2a"], bias=p["ba2"], relu6=True)
+            logits = self._gemm(h2a, p["Wa3"], bias=p["ba3"])
+            prob = torch.softmax(logits, dim=1, out=None if out is None else out["prob"])
             cache.update(h2a=h2a, prob=prob)
         if want in ("both", "critic"):
-            h2c = _relu6(torch.addmm(p["bc2"], h1[:, H:], p["Wc2"]))
-            v = torch.addmm(p["bc3"], h2c, p["Wc3"]).squeeze(1)
+            h2c, v = self.critic_head(h1)
             cache.update(h2c=h2c, v=v)
         return prob, v, cache
+
+    def critic_head(self, h1: torch.Tensor, h2c_out: Optional[torch.Tensor] = None, v_out: Optional[torch.Tensor] = None):
+        """h2c = relu6(h1[:, H:] @ Wc2 + bc2), v = h2c @ Wc3 + bc3 (main.py:152-153) in one launch: the value head is a
+        row dot in the epilogue of the second layer -> (h2c [M, H], v [M])"""
+        H, p = self.h, self.p
+        M = h1.shape[0]
+        v = v_out if v_out is not None else torch.empty(M, dtype=torch.float32, device=self.device)
+        h2c = self._gemm(h1[:, H:], p["Wc2"], h2c_out, bias=p["bc2"], relu6=True, dot_w=p["Wc3"].view(-1), dot_b=p["bc3"],
+                         dot_out=v)
+        return h2c, v
 
     def sample_head(self, h2a: torch.Tensor, seed: int, row_offset: int, counter_dev: Optional[torch.Tensor], counter_add: int,
                     prob_out: Optional[torch.Tensor] = None):
         """logits = h2a @ Wa3 + ba3, then softmax + np.random.choice(p=a_prob) in one kernel (uavnet_softmax_sample,
         Philox keyed by (seed, row_offset + row, *counter_dev + counter_add)) -> (prob [M, N_A], action int64 [M])"""
         M = h2a.shape[0]
-        logits = torch.addmm(self.p["ba3"], h2a, self.p["Wa3"])
+        logits = self._gemm(h2a, self.p["Wa3"], self._buf("logits", (M, self.n_a)), bias=self.p["ba3"])
         prob = prob_out if prob_out is not None else torch.empty_like(logits)
         action = torch.empty(M, dtype=torch.int64, device=self.device)
         rc = self._lib.uavnet_softmax_sample(_ptr(logits), M, self.n_a, int(seed), int(row_offset), _ptr(counter_dev),
@@ -151,11 +185,6 @@ class ACNet:
     def value(self, idx: torch.Tensor) -> torch.Tensor:
         return self.forward(idx, "critic")[1]
 
-    def _ones(self, m: int) -> torch.Tensor:
-        if getattr(self, "_ones_buf", None) is None or self._ones_buf.numel() < m:
-            self._ones_buf = torch.ones(m, dtype=torch.float32, device=self.device)
-        return self._ones_buf[:m]
-
     # ---- losses + gradients (main.py:64-78), accumulated into self.grad -------------------------------------
     def accumulate_grads(self, idx: torch.Tensor, a_his: torch.Tensor, v_target: torch.Tensor, saved: Optional[dict] = None):
         """Adds d(a_loss)/d(actor params) and d(c_loss)/d(critic params) for the batch to ``self.grad``;
@@ -169,36 +198,31 @@ class ACNet:
         else:
             prob, _, c = self.forward(idx, "actor")
             h1, h2a = c["h1"], c["h2a"]
-        h2c = _relu6(torch.addmm(p["bc2"], h1[:, H:], p["Wc2"]))
-        v = torch.addmm(p["bc3"], h2c, p["Wc3"]).squeeze(1)
+        gemm = self._gemm
+        h2c, v = self.critic_head(h1, self._buf("h2c", (M, H)), self._buf("v", (M,)))
         td = (v_target - v).contiguous()
-        ones = self._ones(M)                                              # bias gradients = column sums = ones^T @ d (GEMV)
-        # -- critic --
+        # -- critic: every weight gradient is x^T @ dy accumulated into the flat gradient buffer, its bias gradient the
+        # -- column sums of dy from the same pass; every data gradient is (dy @ W^T) * relu6'(layer output) --
         c_loss = (td * td).mean()
-        dv = (-2.0 / M) * td                                              # [M]
-        g["Wc3"].addmm_(h2c.t(), dv.unsqueeze(1))
-        g["bc3"].add_(dv.sum())
-        dpre2c = (dv.unsqueeze(1) * p["Wc3"].t()) * ((h2c > 0) & (h2c < 6))
-        g["Wc2"].addmm_(h1[:, H:].t(), dpre2c)
-        g["bc2"].addmv_(dpre2c.t(), ones)
-        dpre1 = torch.empty_like(h1)
-        torch.mm(dpre2c, p["Wc2"].t(), out=dpre1[:, H:])
+        dv = ((-2.0 / M) * td).unsqueeze(1)                                # [M, 1]
+        gemm(h2c, dv, g["Wc3"], a_trans=True, accumulate=True, colsum=g["bc3"])
+        dpre2c = gemm(dv, p["Wc3"], self._buf("dpre2c", (M, H)), b_trans=True, mask_src=h2c)
+        gemm(h1[:, H:], dpre2c, g["Wc2"], a_trans=True, accumulate=True, colsum=g["bc2"])
+        dpre1 = self._buf("dpre1", (M, 2 * H))
+        gemm(dpre2c, p["Wc2"], dpre1[:, H:], b_trans=True, mask_src=h1[:, H:])
         # -- actor: d(a_loss)/d(logits) in one fused pass over the softmax output --
-        dz = torch.empty_like(prob)
-        loss_row = torch.empty(M, dtype=torch.float32, device=self.device)
-        rc = self._lib.uavnet_actor_head_bwd(_ptr(prob), _ptr(a_his), _ptr(td), M, self.n_a, ENTROPY_BETA, _ptr(dz),
+        dz = self._buf("dz", (M, self.ld_a))[:, :self.n_a]
+        loss_row = self._buf("loss_row", (M,))
+        rc = self._lib.uavnet_actor_head_bwd(_ptr(prob), _ptr(a_his), _ptr(td), M, self.n_a, ENTROPY_BETA, _ptr(dz), self.ld_a,
                                              _ptr(loss_row), self._stream())
         if rc:
             raise RuntimeError("uavnet_actor_head_bwd failed (%d)" % rc)
         a_loss = loss_row.mean()
-        g["Wa3"].addmm_(h2a.t(), dz)
-        g["ba3"].addmv_(dz.t(), ones)
-        dpre2a = (dz @ p["Wa3"].t()) * ((h2a > 0) & (h2a < 6))
-        g["Wa2"].addmm_(h1[:, :H].t(), dpre2a)
-        g["ba2"].addmv_(dpre2a.t(), ones)
-        torch.mm(dpre2a, p["Wa2"].t(), out=dpre1[:, :H])
-        dpre1.mul_((h1 > 0) & (h1 < 6))
-        g["b1"].addmv_(dpre1.t(), ones)
+        gemm(h2a, dz, g["Wa3"], a_trans=True, accumulate=True, colsum=g["ba3"])
+        dpre2a = gemm(dz, p["Wa3"], self._buf("dpre2a", (M, H)), b_trans=True, mask_src=h2a)
+        gemm(h1[:, :H], dpre2a, g["Wa2"], a_trans=True, accumulate=True, colsum=g["ba2"])
+        gemm(dpre2a, p["Wa2"], dpre1[:, :H], b_trans=True, mask_src=h1[:, :H])
+        gemm(None, dpre1, colsum=g["b1"], accumulate=True)                 # first-layer bias gradient
         rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
                                          self._stream())
         if rc:
@@ -241,8 +265,7 @@ class ACNet:
         flat.copy_(self.flat)
         grad.copy_(self.grad)
         self.flat, self.grad = flat, grad
-        self.p = {k: self.flat[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
-        self.g = {k: self.grad[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        self._bind_views()
         gptrs, pptrs, opened = (vp * world)(), (vp * world)(), []
         gptrs[rank], pptrs[rank] = bufs[0].ptr, bufs[1].ptr
         if world > 1:
@@ -285,8 +308,7 @@ class ACNet:
             self._lib.uavnet_p2p_close(C.c_void_p(ptr))
         flat, grad = self.flat.clone(), self.grad.clone()
         self.flat, self.grad = flat, grad
-        self.p = {k: self.flat[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
-        self.g = {k: self.grad[o:o + n].view(shp) for k, (o, n, shp) in self.segments.items()}
+        self._bind_views()
         for b in q["bufs"]:
             self._lib.uavnet_p2p_free(C.c_void_p(b.ptr))
         self._p2p = None
@@ -357,7 +379,7 @@ class A3CTrainer:
         for t in range(self.T):
             self.buf_idx[t].copy_(env.obs_idx)
             h1 = net.first_layer(self.buf_idx[t], self.buf_h1[t])
-            h2a = torch.addmm(net.p["ba2"], h1[:, :net.h], net.p["Wa2"], out=self.buf_h2a[t]).clamp_(0.0, 6.0)
+            h2a = net._gemm(h1[:, :net.h], net.p["Wa2"], self.buf_h2a[t], bias=net.p["ba2"], relu6=True)
             # softmax + np.random.choice(p=a_prob) (main.py:149,165-169,195) fused; draws keyed by the GLOBAL env id
             _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t])
             _, r, done, _ = env.step(a)                                      # main.py:198

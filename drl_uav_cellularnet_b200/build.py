@@ -16,7 +16,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libuavenv.so")
 SOURCES = ["uavenv.cu", "uavnet.cu"]
-HEADERS = ["env_kernels.cuh", "philox.cuh", os.path.join(ROOT, "include", "uavenv.h"), os.path.join(ROOT, "include", "uavnet.h")]
+HEADERS = ["env_kernels.cuh", "philox.cuh", "tc_gemm.cuh", os.path.join(ROOT, "include", "uavenv.h"), os.path.join(ROOT, "include", "uavnet.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -1,0 +1,440 @@
+// The dense layers of the actor-critic MLP (main.py:148-149,152-153: 200x200, 200x625, 200x1 and their gradients) on
+// the 5th-generation tensor cores: D[M,N] (+)= op(A) . op(B) with tcgen05.mma kind::tf32, accumulators in TMEM, and a
+// fused epilogue (bias, relu6, relu6' mask, row dot = the critic's value head, column sums = bias gradients, split-K
+// accumulation with float REDs).  sm_100a only.
+//
+// Shape of the problem: K is 200 or 625 for the forward / data-gradient GEMMs and 81 920 (the rollout batch) for the
+// weight gradients; N is 200, 625 or 1.  None of the operand shapes is TMA-friendly (625-float rows are not 16-byte
+// multiples, operands are slices of wider activations, the weight gradients read A transposed), so the 256 threads of a
+// CTA stage the operand tiles themselves: global -> registers (next chunk in flight) -> shared memory in the canonical
+// no-swizzle K-major UMMA layout (8 x 16-byte core matrices; transposed sources are transposed on the way in),
+// fence.proxy.async, one elected thread issues the MMAs of the chunk and commits them to the stage's mbarrier.
+//
+// fp32 accuracy: kind::tf32 reads 10 mantissa bits of every operand.  PREC3X stages every tile twice -- hi = the top 19
+// bits, lo = a - hi -- and issues hi.hi + hi.lo + lo.hi into the same accumulator (3xTF32: ~2e-7 relative, what the
+// parity tests of the learner need); the plain mode is one MMA per k-step.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace uavk {
+namespace tc {
+
+constexpr int BM = 128;            // UMMA M (one accumulator row per TMEM lane)
+constexpr int KC = 32;             // reduction elements per stage = 4 MMAs of K = 8
+constexpr int NTHR = 256;
+constexpr int MAX_STAGES = 4;
+constexpr int A_TILE_BYTES = BM * KC * 4;
+constexpr int SMEM_BUDGET_3X = 200 * 1024;       // one CTA per SM
+constexpr int SMEM_BUDGET_1X = 100 * 1024;       // two CTAs per SM: one CTA's epilogue overlaps the other's main loop
+constexpr int EPI_BYTES = (NTHR / 32) * 32 * 33 * 4;       // per-warp 32 x 33 transposition buffers
+
+struct GemmArgs {
+    const float *A; long long lda; int a_trans;      // a_trans = 0: A[M,K] row-major; 1: stored [K,M] row-major
+    const float *B; long long ldb; int b_trans;      // b_trans = 0: B[K,N] row-major; 1: stored [N,K] row-major
+    float *D; long long ldd;
+    long long M; int N; long long K;
+    int BN, tiles_n, stages, tmem_cols;
+    int split_k; long long k_per_split;
+    const float *bias; int relu6;
+    const float *mask_src; long long ld_mask;
+    int accumulate;
+    float *colsum;
+    const float *dot_w; const float *dot_b; float *dot_out;
+    int a_vec, b_vec;                                 // 16-byte loads legal for the operand
+    unsigned int *err;
+    int dbg;                                          // descriptor experiments (UAVNET_GEMM_DBG), 0 in production
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+
+// Bounded wait: a protocol error must not hang the GPU.  After ~2 s the CTA gives up (sticky), the error word is set
+// and the host entry point's caller finds it with uavnet_gemm_check.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile int *dead, unsigned int *err) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (*dead) return;
+        if (clock64() - t0 > 4000000000LL) {
+            *dead = 1;
+            if (err) atomicOr(err, 1u);
+            return;
+        }
+    }
+}
+
+// Shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): start address, leading-dimension byte
+// offset (between the core matrices along K), stride byte offset (between the core matrices along M/N), version 1.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32: D = F32 (bits 4-5 = 1), A/B format TF32 (bits 7-9, 10-12 = 2), a_major bit
+// 15, b_major bit 16 (1 = MN-major), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__device__ __forceinline__ uint32_t instr_desc(int a_mn, int b_mn, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+}
+
+// ---- operand staging -------------------------------------------------------------------------------------------------
+// A tile of R rows (R = 128 for A, BN for B; the M/N index of the GEMM) x KC reduction elements is R * 8 float4 items;
+// thread t takes items t, t + 256, ...  Shared memory always holds the K-major no-swizzle layout: byte offset of (r, k) =
+//   (r >> 3) * 1024 + (k >> 2) * 128 + (r & 7) * 16 + (k & 3) * 4          (LBO = 128, SBO = 1024)
+// (kind::tf32 with MN-major descriptors returned zeros on B200 in every variant tried, profiles/gemm_debug.py; the
+// transposition therefore happens on the way into shared memory.)
+//
+// Row-major source [rows, k] (k contiguous): a float4 is 4 consecutive k of one row = one 16-byte piece of a core
+// matrix; every quarter-warp writes 128 contiguous bytes and reads 64 contiguous bytes per global row.
+// Transposed source [k, rows] (rows contiguous): a float4 is 4 consecutive rows of one k.  A warp item covers 16 k x
+// 8 rows (one 32-byte sector per k, fully used); the four components go out as scalar stores in an order rotated by
+// lane >> 3, which makes the 32 lanes of every store hit 32 different banks.
+// In both mappings a thread's item j is its item 0 moved down by 32 rows (4096 bytes of shared memory).
+template <bool TRANS>
+struct Stager {
+    // hot path (full chunks of vector-loadable operands): one predicated LDG.128 per item from base + k0 * kstride +
+    // j * jstride, one STS.128 (or four rotated scalar STS) at immediate offsets
+    const float *base;     // (row0, kk) of the source
+    long long jstride;     // elements between a thread's items (32 rows)
+    long long kstride;     // elements per unit of k
+    uint32_t valid;        // bit j: item j is a plain in-bounds vector load
+    uint32_t special;      // bit j: item j exists but needs the careful path (partial vector, appended row of ones)
+    uint32_t so[4];        // shared-memory byte offsets of item 0: [0] for row-major sources, one per rotated component else
+    int rot;
+    // careful path
+    const float *src;
+    long long ld, row0, rows_valid, ones_row;
+    int kk, n_items, vec_ok;
+
+    __device__ __forceinline__ void init(const float *s, long long ld_, int vec, int R, long long r0, long long rv, long long ones, int tid) {
+        src = s; ld = ld_; vec_ok = vec; rows_valid = rv; ones_row = ones;
+        const int l = tid & 31, w = tid >> 5;
+        n_items = (R * 8 - tid + NTHR - 1) / NTHR;
+        if (n_items < 0) n_items = 0;
+        int rlo = 0;
+        if (!TRANS) {
+            const int r_in = l & 7, q = ((w & 1) << 2) | (l >> 3), g = w >> 1;
+            row0 = r0 + g * 8 + r_in;
+            kk = q * 4;
+            rot = 0;
+            so[0] = so[1] = so[2] = so[3] = (uint32_t)(g * 1024 + q * 128 + r_in * 16);
+            base = s + row0 * ld_ + kk;
+            jstride = 32 * ld_;
+            kstride = 1;
+        } else {
+            const int t = l >> 3, oct = w >> 1;
+            kk = ((w & 1) << 4) | (t << 2) | (l & 3);
+            rlo = ((l >> 2) & 1) << 2;
+            rot = t;
+            row0 = r0 + oct * 8 + rlo;
+            const uint32_t o = (uint32_t)(oct * 1024 + (kk >> 2) * 128 + (kk & 3) * 4);
+#pragma unroll
+            for (int i = 0; i < 4; i++) so[i] = o + (uint32_t)((rlo + ((i + rot) & 3)) * 16);
+            base = s + kk * ld_ + row0;
+            jstride = 32;
+            kstride = ld_;
+        }
+        valid = special = 0;
+        for (int j = 0; j < n_items; j++) {
+            const long long row = row0 + 32 * j;
+            const bool full = TRANS ? row + 3 < rv : row < rv;
+            const bool part = TRANS ? (row < rv || (ones >= row && ones < row + 4)) : row == ones;
+            if (full && vec) valid |= 1u << j;
+            else if (full || part) special |= 1u << j;
+        }
+    }
+};
+
+// the rare cases: partial vectors, unaligned operands, the appended row of ones -- kept out of line (code size)
+template <bool TRANS>
+__device__ __noinline__ float4 load_item_careful(const float *src, long long ld, long long row, long long rows_valid,
+                                                 long long ones_row, long long k, long long k_end) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!TRANS) {
+        if (row < rows_valid) {
+            const float *p = src + row * ld;
+            if (k < k_end) v.x = __ldg(p + k);
+            if (k + 1 < k_end) v.y = __ldg(p + k + 1);
+            if (k + 2 < k_end) v.z = __ldg(p + k + 2);
+            if (k + 3 < k_end) v.w = __ldg(p + k + 3);
+        } else if (row == ones_row) {
+            v.x = k < k_end ? 1.f : 0.f; v.y = k + 1 < k_end ? 1.f : 0.f;
+            v.z = k + 2 < k_end ? 1.f : 0.f; v.w = k + 3 < k_end ? 1.f : 0.f;
+        }
+    } else if (k < k_end) {
+        const float *p = src + k * ld;
+        if (row < rows_valid) v.x = __ldg(p + row);
+        if (row + 1 < rows_valid) v.y = __ldg(p + row + 1);
+        if (row + 2 < rows_valid) v.z = __ldg(p + row + 2);
+        if (row + 3 < rows_valid) v.w = __ldg(p + row + 3);
+        if (ones_row >= row && ones_row < row + 4) {
+            const int d = (int)(ones_row - row);
+            if (d == 0) v.x = 1.f; else if (d == 1) v.y = 1.f; else if (d == 2) v.z = 1.f; else v.w = 1.f;
+        }
+    }
+    return v;
+}
+
+template <bool TRANS, int MAXI>
+__device__ __forceinline__ void load_tile(float4 (&reg)[MAXI], const Stager<TRANS> &st, long long k0, long long k_end) {
+    if (k0 + KC <= k_end) {                                   // CTA-uniform: a full chunk
+        const float *p = st.base + k0 * st.kstride;
+#pragma unroll
+        for (int j = 0; j < MAXI; j++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (st.valid & (1u << j)) v = __ldg(reinterpret_cast<const float4 *>(p));
+            else if (st.special & (1u << j))
+                v = load_item_careful<TRANS>(st.src, st.ld, st.row0 + 32 * j, st.rows_valid, st.ones_row, k0 + st.kk, k_end);
+            reg[j] = v;
+            p += st.jstride;
+        }
+    } else {                                                  // the last, partial chunk of the reduction
+#pragma unroll
+        for (int j = 0; j < MAXI; j++) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < st.n_items)
+                v = load_item_careful<TRANS>(st.src, st.ld, st.row0 + 32 * j, st.rows_valid, st.ones_row, k0 + st.kk, k_end);
+            reg[j] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+template <bool TRANS, int MAXI, bool PREC3X>
+__device__ __forceinline__ void store_tile(const float4 (&reg)[MAXI], const Stager<TRANS> &st, uint8_t *tile_hi, uint8_t *tile_lo) {
+#pragma unroll
+    for (int j = 0; j < MAXI; j++) {
+        if (j < st.n_items) {
+            float4 v = reg[j];
+            if (!TRANS) {
+                uint8_t *d = tile_hi + st.so[0] + j * 4096;
+                if (PREC3X) {
+                    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+                    *reinterpret_cast<float4 *>(d) = h;
+                    *reinterpret_cast<float4 *>(tile_lo + st.so[0] + j * 4096) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                } else {
+                    *reinterpret_cast<float4 *>(d) = v;
+                }
+            } else {
+                // rotate the components by rot (two conditional stages), then four scalar stores at fixed offsets
+                if (st.rot & 1) { const float t0 = v.x; v.x = v.y; v.y = v.z; v.z = v.w; v.w = t0; }
+                if (st.rot & 2) { const float t0 = v.x, t1 = v.y; v.x = v.z; v.y = v.w; v.z = t0; v.w = t1; }
+                const float c[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (PREC3X) {
+                        const float h = tf32_hi(c[i]);
+                        *reinterpret_cast<float *>(tile_hi + st.so[i] + j * 4096) = h;
+                        *reinterpret_cast<float *>(tile_lo + st.so[i] + j * 4096) = c[i] - h;
+                    } else {
+                        *reinterpret_cast<float *>(tile_hi + st.so[i] + j * 4096) = c[i];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// PREC3X: 3xTF32;  AT: A is stored [K, M];  BS: B is stored [K, N] (the source of the B tile is transposed)
+template <bool PREC3X, bool AT, bool BS>
+__global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid_constant__ GemmArgs g) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bars[MAX_STAGES + 1];
+    __shared__ uint32_t tmem_slot;
+    __shared__ int dead;
+    __shared__ float dot_part[2][BM];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int split = blockIdx.x % g.split_k;
+    const int t = blockIdx.x / g.split_k;
+    const int tn = t % g.tiles_n;
+    const long long m0 = (long long)(t / g.tiles_n) * BM;
+    const int n0 = tn * g.BN;
+    int bn_eff = ((g.N - n0 + 15) >> 4) << 4;
+    if (bn_eff > g.BN) bn_eff = g.BN;
+    const long long k_begin = (long long)split * g.k_per_split;
+    long long k_end = k_begin + g.k_per_split;
+    if (k_end > g.K) k_end = g.K;
+    const int nchunks = (int)((k_end - k_begin + KC - 1) / KC);
+    if (nchunks <= 0) return;                                   // uniform over the CTA, nothing allocated yet
+
+    const int b_tile_bytes = g.BN * KC * 4;
+    const int stage_bytes = (A_TILE_BYTES + b_tile_bytes) * (PREC3X ? 2 : 1);
+
+    if (tid == 0) {
+        for (int s = 0; s <= MAX_STAGES; s++) mbar_init(smem_u32(&bars[s]), 1);
+        dead = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = instr_desc(0, 0, bn_eff);
+
+    Stager<AT> sa;
+    Stager<BS> sb;
+    sa.init(g.A, g.lda, g.a_vec, BM, m0, g.M, g.colsum ? g.M : -1, tid);       // a row of ones appended to A: bias gradient
+    sb.init(g.B, g.ldb, g.b_vec, g.BN, n0, g.N, -1, tid);
+
+    float4 ra[4], rb[8];
+    for (int i = -1; i < nchunks; i++) {
+        uint8_t *st = nullptr;
+        if (i >= 0) {
+            const int s = i % g.stages, u = i / g.stages;
+            if (u > 0) mbar_wait(smem_u32(&bars[s]), (uint32_t)((u - 1) & 1), &dead, g.err);
+            st = smem + (size_t)s * stage_bytes;
+            store_tile<AT, 4, PREC3X>(ra, sa, st, st + A_TILE_BYTES + b_tile_bytes);
+            store_tile<BS, 8, PREC3X>(rb, sb, st + A_TILE_BYTES, st + 2 * A_TILE_BYTES + b_tile_bytes);
+        }
+        if (i + 1 < nchunks) {                                   // the next chunk's loads fly during the barrier and the MMAs
+            const long long k0 = k_begin + (long long)(i + 1) * KC;
+            load_tile<AT, 4>(ra, sa, k0, k_end);
+            load_tile<BS, 8>(rb, sb, k0, k_end);
+        }
+        if (i >= 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // both operands sit K-major in shared memory: 256 bytes per k-step of 8, LBO 128, SBO 1024
+                const uint32_t a_hi = smem_u32(st), b_hi = a_hi + A_TILE_BYTES;
+                const uint32_t a_lo = b_hi + b_tile_bytes, b_lo = a_lo + A_TILE_BYTES;
+#pragma unroll
+                for (int j = 0; j < KC / 8; j++) {
+                    const uint64_t da = smem_desc(a_hi + j * 256, 128u, 1024u), db = smem_desc(b_hi + j * 256, 128u, 1024u);
+                    if (PREC3X) {
+                        const uint64_t dal = smem_desc(a_lo + j * 256, 128u, 1024u), dbl = smem_desc(b_lo + j * 256, 128u, 1024u);
+                        mma_tf32(tmem, dal, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                        mma_tf32(tmem, da, dbl, idesc, 1u);
+                        mma_tf32(tmem, da, db, idesc, 1u);
+                    } else {
+                        mma_tf32(tmem, da, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
+                    }
+                }
+                mma_commit(smem_u32(&bars[i % g.stages]));       // the stage is free once these MMAs have read it
+                if (i == nchunks - 1) mma_commit(smem_u32(&bars[MAX_STAGES]));
+            }
+        }
+    }
+    mbar_wait(smem_u32(&bars[MAX_STAGES]), 0u, &dead, g.err);      // every MMA has written the accumulator
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    __syncthreads();                                               // stage memory is reused below
+
+    // ---- epilogue: TMEM -> registers (thread = row) -> per-warp transposition buffer -> coalesced global rows ----
+    const int lane_base = (warp & 3) * 32, half = warp >> 2;
+    float *buf = reinterpret_cast<float *>(smem) + warp * (32 * 33);
+    const long long rows_total = g.M + (g.colsum ? 1 : 0);
+    const long long row_base = m0 + lane_base;
+    float dot = 0.f;
+    for (int c0 = half * 32; c0 < bn_eff; c0 += 64) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
+        if (g.bias || g.relu6 || g.dot_w) {
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const int col = n0 + c0 + j;
+                if (col < g.N) {
+                    if (g.bias) v[j] += __ldg(g.bias + col);
+                    if (g.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
+                    if (g.dot_w) dot += v[j] * __ldg(g.dot_w + col);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j++) buf[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int col = n0 + c0 + lane;
+        if (col < g.N && c0 + lane < bn_eff && row_base < rows_total) {
+            if (g.D) {
+                float *dp = g.D + row_base * g.ldd + col;
+                const float *mp = g.mask_src ? g.mask_src + row_base * g.ld_mask + col : nullptr;
+                for (int r8 = 0; r8 < 32; r8 += 8) {
+                    float x[8], m[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {                  // the mask loads of 8 rows in flight together
+                        x[q] = buf[(r8 + q) * 33 + lane];
+                        m[q] = (mp && row_base + r8 + q < g.M) ? __ldg(mp + (long long)(r8 + q) * g.ld_mask) : 1.f;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        if (row_base + r8 + q < g.M) {
+                            const float y = (m[q] > 0.f && m[q] < 6.f) ? x[q] : 0.f;
+                            if (g.accumulate) atomicAdd(dp + (long long)(r8 + q) * g.ldd, y);
+                            else dp[(long long)(r8 + q) * g.ldd] = y;
+                        }
+                    }
+                }
+            }
+            if (g.colsum && g.M >= row_base && g.M < row_base + 32) atomicAdd(g.colsum + col, buf[(int)(g.M - row_base) * 33 + lane]);
+        }
+        __syncwarp();
+    }
+    if (g.dot_out) {
+        dot_part[half][lane_base + lane] = dot;
+        __syncthreads();
+        if (tid < BM && m0 + tid < g.M) g.dot_out[m0 + tid] = dot_part[0][tid] + dot_part[1][tid] + (g.dot_b ? __ldg(g.dot_b) : 0.f);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(g.tmem_cols) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace uavk

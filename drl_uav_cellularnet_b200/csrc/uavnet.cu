@@ -11,6 +11,8 @@
 #include <string.h>
 
 #include "philox.cuh"
+#include "tc_gemm.cuh"
+#include <stdlib.h>
 
 namespace uavk {
 
@@ -100,7 +102,8 @@ __global__ void __launch_bounds__(NET_THREADS) rmsprop_kernel(float *__restrict_
 template <int PL>   // PL = ceil(A / 32) register slots per lane; 0 = any A, probabilities re-read for the second pass
 __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float *__restrict__ prob, const long long *__restrict__ a_his,
                                                                      const float *__restrict__ td, long long M, int A, float beta,
-                                                                     float inv_m, float *__restrict__ dz, float *__restrict__ loss_row) {
+                                                                     float inv_m, float *__restrict__ dz, long long ldz,
+                                                                     float *__restrict__ loss_row) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * NET_THREADS + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * NET_THREADS) >> 5;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
         const float pa = pr[a];
         const float ga = -t * inv_m / (pa + 1e-5f);
         float ent = 0.f, dot = 0.f;                       // sum p*lp (= -H), sum p*g
-        float *dr = dz + m * A;
+        float *dr = dz + m * ldz;
         if constexpr (PL > 0) {
             float pv[PL], gv[PL];                         // the row lives in registers between the two passes
 #pragma unroll
@@ -276,16 +279,16 @@ int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
 }
 
 int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
-                          float *dz, float *loss_row, void *stream) {
-    if (!prob || !a_his || !td || !dz || M < 1 || A < 1) return UAVNET_EINVAL;
+                          float *dz, int64_t ldz, float *loss_row, void *stream) {
+    if (!prob || !a_his || !td || !dz || M < 1 || A < 1 || ldz < A) return UAVNET_EINVAL;
     const int grid = grid_for(M * 32);
     const float inv_m = 1.0f / (float)M;
     const long long *ah = (const long long *)a_his;
     cudaStream_t st = (cudaStream_t)stream;
-    if (A <= 256) actor_head_bwd_kernel<8><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
-    else if (A <= 640) actor_head_bwd_kernel<20><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
-    else if (A <= 1024) actor_head_bwd_kernel<32><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
-    else actor_head_bwd_kernel<0><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, loss_row);
+    if (A <= 256) actor_head_bwd_kernel<8><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, ldz, loss_row);
+    else if (A <= 640) actor_head_bwd_kernel<20><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, ldz, loss_row);
+    else if (A <= 1024) actor_head_bwd_kernel<32><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, ldz, loss_row);
+    else actor_head_bwd_kernel<0><<<grid, NET_THREADS, 0, st>>>(prob, ah, td, M, A, beta, inv_m, dz, ldz, loss_row);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
@@ -356,6 +359,94 @@ int uavnet_rmsprop(float *param, float *grad, float *ms, int64_t n, float lr, fl
     rmsprop_kernel<<<grid_for((n + 3) / 4), NET_THREADS, 0, (cudaStream_t)stream>>>(param, grad, ms, n, lr, decay, eps,
                                                                                    grad_scale, zero_grad);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+// ---- dense layers on the tensor cores (tc_gemm.cuh) ----
+static unsigned int *g_gemm_err = nullptr;          // device word, sticky: a CTA gave up on an mbarrier (protocol error)
+
+int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
+    if (!d || !d->B || d->M < 0 || d->N < 1 || d->K < 1 || d->N > 65536) return UAVNET_EINVAL;
+    if (d->M > 0 && !d->A) return UAVNET_EINVAL;
+    if (!d->D && !d->colsum && !d->dot_out) return UAVNET_EINVAL;
+    if (d->M == 0 && !d->colsum) return UAVNET_EINVAL;
+    if ((d->D && d->ldd < d->N) || (d->mask_src && d->ld_mask < d->N)) return UAVNET_EINVAL;
+    if (d->a_trans ? d->lda < d->M : d->lda < d->K) { if (d->M > 0) return UAVNET_EINVAL; }
+    if (d->b_trans ? d->ldb < d->K : d->ldb < d->N) return UAVNET_EINVAL;
+    if (d->split_k < 0 || (d->split_k > 1 && !d->accumulate)) return UAVNET_EINVAL;
+    if (d->colsum && !d->accumulate) return UAVNET_EINVAL;                  // the ones row accumulates like the rest
+    if (d->accumulate && (d->bias || d->relu6 || d->dot_out)) return UAVNET_EINVAL;
+    if (d->dot_out && (!d->dot_w || d->N > 256)) return UAVNET_EINVAL;
+    if (d->precision != UAVNET_GEMM_TF32 && d->precision != UAVNET_GEMM_3XTF32) return UAVNET_EINVAL;
+    const bool p3 = d->precision == UAVNET_GEMM_3XTF32;
+    tc::GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A = d->A; g.lda = d->lda; g.a_trans = d->a_trans ? 1 : 0;
+    g.B = d->B; g.ldb = d->ldb; g.b_trans = d->b_trans ? 1 : 0;
+    g.D = d->D; g.ldd = d->ldd; g.M = d->M; g.N = d->N; g.K = d->K;
+    g.bias = d->bias; g.relu6 = d->relu6; g.mask_src = d->mask_src; g.ld_mask = d->ld_mask; g.accumulate = d->accumulate;
+    g.colsum = d->colsum; g.dot_w = d->dot_w; g.dot_b = d->dot_b; g.dot_out = d->dot_out;
+    // N tile: as few tiles as possible, each a multiple of 16 columns, at most 256
+    const int bn_max = 256;
+    const int tiles_n = (d->N + bn_max - 1) / bn_max;
+    g.tiles_n = tiles_n;
+    g.BN = (((d->N + tiles_n - 1) / tiles_n) + 15) / 16 * 16;
+    g.tmem_cols = 32;
+    while (g.tmem_cols < g.BN) g.tmem_cols <<= 1;
+    const int stage_bytes = (tc::A_TILE_BYTES + g.BN * tc::KC * 4) * (p3 ? 2 : 1);
+    const int budget = p3 ? tc::SMEM_BUDGET_3X : tc::SMEM_BUDGET_1X;
+    g.stages = budget / stage_bytes;
+    if (g.stages > tc::MAX_STAGES) g.stages = tc::MAX_STAGES;
+    if (g.stages < 2) return UAVNET_EINVAL;
+    int smem = g.stages * stage_bytes;
+    if (smem < tc::EPI_BYTES) smem = tc::EPI_BYTES;
+    const long long rows = d->M + (d->colsum ? 1 : 0);
+    const long long tiles_m = (rows + tc::BM - 1) / tc::BM;
+    const long long chunks = (d->K + tc::KC - 1) / tc::KC;
+    long long split = d->split_k;
+    if (!d->accumulate) split = 1;
+    else if (split == 0) {                          // fill the GPU about twice
+        split = (2 * 148) / (tiles_m * tiles_n);
+        if (split < 1) split = 1;
+    }
+    if (split > chunks) split = chunks;
+    const long long cps = (chunks + split - 1) / split;
+    g.k_per_split = cps * tc::KC;
+    g.split_k = (int)((chunks + cps - 1) / cps);
+    const long long grid = tiles_m * tiles_n * g.split_k;
+    if (grid < 1 || grid > 0x7fffffffLL) return UAVNET_EINVAL;
+    g.a_vec = d->A && aligned16(d->A) && (d->lda % 4 == 0);
+    g.b_vec = aligned16(d->B) && (d->ldb % 4 == 0);
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("UAVNET_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    g.dbg = dbg;
+    if (!g_gemm_err) {
+        if (cudaMalloc(&g_gemm_err, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); g_gemm_err = nullptr; return UAVNET_ECUDA; }
+        cudaMemset(g_gemm_err, 0, sizeof(unsigned int));
+    }
+    g.err = g_gemm_err;
+    typedef void (*kern_t)(const tc::GemmArgs);
+    static const kern_t kerns[8] = {
+        tc::gemm_kernel<false, false, false>, tc::gemm_kernel<false, false, true>, tc::gemm_kernel<false, true, false>,
+        tc::gemm_kernel<false, true, true>,   tc::gemm_kernel<true, false, false>, tc::gemm_kernel<true, false, true>,
+        tc::gemm_kernel<true, true, false>,   tc::gemm_kernel<true, true, true>};
+    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+    const int which = (p3 ? 4 : 0) | (g.a_trans ? 2 : 0) | (g.b_trans ? 0 : 1);   // B stored [K,N]: its tile source is transposed
+    if (!attr_done[which]) {
+        if (cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess) {
+            cudaGetLastError();
+            return UAVNET_ECUDA;
+        }
+        attr_done[which] = true;
+    }
+    kerns[which]<<<(unsigned)grid, tc::NTHR, smem, (cudaStream_t)stream>>>(g);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_gemm_check(void) {
+    if (!g_gemm_err) return 0;
+    unsigned int v = 0;
+    if (cudaMemcpy(&v, g_gemm_err, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return UAVNET_ECUDA; }
+    return (int)v;
 }
 
 }  // extern "C"

@@ -5,7 +5,7 @@
  * trains them with two RMSProp optimisers (main.py:300-301) from 10-step rollouts (main.py:212-238).  The observation
  * has ~44 non-zero cells of 50 000, so the first layer is a gather-sum of weight rows: the env kernel emits the
  * non-zero cells as flat indices (uavenv_out.obs_idx) and these entry points consume them.  The small dense layers
- * (200x200, 200x625) are plain library GEMMs on the Python side.
+ * (200x200, 200x625, 200x1) and their gradients run on the tcgen05 tensor cores through uavnet_gemm.
  *
  * Plain C types, raw device pointers, the stream is a cudaStream_t passed as void*.  Every entry point returns 0 or a
  * negative UAVNET_E* code and only enqueues work on the stream.
@@ -45,9 +45,10 @@ int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t se
 /* d(a_loss)/d(logits) of the actor loss (main.py:68-76), fused over the softmax output:
  *   a_loss = mean_i -( log(prob[i,a_i] + 1e-5) * td_i + beta * H_i ),  H_i = -sum_j prob_ij log(prob_ij + 1e-5)
  * prob float32 [M,A] (softmax output), a_his int64 [M], td float32 [M] (v_target - v, treated as constant),
- * dz float32 [M,A] out, loss_row float32 [M] out (the per-sample loss term; its mean is a_loss; may be NULL). */
+ * dz float32 [M,A] out with leading dimension ldz >= A (rows padded to 16 bytes feed uavnet_gemm's vector path),
+ * loss_row float32 [M] out (the per-sample loss term; its mean is a_loss; may be NULL). */
 int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
-                          float *dz, float *loss_row, void *stream);
+                          float *dz, int64_t ldz, float *loss_row, void *stream);
 
 /* TensorFlow-1 RMSPropOptimizer step (main.py:300-301; decay 0.9, momentum 0, epsilon 1e-10, slot `ms` starts at 1):
  *   g = grad * grad_scale;  ms = decay*ms + (1-decay)*g*g;  param -= lr * g / sqrt(ms + eps);  grad = 0 (if zero_grad)
@@ -74,6 +75,37 @@ int uavnet_p2p_free(void *dev_ptr);
  * parameters after all ranks' launches completed (two stream-ordered collectives, e.g. 4-byte all-reduces). */
 int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_local, int64_t n, int32_t rank, int32_t world,
                        float lr, float decay, float eps, void *stream);
+
+/* ---- the dense layers (main.py:148-149,152-153: 200->200 relu6, 200->625 softmax logits, 200->1) and their gradients
+ * on the 5th-generation tensor cores: tcgen05.mma kind::tf32, fp32 accumulation in tensor memory, fused epilogue ----
+ *   D[M,N] (+)= op(A)[M,K] . op(B)[K,N]
+ *   a_trans = 0: A is [M,K] row-major (leading dimension lda);  1: A is stored [K,M] row-major (weight gradients X^T . dY)
+ *   b_trans = 0: B is [K,N] row-major (a weight matrix as tf.layers.dense stores it);  1: B is stored [N,K] row-major
+ *                (data gradients dY . W^T read the same weight matrix)
+ * epilogue, in this order: + bias[N]; relu6; dot_out[m] = sum_n D[m,n] * dot_w[n] + *dot_b (the critic's value head on top
+ * of its second layer; N <= 256); D *= (0 < mask_src[m,n] < 6) (relu6 backward, mask_src = the layer's output); then either
+ * a plain store or, with accumulate != 0, float REDs (D += ...) from split_k slices of K (0 = chosen to fill the GPU).
+ * colsum (accumulate only): colsum[n] += sum_k op(B)[k,n] -- a row of ones appended to op(A), i.e. the bias gradient of
+ * the layer comes out of the same pass; M may be 0 (column sums only).  D may be NULL when only dot_out / colsum is wanted.
+ * precision: UAVNET_GEMM_TF32 (operands rounded to 10 mantissa bits) or UAVNET_GEMM_3XTF32 (hi/lo split, three MMAs per
+ * k-step: fp32-class accuracy).  Any M, N <= 65536, K, leading dimensions and alignments (16-byte aligned operands with
+ * leading dimensions that are multiples of 4 take vector loads).  Only enqueues work; uavnet_gemm_check() synchronises
+ * the device and returns non-zero if any launch since the start gave up on a barrier (a bug, never a data condition). */
+enum { UAVNET_GEMM_TF32 = 0, UAVNET_GEMM_3XTF32 = 1 };
+typedef struct uavnet_gemm_desc {
+    const float *A; int64_t lda; int32_t a_trans;
+    const float *B; int64_t ldb; int32_t b_trans;
+    float *D; int64_t ldd;
+    int64_t M; int32_t N; int64_t K;
+    const float *bias; int32_t relu6;
+    const float *mask_src; int64_t ld_mask;
+    int32_t accumulate; int32_t split_k;
+    float *colsum;
+    const float *dot_w; const float *dot_b; float *dot_out;
+    int32_t precision;
+} uavnet_gemm_desc;
+int uavnet_gemm(const uavnet_gemm_desc *desc, void *stream);
+int uavnet_gemm_check(void);
 
 #ifdef __cplusplus
 }

@@ -19,7 +19,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=8192)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--warmup", type=int, default=3)
-ap.add_argument("--tf32", action="store_true", help="TF32 tensor-core GEMMs for the dense layers (default: fp32 SIMT)")
+ap.add_argument("--tf32", action="store_true", help="dense layers with one tcgen05 TF32 MMA per k-step (default: 3xTF32, fp32-class accuracy)")
 ap.add_argument("--p2p", action="store_true", help="gradient push as one peer-memory kernel (uavnet_p2p_rmsprop) instead of NCCL all-reduce + RMSProp")
 ap.add_argument("--graph", action="store_true", help="also time the iteration replayed as one CUDA graph")
 args = ap.parse_args()
@@ -27,10 +27,8 @@ rank, world, local = udist.world()
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 udist.init("nccl", dev)
-if args.tf32:
-    torch.backends.cuda.matmul.allow_tf32 = True
 env = BatchedMobiEnvironment(args.envs, 4, 40, 100, "group", seed=2026, obs="none", env_offset=rank * args.envs, device=local)
-net = ACNet(env.observation_space_dim, env.action_space_dim, dev)
+net = ACNet(env.observation_space_dim, env.action_space_dim, dev, precision="tf32" if args.tf32 else "fp32")
 if args.p2p:
     net.enable_p2p()
 tr = A3CTrainer(env, net, seed=100 + rank)

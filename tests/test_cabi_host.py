@@ -70,7 +70,11 @@ def test_entry_points_reject_bad_arguments_without_a_gpu(native):
     assert L.uavnet_sparse_fwd(None, 1, 1, 1, None, None, 4, None, 1, None) == -1
     assert L.uavnet_sparse_bwd(None, 1, 1, 1, None, 4, None, None) == -1
     assert L.uavnet_rmsprop(None, None, None, 4, 1e-4, 0.9, 1e-10, 1.0, 1, None) == -1
-    assert L.uavnet_actor_head_bwd(None, None, None, 1, 625, 0.001, None, None, None) == -1
+    assert L.uavnet_actor_head_bwd(None, None, None, 1, 625, 0.001, None, 625, None, None) == -1
+    assert L.uavnet_gemm(None, None) == -1
+    d = native.GemmDesc()
+    assert L.uavnet_gemm(C.byref(d), None) == -1                 # no operands
+    assert L.uavnet_gemm_check() == 0                            # nothing launched: no device access
     h = C.c_void_p()
     assert L.uavenv_create(None, C.byref(h)) == native.EINVAL
 
