@@ -14,6 +14,7 @@
 // bits, lo = a - hi -- and issues hi.hi + hi.lo + lo.hi into the same accumulator (3xTF32: ~2e-7 relative, what the
 // parity tests of the learner need); the plain mode is one MMA per k-step.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -44,7 +45,14 @@ struct GemmArgs {
     int a_vec, b_vec;                                 // 16-byte loads legal for the operand
     unsigned int *err;
     int dbg;                                          // descriptor experiments (UAVNET_GEMM_DBG), 0 in production
+    alignas(64) CUtensorMap tmap_a;                   // operand mode TMA: [rows, K] float32, box 32 x 128 (A) / 32 x BN (B),
+    alignas(64) CUtensorMap tmap_b;                   // 128-byte swizzle
 };
+
+// operand staging modes
+constexpr int OP_ROWMAJOR = 0;     // threads, source [rows, k]
+constexpr int OP_TRANSPOSED = 1;   // threads, source [k, rows], transposed on the way into shared memory
+constexpr int OP_TMA = 2;          // cp.async.bulk.tensor boxes of a [rows, k] source (16-byte aligned, ld % 4 == 0)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,6 +95,28 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
     return d;
+}
+
+// K-major tile as TMA writes it with CU_TENSOR_MAP_SWIZZLE_128B: 128-byte rows, 16-byte pieces XOR-ed with (row & 7);
+// 8-row groups 1024 bytes apart (SBO), layout type 2, the leading offset is not used (1, as CUTLASS encodes it).
+// A k-step of 8 tf32 advances the start address by 32 bytes inside the row.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+                 : "memory");
 }
 
 // cute::UMMA::InstrDescriptor for kind::tf32: D = F32 (bits 4-5 = 1), A/B format TF32 (bits 7-9, 10-12 = 2), a_major bit
@@ -285,11 +315,15 @@ __device__ __forceinline__ void store_tile(const float4 (&reg)[MAXI], const Stag
     }
 }
 
-// PREC3X: 3xTF32;  AT: A is stored [K, M];  BS: B is stored [K, N] (the source of the B tile is transposed)
-template <bool PREC3X, bool AT, bool BS>
+// PREC3X: 3xTF32;  AM / BM_: staging mode of the A / B tile (OP_*)
+template <bool PREC3X, int AM, int BM_>
 __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid_constant__ GemmArgs g) {
+    static_assert(!PREC3X || (AM != OP_TMA && BM_ != OP_TMA), "the hi/lo split needs the operands in registers");
+    constexpr bool ANY_TMA = AM == OP_TMA || BM_ == OP_TMA;
+    constexpr bool ANY_THREADS = AM != OP_TMA || BM_ != OP_TMA;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t bars[MAX_STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[MAX_STAGES + 1];        // stage free (MMAs have read it); [MAX_STAGES]: all done
+    __shared__ __align__(8) uint64_t full[MAX_STAGES];            // TMA bytes of the stage have landed
     __shared__ uint32_t tmem_slot;
     __shared__ int dead;
     __shared__ float dot_part[2][BM];
@@ -310,9 +344,11 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
 
     const int b_tile_bytes = g.BN * KC * 4;
     const int stage_bytes = (A_TILE_BYTES + b_tile_bytes) * (PREC3X ? 2 : 1);
+    const uint32_t tx_bytes = (AM == OP_TMA ? A_TILE_BYTES : 0) + (BM_ == OP_TMA ? b_tile_bytes : 0);
 
     if (tid == 0) {
         for (int s = 0; s <= MAX_STAGES; s++) mbar_init(smem_u32(&bars[s]), 1);
+        for (int s = 0; s < MAX_STAGES; s++) mbar_init(smem_u32(&full[s]), 1);
         dead = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -326,37 +362,58 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
     const uint32_t tmem = tmem_slot;
     const uint32_t idesc = instr_desc(0, 0, bn_eff);
 
-    Stager<AT> sa;
-    Stager<BS> sb;
-    sa.init(g.A, g.lda, g.a_vec, BM, m0, g.M, g.colsum ? g.M : -1, tid);       // a row of ones appended to A: bias gradient
-    sb.init(g.B, g.ldb, g.b_vec, g.BN, n0, g.N, -1, tid);
+    Stager<AM == OP_TRANSPOSED> sa;
+    Stager<BM_ == OP_TRANSPOSED> sb;
+    if (AM != OP_TMA) sa.init(g.A, g.lda, g.a_vec, BM, m0, g.M, g.colsum ? g.M : -1, tid);   // a row of ones appended to A: bias gradient
+    if (BM_ != OP_TMA) sb.init(g.B, g.ldb, g.b_vec, g.BN, n0, g.N, -1, tid);
+
+    // TMA operands: thread 0 keeps stages - 1 chunks in flight (issue for chunk c = the box at k = k_begin + 32 c)
+    auto tma_issue = [&](int c) {
+        const int s = c % g.stages;
+        const uint32_t fb = smem_u32(&full[s]);
+        const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+        const int kc = (int)(k_begin + (long long)c * KC);
+        mbar_expect_tx(fb, tx_bytes);
+        if (AM == OP_TMA) tma_load_2d(dst, &g.tmap_a, kc, (int)m0, fb);
+        if (BM_ == OP_TMA) tma_load_2d(dst + A_TILE_BYTES, &g.tmap_b, kc, n0, fb);
+    };
+    if (ANY_TMA && tid == 0) {
+        for (int c = 0; c < g.stages - 1 && c < nchunks; c++) tma_issue(c);
+    }
 
     float4 ra[4], rb[8];
-    for (int i = -1; i < nchunks; i++) {
+    for (int i = ANY_THREADS ? -1 : 0; i < nchunks; i++) {
         uint8_t *st = nullptr;
         if (i >= 0) {
             const int s = i % g.stages, u = i / g.stages;
-            if (u > 0) mbar_wait(smem_u32(&bars[s]), (uint32_t)((u - 1) & 1), &dead, g.err);
             st = smem + (size_t)s * stage_bytes;
-            store_tile<AT, 4, PREC3X>(ra, sa, st, st + A_TILE_BYTES + b_tile_bytes);
-            store_tile<BS, 8, PREC3X>(rb, sb, st + A_TILE_BYTES, st + 2 * A_TILE_BYTES + b_tile_bytes);
+            if (ANY_THREADS) {
+                if (u > 0) mbar_wait(smem_u32(&bars[s]), (uint32_t)((u - 1) & 1), &dead, g.err);
+                if (AM != OP_TMA) store_tile<AM == OP_TRANSPOSED, 4, PREC3X>(ra, sa, st, st + A_TILE_BYTES + b_tile_bytes);
+                if (BM_ != OP_TMA) store_tile<BM_ == OP_TRANSPOSED, 8, PREC3X>(rb, sb, st + A_TILE_BYTES, st + 2 * A_TILE_BYTES + b_tile_bytes);
+            }
         }
-        if (i + 1 < nchunks) {                                   // the next chunk's loads fly during the barrier and the MMAs
+        if (ANY_THREADS && i + 1 < nchunks) {                    // the next chunk's loads fly during the barrier and the MMAs
             const long long k0 = k_begin + (long long)(i + 1) * KC;
-            load_tile<AT, 4>(ra, sa, k0, k_end);
-            load_tile<BS, 8>(rb, sb, k0, k_end);
+            if (AM != OP_TMA) load_tile<AM == OP_TRANSPOSED, 4>(ra, sa, k0, k_end);
+            if (BM_ != OP_TMA) load_tile<BM_ == OP_TRANSPOSED, 8>(rb, sb, k0, k_end);
         }
         if (i >= 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
+            if (ANY_THREADS) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+            }
             if (tid == 0) {
+                if (ANY_TMA) mbar_wait(smem_u32(&full[i % g.stages]), (uint32_t)((i / g.stages) & 1), &dead, g.err);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // both operands sit K-major in shared memory: 256 bytes per k-step of 8, LBO 128, SBO 1024
+                // thread-staged tiles are K-major without swizzle: 256 bytes per k-step of 8, LBO 128, SBO 1024;
+                // TMA tiles carry the 128-byte swizzle: 32 bytes per k-step inside the row
                 const uint32_t a_hi = smem_u32(st), b_hi = a_hi + A_TILE_BYTES;
                 const uint32_t a_lo = b_hi + b_tile_bytes, b_lo = a_lo + A_TILE_BYTES;
 #pragma unroll
                 for (int j = 0; j < KC / 8; j++) {
-                    const uint64_t da = smem_desc(a_hi + j * 256, 128u, 1024u), db = smem_desc(b_hi + j * 256, 128u, 1024u);
+                    const uint64_t da = AM == OP_TMA ? smem_desc_sw128(a_hi + j * 32) : smem_desc(a_hi + j * 256, 128u, 1024u);
+                    const uint64_t db = BM_ == OP_TMA ? smem_desc_sw128(b_hi + j * 32) : smem_desc(b_hi + j * 256, 128u, 1024u);
                     if (PREC3X) {
                         const uint64_t dal = smem_desc(a_lo + j * 256, 128u, 1024u), dbl = smem_desc(b_lo + j * 256, 128u, 1024u);
                         mma_tf32(tmem, dal, db, idesc, (i > 0 || j > 0) ? 1u : 0u);
@@ -368,6 +425,13 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
                 }
                 mma_commit(smem_u32(&bars[i % g.stages]));       // the stage is free once these MMAs have read it
                 if (i == nchunks - 1) mma_commit(smem_u32(&bars[MAX_STAGES]));
+                if (ANY_TMA) {
+                    const int c = i + g.stages - 1;              // refill the stage chunk i - 1 used
+                    if (c < nchunks) {
+                        if (c >= g.stages) mbar_wait(smem_u32(&bars[c % g.stages]), (uint32_t)(((c / g.stages) - 1) & 1), &dead, g.err);
+                        tma_issue(c);
+                    }
+                }
             }
         }
     }
@@ -376,22 +440,30 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
     __syncthreads();                                               // stage memory is reused below
 
     // ---- epilogue: TMEM -> registers (thread = row) -> per-warp transposition buffer -> coalesced global rows ----
+    // bias / relu6 / mask are applied in the second phase (lane = column: one bias register per lane, the mask read
+    // coalesced); only the value head needs the finished activations in the first phase (thread = row).
     const int lane_base = (warp & 3) * 32, half = warp >> 2;
     float *buf = reinterpret_cast<float *>(smem) + warp * (32 * 33);
-    const long long rows_total = g.M + (g.colsum ? 1 : 0);
     const long long row_base = m0 + lane_base;
+    const float *bias = g.bias, *dot_w = g.dot_w, *mask_src = g.mask_src;
+    float *D = g.D;
+    const bool relu6 = g.relu6 != 0, accumulate = g.accumulate != 0;
+    const long long ldd = g.ldd, ld_mask = g.ld_mask;
+    long long left = g.M - row_base;                              // rows of this warp that exist in D
+    const int nrows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
+    const bool ones_here = g.colsum && left >= 0 && left < 32;    // the appended row of ones lands in this warp's rows
     float dot = 0.f;
     for (int c0 = half * 32; c0 < bn_eff; c0 += 64) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
-        if (g.bias || g.relu6 || g.dot_w) {
+        if (dot_w) {                                               // critic: relu6(. + bias) . w3 per row
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const int col = n0 + c0 + j;
                 if (col < g.N) {
-                    if (g.bias) v[j] += __ldg(g.bias + col);
-                    if (g.relu6) v[j] = fminf(fmaxf(v[j], 0.f), 6.f);
-                    if (g.dot_w) dot += v[j] * __ldg(g.dot_w + col);
+                    float x = v[j] + (bias ? __ldg(bias + col) : 0.f);
+                    if (relu6) x = fminf(fmaxf(x, 0.f), 6.f);
+                    dot += x * __ldg(dot_w + col);
                 }
             }
         }
@@ -399,28 +471,40 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
         for (int j = 0; j < 32; j++) buf[lane * 33 + j] = v[j];
         __syncwarp();
         const int col = n0 + c0 + lane;
-        if (col < g.N && c0 + lane < bn_eff && row_base < rows_total) {
-            if (g.D) {
-                float *dp = g.D + row_base * g.ldd + col;
-                const float *mp = g.mask_src ? g.mask_src + row_base * g.ld_mask + col : nullptr;
-                for (int r8 = 0; r8 < 32; r8 += 8) {
-                    float x[8], m[8];
+        if (col < g.N && c0 + lane < bn_eff) {
+            if (D && nrows > 0) {
+                const float bcol = bias ? __ldg(bias + col) : 0.f;
+                float *dp = D + row_base * ldd + col;
+                const float *mp = mask_src ? mask_src + row_base * ld_mask + col : nullptr;
+                const float *bp = buf + lane;
+                if (nrows == 32) {
+                    for (int r8 = 0; r8 < 32; r8 += 8) {
+                        float x[8], m[8];
 #pragma unroll
-                    for (int q = 0; q < 8; q++) {                  // the mask loads of 8 rows in flight together
-                        x[q] = buf[(r8 + q) * 33 + lane];
-                        m[q] = (mp && row_base + r8 + q < g.M) ? __ldg(mp + (long long)(r8 + q) * g.ld_mask) : 1.f;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        if (row_base + r8 + q < g.M) {
-                            const float y = (m[q] > 0.f && m[q] < 6.f) ? x[q] : 0.f;
-                            if (g.accumulate) atomicAdd(dp + (long long)(r8 + q) * g.ldd, y);
-                            else dp[(long long)(r8 + q) * g.ldd] = y;
+                        for (int q = 0; q < 8; q++) {              // 8 rows in flight: mask loads, then stores
+                            x[q] = bp[(r8 + q) * 33] + bcol;
+                            m[q] = 1.f;
+                            if (mp) { m[q] = __ldg(mp); mp += ld_mask; }
                         }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            float y = relu6 ? fminf(fmaxf(x[q], 0.f), 6.f) : x[q];
+                            y = (m[q] > 0.f && m[q] < 6.f) ? y : 0.f;
+                            if (accumulate) atomicAdd(dp, y); else *dp = y;
+                            dp += ldd;
+                        }
+                    }
+                } else {
+                    for (int rr = 0; rr < nrows; rr++) {
+                        float y = bp[rr * 33] + bcol;
+                        if (relu6) y = fminf(fmaxf(y, 0.f), 6.f);
+                        if (mp) { const float m = __ldg(mp); mp += ld_mask; y = (m > 0.f && m < 6.f) ? y : 0.f; }
+                        if (accumulate) atomicAdd(dp, y); else *dp = y;
+                        dp += ldd;
                     }
                 }
             }
-            if (g.colsum && g.M >= row_base && g.M < row_base + 32) atomicAdd(g.colsum + col, buf[(int)(g.M - row_base) * 33 + lane]);
+            if (ones_here) atomicAdd(g.colsum + col, buf[(int)left * 33 + lane]);
         }
         __syncwarp();
     }

@@ -362,6 +362,23 @@ int uavnet_rmsprop(float *param, float *grad, float *ms, int64_t n, float lr, fl
 }
 
 // ---- dense layers on the tensor cores (tc_gemm.cuh) ----
+typedef CUresult (*tmap_encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D map of a row-major float32 matrix [rows, k] (leading dimension ld elements): boxes of 32 k x box_rows rows,
+// 128-byte swizzle, out-of-range elements read as zero (partial k chunks and partial row tiles need no special case)
+static bool make_tmap(tmap_encode_t encode, CUtensorMap *map, const float *base, long long k, long long rows, long long ld, int box_rows) {
+    if (!encode || k < 1 || rows < 1 || box_rows < 1 || box_rows > 256 || (ld * 4) % 16 != 0) return false;
+    const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::KC, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static unsigned int *g_gemm_err = nullptr;          // device word, sticky: a CTA gave up on an mbarrier (protocol error)
 
 int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
@@ -424,13 +441,37 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
         cudaMemset(g_gemm_err, 0, sizeof(unsigned int));
     }
     g.err = g_gemm_err;
+    // staging mode per operand: TMA boxes for row-major, 16-byte aligned operands (one MMA per k-step only: the hi/lo
+    // split of 3xTF32 needs the data in registers), threads otherwise
+    static int no_tma = -1;
+    if (no_tma < 0) { const char *e = getenv("UAVNET_GEMM_NO_TMA"); no_tma = (e && atoi(e)) ? 1 : 0; }
+    static tmap_encode_t encode = nullptr;
+    if (!encode && !no_tma) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            cudaGetLastError();
+            no_tma = 1;
+        } else {
+            encode = (tmap_encode_t)fn;
+        }
+    }
+    int am = g.a_trans ? tc::OP_TRANSPOSED : tc::OP_ROWMAJOR, bm = g.b_trans ? tc::OP_ROWMAJOR : tc::OP_TRANSPOSED;
+    if (!p3 && !no_tma) {
+        if (am == tc::OP_ROWMAJOR && g.a_vec && !d->colsum && d->M > 0 &&
+            make_tmap(encode, &g.tmap_a, d->A, d->K, d->M, d->lda, tc::BM)) am = tc::OP_TMA;
+        if (bm == tc::OP_ROWMAJOR && g.b_vec && make_tmap(encode, &g.tmap_b, d->B, d->K, d->N, d->ldb, g.BN)) bm = tc::OP_TMA;
+    }
     typedef void (*kern_t)(const tc::GemmArgs);
-    static const kern_t kerns[8] = {
-        tc::gemm_kernel<false, false, false>, tc::gemm_kernel<false, false, true>, tc::gemm_kernel<false, true, false>,
-        tc::gemm_kernel<false, true, true>,   tc::gemm_kernel<true, false, false>, tc::gemm_kernel<true, false, true>,
-        tc::gemm_kernel<true, true, false>,   tc::gemm_kernel<true, true, true>};
-    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
-    const int which = (p3 ? 4 : 0) | (g.a_trans ? 2 : 0) | (g.b_trans ? 0 : 1);   // B stored [K,N]: its tile source is transposed
+#define UAVK_G(P, A_, B_) tc::gemm_kernel<P, A_, B_>
+    static const kern_t kerns[18] = {
+        UAVK_G(false, 0, 0), UAVK_G(false, 0, 1), UAVK_G(false, 0, 2), UAVK_G(false, 1, 0), UAVK_G(false, 1, 1), UAVK_G(false, 1, 2),
+        UAVK_G(false, 2, 0), UAVK_G(false, 2, 1), UAVK_G(false, 2, 2),
+        UAVK_G(true, 0, 0), UAVK_G(true, 0, 1), nullptr, UAVK_G(true, 1, 0), UAVK_G(true, 1, 1), nullptr, nullptr, nullptr, nullptr};
+#undef UAVK_G
+    static bool attr_done[18] = {false};
+    const int which = (p3 ? 9 : 0) + am * 3 + bm;
+    if (!kerns[which]) return UAVNET_EINVAL;
     if (!attr_done[which]) {
         if (cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess) {
             cudaGetLastError();
