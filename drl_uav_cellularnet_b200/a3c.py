@@ -94,6 +94,20 @@ class ACNet:
             self.p[k].copy_(torch.randn(self.segments[k][3], generator=gen) * 0.1)
         self.n_params = sum(int(np.prod(shp)) for _, _, _, shp in self.segments.values())
         self._scratch = {}
+        # [N, K] copies of the forward weights: both operands of the forward GEMMs are then row-major and go through TMA
+        self.pt = {"Wa2": torch.empty((H, H), dtype=torch.float32, device=self.device),
+                   "Wa3": torch.empty((self.n_a, H), dtype=torch.float32, device=self.device),
+                   "Wc2": torch.empty((H, H), dtype=torch.float32, device=self.device)}
+        self._pt_seen = None
+
+    def _sync_transposed(self):
+        """Refresh the transposed weight copies if the parameters changed (torch's version counter sees in-place edits
+        through any view; ``apply_grads`` / ``enable_p2p`` mark the raw-pointer writes)."""
+        seen = (self.flat.data_ptr(), self.flat._version)
+        if self._pt_seen != seen:
+            for k, t in self.pt.items():
+                t.copy_(self.p[k].t())
+            self._pt_seen = (self.flat.data_ptr(), self.flat._version)
 
     def _bind_views(self):
         def views(buf):
@@ -135,12 +149,13 @@ class ACNet:
         """-> (a_prob [M, N_A] or None, v [M] or None, cache).  `out`: preallocated h1 / h2a / prob buffers (the
         trainer's rollout storage) to write the activations into."""
         H, p = self.h, self.p
+        self._sync_transposed()
         h1 = self.first_layer(idx, None if out is None else out["h1"])
         cache = {"idx": idx, "h1": h1}
         prob = v = None
         if want in ("both", "actor"):
-            h2a = self._gemm(h1[:, :H], p["Wa2"], None if out is None else out["h2a"], bias=p["ba2"], relu6=True)
-            logits = self._gemm(h2a, p["Wa3"], bias=p["ba3"])
+            h2a = self.actor_hidden(h1, None if out is None else out["h2a"])
+            logits = self._gemm(h2a, self.pt["Wa3"], b_trans=True, bias=p["ba3"])
             prob = torch.softmax(logits, dim=1, out=None if out is None else out["prob"])
             cache.update(h2a=h2a, prob=prob)
         if want in ("both", "critic"):
@@ -148,14 +163,20 @@ class ACNet:
             cache.update(h2c=h2c, v=v)
         return prob, v, cache
 
+    def actor_hidden(self, h1: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """h2a = relu6(h1[:, :H] @ Wa2 + ba2) (main.py:148)"""
+        self._sync_transposed()
+        return self._gemm(h1[:, :self.h], self.pt["Wa2"], out, b_trans=True, bias=self.p["ba2"], relu6=True)
+
     def critic_head(self, h1: torch.Tensor, h2c_out: Optional[torch.Tensor] = None, v_out: Optional[torch.Tensor] = None):
         """h2c = relu6(h1[:, H:] @ Wc2 + bc2), v = h2c @ Wc3 + bc3 (main.py:152-153) in one launch: the value head is a
         row dot in the epilogue of the second layer -> (h2c [M, H], v [M])"""
         H, p = self.h, self.p
         M = h1.shape[0]
         v = v_out if v_out is not None else torch.empty(M, dtype=torch.float32, device=self.device)
-        h2c = self._gemm(h1[:, H:], p["Wc2"], h2c_out, bias=p["bc2"], relu6=True, dot_w=p["Wc3"].view(-1), dot_b=p["bc3"],
-                         dot_out=v)
+        self._sync_transposed()
+        h2c = self._gemm(h1[:, H:], self.pt["Wc2"], h2c_out, b_trans=True, bias=p["bc2"], relu6=True, dot_w=p["Wc3"].view(-1),
+                         dot_b=p["bc3"], dot_out=v)
         return h2c, v
 
     def sample_head(self, h2a: torch.Tensor, seed: int, row_offset: int, counter_dev: Optional[torch.Tensor], counter_add: int,
@@ -163,7 +184,8 @@ class ACNet:
         """logits = h2a @ Wa3 + ba3, then softmax + np.random.choice(p=a_prob) in one kernel (uavnet_softmax_sample,
         Philox keyed by (seed, row_offset + row, *counter_dev + counter_add)) -> (prob [M, N_A], action int64 [M])"""
         M = h2a.shape[0]
-        logits = self._gemm(h2a, self.p["Wa3"], self._buf("logits", (M, self.n_a)), bias=self.p["ba3"])
+        self._sync_transposed()
+        logits = self._gemm(h2a, self.pt["Wa3"], self._buf("logits", (M, self.n_a)), b_trans=True, bias=self.p["ba3"])
         prob = prob_out if prob_out is not None else torch.empty_like(logits)
         action = torch.empty(M, dtype=torch.int64, device=self.device)
         rc = self._lib.uavnet_softmax_sample(_ptr(logits), M, self.n_a, int(seed), int(row_offset), _ptr(counter_dev),
@@ -233,6 +255,7 @@ class ACNet:
     def apply_grads(self, lr: float = LR_A, world_size: int = 1):
         """grad /= world_size (after the caller's all-reduce), RMSProp step on every parameter, grad = 0.
         With ``enable_p2p()`` the all-reduce is not needed: one peer-memory kernel does reduce + step + broadcast."""
+        self._pt_seen = None                       # the kernels below write the parameters through raw pointers
         if getattr(self, "_p2p", None):
             return self._apply_grads_p2p(lr)
         rc = self._lib.uavnet_rmsprop(_ptr(self.flat), _ptr(self.grad), _ptr(self.ms), self.n_flat, lr, RMS_DECAY, RMS_EPS,
@@ -379,7 +402,7 @@ class A3CTrainer:
         for t in range(self.T):
             self.buf_idx[t].copy_(env.obs_idx)
             h1 = net.first_layer(self.buf_idx[t], self.buf_h1[t])
-            h2a = net._gemm(h1[:, :net.h], net.p["Wa2"], self.buf_h2a[t], bias=net.p["ba2"], relu6=True)
+            h2a = net.actor_hidden(h1, self.buf_h2a[t])
             # softmax + np.random.choice(p=a_prob) (main.py:149,165-169,195) fused; draws keyed by the GLOBAL env id
             _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t])
             _, r, done, _ = env.step(a)                                      # main.py:198

@@ -78,6 +78,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatil
     if (mbar_try(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try(bar, parity)) {
+        __nanosleep(40);
         if (*dead) return;
         if (clock64() - t0 > 4000000000LL) {
             *dead = 1;
@@ -256,25 +257,21 @@ __device__ __noinline__ float4 load_item_careful(const float *src, long long ld,
 
 template <bool TRANS, int MAXI>
 __device__ __forceinline__ void load_tile(float4 (&reg)[MAXI], const Stager<TRANS> &st, long long k0, long long k_end) {
-    if (k0 + KC <= k_end) {                                   // CTA-uniform: a full chunk
-        const float *p = st.base + k0 * st.kstride;
+    // in a partial last chunk an item is either wholly inside the reduction range (plain vector load), wholly outside
+    // (zeros), or -- row-major sources with K % 4 != 0 only -- straddles its end (careful path)
+    const long long k = k0 + st.kk;
+    const bool k_in = TRANS ? k < k_end : k + 3 < k_end;
+    const bool k_part = !TRANS && k < k_end && !k_in;
+    const float *p = st.base + k0 * st.kstride;
 #pragma unroll
-        for (int j = 0; j < MAXI; j++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (st.valid & (1u << j)) v = __ldg(reinterpret_cast<const float4 *>(p));
-            else if (st.special & (1u << j))
-                v = load_item_careful<TRANS>(st.src, st.ld, st.row0 + 32 * j, st.rows_valid, st.ones_row, k0 + st.kk, k_end);
-            reg[j] = v;
-            p += st.jstride;
-        }
-    } else {                                                  // the last, partial chunk of the reduction
-#pragma unroll
-        for (int j = 0; j < MAXI; j++) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (j < st.n_items)
-                v = load_item_careful<TRANS>(st.src, st.ld, st.row0 + 32 * j, st.rows_valid, st.ones_row, k0 + st.kk, k_end);
-            reg[j] = v;
-        }
+    for (int j = 0; j < MAXI; j++) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t bit = 1u << j;
+        if ((st.valid & bit) && k_in) v = __ldg(reinterpret_cast<const float4 *>(p));
+        else if (((st.special & bit) && (k_in || k_part)) || ((st.valid & bit) && k_part))
+            v = load_item_careful<TRANS>(st.src, st.ld, st.row0 + 32 * j, st.rows_valid, st.ones_row, k, k_end);
+        reg[j] = v;
+        p += st.jstride;
     }
 }
 
@@ -383,6 +380,7 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
 
     float4 ra[4], rb[8];
     for (int i = ANY_THREADS ? -1 : 0; i < nchunks; i++) {
+        if (!ANY_THREADS && tid != 0) break;                      // both operands by TMA: one thread drives the pipeline
         uint8_t *st = nullptr;
         if (i >= 0) {
             const int s = i % g.stages, u = i / g.stages;
@@ -435,9 +433,9 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
             }
         }
     }
-    mbar_wait(smem_u32(&bars[MAX_STAGES]), 0u, &dead, g.err);      // every MMA has written the accumulator
+    if (tid == 0) mbar_wait(smem_u32(&bars[MAX_STAGES]), 0u, &dead, g.err);   // every MMA has written the accumulator
+    __syncthreads();                                               // (the other threads sleep in the hardware barrier)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    __syncthreads();                                               // stage memory is reused below
 
     // ---- epilogue: TMEM -> registers (thread = row) -> per-warp transposition buffer -> coalesced global rows ----
     // bias / relu6 / mask are applied in the second phase (lane = column: one bias register per lane, the mask read

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
                 const int j = lane + 32 * k;
                 pv[k] = j < A ? pr[j] : 0.f;
                 const float lp = __logf(pv[k] + 1e-5f);
-                gv[k] = bm * (lp + pv[k] / (pv[k] + 1e-5f)) + (j == a ? ga : 0.f);
+                gv[k] = bm * (lp + __fdividef(pv[k], pv[k] + 1e-5f)) + (j == a ? ga : 0.f);
                 ent += pv[k] * lp;
                 dot += pv[k] * gv[k];
             }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
                 const float p = pr[j];
                 const float lp = __logf(p + 1e-5f);
                 ent += p * lp;
-                dot += p * (bm * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f));
+                dot += p * (bm * (lp + __fdividef(p, p + 1e-5f)) + (j == a ? ga : 0.f));
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
             for (int j = lane; j < A; j += 32) {
                 const float p = pr[j];
                 const float lp = __logf(p + 1e-5f);
-                dr[j] = p * ((bm * (lp + p / (p + 1e-5f)) + (j == a ? ga : 0.f)) - dot);
+                dr[j] = p * ((bm * (lp + __fdividef(p, p + 1e-5f)) + (j == a ? ga : 0.f)) - dot);
             }
         }
         if (lane == 0 && loss_row) loss_row[m] = -(__logf(pa + 1e-5f) * t - beta * ent);
@@ -404,20 +404,23 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     g.colsum = d->colsum; g.dot_w = d->dot_w; g.dot_b = d->dot_b; g.dot_out = d->dot_out;
     // N tile: as few tiles as possible, each a multiple of 16 columns, at most 256
     const int bn_max = 256;
-    const int tiles_n = (d->N + bn_max - 1) / bn_max;
+    const long long rows = d->M + (d->colsum ? 1 : 0);
+    const long long tiles_m = (rows + tc::BM - 1) / tc::BM;
+    int tiles_n = (d->N + bn_max - 1) / bn_max;
     g.tiles_n = tiles_n;
     g.BN = (((d->N + tiles_n - 1) / tiles_n) + 15) / 16 * 16;
     g.tmem_cols = 32;
     while (g.tmem_cols < g.BN) g.tmem_cols <<= 1;
     const int stage_bytes = (tc::A_TILE_BYTES + g.BN * tc::KC * 4) * (p3 ? 2 : 1);
-    const int budget = p3 ? tc::SMEM_BUDGET_3X : tc::SMEM_BUDGET_1X;
+    static int budget_kb = -1;                                               // tuning experiments only
+    if (budget_kb < 0) { const char *e = getenv("UAVNET_GEMM_BUDGET_KB"); budget_kb = e ? atoi(e) : 0; }
+    int budget = p3 ? tc::SMEM_BUDGET_3X : tc::SMEM_BUDGET_1X;
+    if (budget_kb >= 64 && budget_kb <= 220) budget = budget_kb * 1024;
     g.stages = budget / stage_bytes;
     if (g.stages > tc::MAX_STAGES) g.stages = tc::MAX_STAGES;
     if (g.stages < 2) return UAVNET_EINVAL;
     int smem = g.stages * stage_bytes;
     if (smem < tc::EPI_BYTES) smem = tc::EPI_BYTES;
-    const long long rows = d->M + (d->colsum ? 1 : 0);
-    const long long tiles_m = (rows + tc::BM - 1) / tc::BM;
     const long long chunks = (d->K + tc::KC - 1) / tc::KC;
     long long split = d->split_k;
     if (!d->accumulate) split = 1;
@@ -473,7 +476,7 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     const int which = (p3 ? 9 : 0) + am * 3 + bm;
     if (!kerns[which]) return UAVNET_EINVAL;
     if (!attr_done[which]) {
-        if (cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, budget) != cudaSuccess) {
+        if (cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return UAVNET_ECUDA;
         }
