@@ -180,14 +180,14 @@ class ACNet:
         return h2c, v
 
     def sample_head(self, h2a: torch.Tensor, seed: int, row_offset: int, counter_dev: Optional[torch.Tensor], counter_add: int,
-                    prob_out: Optional[torch.Tensor] = None):
+                    prob_out: Optional[torch.Tensor] = None, action_out: Optional[torch.Tensor] = None):
         """logits = h2a @ Wa3 + ba3, then softmax + np.random.choice(p=a_prob) in one kernel (uavnet_softmax_sample,
         Philox keyed by (seed, row_offset + row, *counter_dev + counter_add)) -> (prob [M, N_A], action int64 [M])"""
         M = h2a.shape[0]
         self._sync_transposed()
         logits = self._gemm(h2a, self.pt["Wa3"], self._buf("logits", (M, self.n_a)), b_trans=True, bias=self.p["ba3"])
         prob = prob_out if prob_out is not None else torch.empty_like(logits)
-        action = torch.empty(M, dtype=torch.int64, device=self.device)
+        action = action_out if action_out is not None else torch.empty(M, dtype=torch.int64, device=self.device)
         rc = self._lib.uavnet_softmax_sample(_ptr(logits), M, self.n_a, int(seed), int(row_offset), _ptr(counter_dev),
                                              int(counter_add), _ptr(prob), _ptr(action), self._stream())
         if rc:
@@ -360,15 +360,26 @@ class ACNet:
             p[k].copy_(torch.from_numpy(np.asarray(a[i], dtype=np.float32)))
 
 
-def n_step_targets(rewards: torch.Tensor, dones: torch.Tensor, v_boot: torch.Tensor, gamma: float = GAMMA) -> torch.Tensor:
+def n_step_targets(rewards: torch.Tensor, dones: torch.Tensor, v_boot: torch.Tensor, gamma: float = GAMMA,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Discounted n-step value targets of main.py:217-227, batched over envs: walking the buffer backwards,
     v = r + gamma * v, starting from the bootstrap value of the state after the last step -- 0 where the episode ended
-    (`if done: v_s_ = 0`), and never carried across an episode end.  rewards/dones [T, E], v_boot [E] -> [T, E]."""
-    T = rewards.shape[0]
+    (`if done: v_s_ = 0`), and never carried across an episode end.  rewards/dones [T, E], v_boot [E] -> [T, E].
+    float32 CUDA inputs run as one kernel (uavnet_nstep_targets); anything else (float64 checks, CPU) as torch ops."""
+    T, E = rewards.shape
+    if rewards.is_cuda and rewards.dtype == torch.float32 and v_boot.dtype == torch.float32 and dones.dtype in (torch.bool, torch.uint8) \
+            and rewards.is_contiguous() and dones.is_contiguous() and v_boot.is_contiguous():
+        if out is None:
+            out = torch.empty_like(rewards)
+        stream = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+        rc = N.lib().uavnet_nstep_targets(_ptr(rewards), _ptr(dones), _ptr(v_boot), T, E, float(gamma), _ptr(out), stream)
+        if rc:
+            raise RuntimeError("uavnet_nstep_targets failed (%d)" % rc)
+        return out
     out = torch.empty_like(rewards)
     v = v_boot
     for t in range(T - 1, -1, -1):
-        v = rewards[t] + gamma * torch.where(dones[t], torch.zeros_like(v), v)
+        v = rewards[t] + gamma * torch.where(dones[t].bool(), torch.zeros_like(v), v)
         out[t] = v
     return out
 
@@ -385,7 +396,10 @@ class A3CTrainer:
         self.seed = int(seed)
         self.gen = torch.Generator(device=dev).manual_seed(int(seed))
         self._draws = torch.zeros(1, dtype=torch.int32, device=dev)          # rollout steps sampled so far (Philox counter)
-        self.buf_idx = torch.empty((self.T, self.E, self.K), dtype=torch.int32, device=dev)
+        # T + 1 slots: the env writes the state after step t straight into slot t + 1 (bind_obs_idx); slot T is the
+        # bootstrap state and becomes slot 0 of the next rollout
+        self.buf_idx = torch.empty((self.T + 1, self.E, self.K), dtype=torch.int32, device=dev)
+        self.buf_vt = torch.empty((self.T, self.E), dtype=torch.float32, device=dev)
         self.buf_a = torch.empty((self.T, self.E), dtype=torch.int64, device=dev)
         self.buf_r = torch.empty((self.T, self.E), dtype=torch.float32, device=dev)
         self.buf_done = torch.empty((self.T, self.E), dtype=torch.bool, device=dev)
@@ -394,31 +408,36 @@ class A3CTrainer:
         self.buf_h2a = torch.empty((self.T, self.E, net.h), dtype=torch.float32, device=dev)
         self.buf_prob = torch.empty((self.T, self.E, net.n_a), dtype=torch.float32, device=dev)
         self.ep_return = torch.zeros(self.E, dtype=torch.float64, device=dev)
+        self.env.bind_obs_idx(self.buf_idx[0])
         self.env.reset()
         self.updates = 0
 
     def rollout(self):
         env, net = self.env, self.net
         for t in range(self.T):
-            self.buf_idx[t].copy_(env.obs_idx)
-            h1 = net.first_layer(self.buf_idx[t], self.buf_h1[t])
+            idx = self.buf_idx[t]                                            # s_t, written there by the env itself
+            h1 = net.first_layer(idx, self.buf_h1[t])
             h2a = net.actor_hidden(h1, self.buf_h2a[t])
             # softmax + np.random.choice(p=a_prob) (main.py:149,165-169,195) fused; draws keyed by the GLOBAL env id
-            _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t])
+            _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t],
+                                   action_out=self.buf_a[t])
+            env.bind_obs_idx(self.buf_idx[t + 1])
             _, r, done, _ = env.step(a)                                      # main.py:198
-            self.buf_a[t].copy_(a)
             self.buf_r[t].copy_(r)
             self.buf_done[t].copy_(done)
             self.ep_return += r
             env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)
         self._draws += self.T                                                # next rollout: fresh Philox counters
-        v_boot = net.value(env.obs_idx.clone())                              # main.py:217-220
-        return n_step_targets(self.buf_r, self.buf_done, v_boot)
+        v_boot = net.value(self.buf_idx[self.T])                             # main.py:217-220
+        vt = n_step_targets(self.buf_r, self.buf_done, v_boot, out=self.buf_vt)
+        self.buf_idx[0].copy_(self.buf_idx[self.T])                          # the next rollout starts where this one ended
+        env.bind_obs_idx(self.buf_idx[0])
+        return vt
 
     def update(self, v_target: torch.Tensor):
         net, M = self.net, self.T * self.E
         saved = {"h1": self.buf_h1.view(M, -1), "h2a": self.buf_h2a.view(M, -1), "prob": self.buf_prob.view(M, -1)}
-        a_loss, c_loss = net.accumulate_grads(self.buf_idx.view(M, self.K), self.buf_a.view(M), v_target.reshape(M), saved)
+        a_loss, c_loss = net.accumulate_grads(self.buf_idx[:self.T].view(M, self.K), self.buf_a.view(M), v_target.reshape(M), saved)
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()

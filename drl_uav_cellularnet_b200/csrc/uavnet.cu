@@ -245,6 +245,19 @@ __global__ void __launch_bounds__(NET_THREADS) softmax_sample_kernel(const float
     }
 }
 
+// n-step value targets of the worker loop (main.py:217-227), one thread per env walking its T rewards backwards
+__global__ void __launch_bounds__(NET_THREADS) nstep_targets_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done,
+                                                                    const float *__restrict__ v_boot, int T, long long E, float gamma,
+                                                                    float *__restrict__ out) {
+    const long long e = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
+    if (e >= E) return;
+    float v = v_boot[e];
+    for (int t = T - 1; t >= 0; t--) {
+        v = r[t * E + e] + gamma * (done[t * E + e] ? 0.f : v);
+        out[t * E + e] = v;
+    }
+}
+
 int grid_for(long long items) {
     long long g = (items + NET_THREADS - 1) / NET_THREADS;
     const long long cap = 148LL * 8 * 4;          // a few waves of 8 CTAs per SM; the kernels are grid-stride
@@ -350,6 +363,14 @@ int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t se
     if (!logits || M < 1 || A < 1 || (!prob && !action)) return UAVNET_EINVAL;
     softmax_sample_kernel<<<grid_for(M * 32), NET_THREADS, 0, (cudaStream_t)stream>>>(
         logits, M, A, (uint32_t)seed, (uint32_t)(seed >> 32), row_offset, counter_dev, counter_add, prob, (long long *)action);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_nstep_targets(const float *rewards, const uint8_t *dones, const float *v_boot, int32_t T, int64_t E, float gamma,
+                         float *out, void *stream) {
+    if (!rewards || !dones || !v_boot || !out || T < 1 || E < 1) return UAVNET_EINVAL;
+    nstep_targets_kernel<<<(unsigned)((E + NET_THREADS - 1) / NET_THREADS), NET_THREADS, 0, (cudaStream_t)stream>>>(
+        rewards, dones, v_boot, T, E, gamma, out);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 

@@ -116,6 +116,7 @@ class BatchedMobiEnvironment:
         self.ue_xy, self.bs_xy = z((E, nUE, 2), torch.int16), z((E, nBS, 2), torch.int16)
         self.bs_digits = z((E, nBS), torch.uint8)
         self.obs_idx = z((E, nUE + nBS), torch.int32)       # sparse form of the observation (valid after reset())
+        self._own_obs_idx = self.obs_idx
         self.sinr_all = z((E, nUE, nBS), ft) if diagnostics else None
         self.fading_used = z((E, nUE, nBS), torch.float32) if diagnostics else None
         self._out = N.Out(obs=_ptr(self.obs), reward=_ptr(self.reward), mean_sinr=_ptr(self.mean_sinr),
@@ -197,6 +198,17 @@ class BatchedMobiEnvironment:
         if rc:
             self._raise(rc, "set_trace")
         self.trace_len = tr.shape[0]
+
+    def bind_obs_idx(self, buf: Optional[torch.Tensor] = None):
+        """Redirect the sparse observation (uavenv_out.obs_idx) to a caller-owned int32 [E, nUE + nBS] buffer, e.g. the
+        next slot of a rollout storage, so that the states need no copy; None = back to the env's own buffer.  The
+        buffer is written by every later reset / step (a masked reset only touches the masked envs)."""
+        if buf is None:
+            buf = self._own_obs_idx
+        if not (buf.is_cuda and buf.dtype == torch.int32 and buf.is_contiguous() and tuple(buf.shape) == tuple(self._own_obs_idx.shape)):
+            raise ValueError("obs_idx buffer must be a contiguous int32 CUDA tensor of shape %s" % (tuple(self._own_obs_idx.shape),))
+        self.obs_idx = buf
+        self._out.obs_idx = buf.data_ptr()
 
     # -- the three passes ---------------------------------------------------------------------------------
     def ctor_pass(self, fading=None):

@@ -50,6 +50,12 @@ int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t se
 int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
                           float *dz, int64_t ldz, float *loss_row, void *stream);
 
+/* Discounted n-step value targets of the worker loop (main.py:217-227), batched over envs: walking the rollout
+ * backwards, v = r[t] + gamma * (done[t] ? 0 : v), starting from the bootstrap value v_boot of the state after the last
+ * step.  rewards float32 [T,E], dones uint8 [T,E], v_boot float32 [E], out float32 [T,E]. */
+int uavnet_nstep_targets(const float *rewards, const uint8_t *dones, const float *v_boot, int32_t T, int64_t E, float gamma,
+                         float *out, void *stream);
+
 /* TensorFlow-1 RMSPropOptimizer step (main.py:300-301; decay 0.9, momentum 0, epsilon 1e-10, slot `ms` starts at 1):
  *   g = grad * grad_scale;  ms = decay*ms + (1-decay)*g*g;  param -= lr * g / sqrt(ms + eps);  grad = 0 (if zero_grad)
  * over n float32 elements (any n; 16-byte aligned pointers). */

@@ -156,6 +156,33 @@ def test_n_step_targets_match_worker_loop(pkg):
                 tgt.reverse()
                 assert np.allclose(got[t0:t + 1, e], tgt, rtol=0, atol=1e-12), (e, t0, t)
                 t0 = t + 1
+    # the float32 kernel (uavnet_nstep_targets) against the same recursion
+    got32 = n_step_targets(torch.from_numpy(r).float().cuda(), torch.from_numpy(done).cuda(), torch.from_numpy(vb).float().cuda())
+    assert got32.dtype == torch.float32 and np.allclose(got32.cpu().numpy(), got, rtol=0, atol=1e-5)
+
+
+def test_rollout_states_are_written_in_place_by_the_env(pkg):
+    """The trainer's rollout storage: slot t holds the sparse observation the policy saw at step t (written by the env
+    itself through bind_obs_idx, masked resets included), slot T the bootstrap state = slot 0 of the next rollout."""
+    from drl_uav_cellularnet_b200.a3c import A3CTrainer, ACNet
+    E = 32
+    env = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=5, obs="none", max_step=7)
+    ref = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "group", seed=5, obs="none", max_step=7)
+    net = ACNet(env.observation_space_dim, env.action_space_dim, env.device)
+    tr = A3CTrainer(env, net, seed=3)
+    ref.reset()
+    for it in range(2):
+        first = tr.buf_idx[0].clone()
+        tr.rollout()
+        assert torch.equal(first, ref.obs_idx), "slot 0 is not the state the rollout started from"
+        for t in range(tr.T):                                      # replay the sampled actions on an independent env
+            assert torch.equal(tr.buf_idx[t] if t else first, ref.obs_idx), (it, t)
+            _, r, done, _ = ref.step(tr.buf_a[t])
+            assert torch.equal(done, tr.buf_done[t]) and torch.allclose(r.float(), tr.buf_r[t])
+            ref.reset(env_mask=ref.done_u8)
+        assert torch.equal(tr.buf_idx[tr.T], ref.obs_idx) and torch.equal(tr.buf_idx[0], ref.obs_idx)
+    assert tr.buf_done.any(), "max_step 7 < 20 steps: some episode must have ended"
+    assert env.check() == 0 and ref.check() == 0
 
 
 def test_actor_npz_round_trip(pkg, tmp_path):
@@ -187,7 +214,7 @@ def test_trainer_iterations_run_and_learn_signal(pkg):
     assert float((net.flat - p0).abs().max()) > 0 and float(net.grad.abs().max()) == 0.0
     assert int(env.step_n.max()) == 15 and saw_done                            # 40 steps, MAXSTEP 25: episodes restarted
     M = tr.T * tr.E
-    idx, a, vt = tr.buf_idx.view(M, -1), tr.buf_a.view(M), torch.zeros(M, device=env.device)
+    idx, a, vt = tr.buf_idx[:tr.T].reshape(M, -1), tr.buf_a.view(M), torch.zeros(M, device=env.device)
     first = last = None
     for it in range(60):
         _, c_loss = net.accumulate_grads(idx, a, vt)
