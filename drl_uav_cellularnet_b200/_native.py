@@ -61,7 +61,7 @@ class GemmDesc(C.Structure):
                 ("bias", C.c_void_p), ("relu6", C.c_int32),
                 ("mask_src", C.c_void_p), ("ld_mask", C.c_int64),
                 ("accumulate", C.c_int32), ("split_k", C.c_int32),
-                ("colsum", C.c_void_p),
+                ("colsum", C.c_void_p), ("out_colsum", C.c_void_p),
                 ("dot_w", C.c_void_p), ("dot_b", C.c_void_p), ("dot_out", C.c_void_p),
                 ("precision", C.c_int32)]
 
@@ -74,7 +74,7 @@ SYMBOLS = [
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
     "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
-    "uavnet_p2p_rmsprop", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets",
+    "uavnet_p2p_rmsprop", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask",
     "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
 ]
 
@@ -129,6 +129,7 @@ def lib():
     L.uavenv_diag_fill.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp]
     L.uavnet_gemm.argtypes = [P(GemmDesc), vp]
     L.uavnet_gemm_check.argtypes = []
+    L.uavnet_rank1_mask.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
     L.uavnet_nstep_targets.argtypes = [vp, vp, vp, C.c_int32, C.c_int64, C.c_float, vp, vp]
     _lib = L
     return L

@@ -228,10 +228,13 @@ class ACNet:
         c_loss = (td * td).mean()
         dv = ((-2.0 / M) * td).unsqueeze(1)                                # [M, 1]
         gemm(h2c, dv, g["Wc3"], a_trans=True, accumulate=True, colsum=g["bc3"])
-        dpre2c = gemm(dv, p["Wc3"], self._buf("dpre2c", (M, H)), b_trans=True, mask_src=h2c)
+        dpre2c = self._buf("dpre2c", (M, H))                               # (dv (x) wc3) * relu6'(h2c)
+        rc = self._lib.uavnet_rank1_mask(_ptr(dv), _ptr(p["Wc3"]), _ptr(h2c), M, H, _ptr(dpre2c), self._stream())
+        if rc:
+            raise RuntimeError("uavnet_rank1_mask failed (%d)" % rc)
         gemm(h1[:, H:], dpre2c, g["Wc2"], a_trans=True, accumulate=True, colsum=g["bc2"])
         dpre1 = self._buf("dpre1", (M, 2 * H))
-        gemm(dpre2c, p["Wc2"], dpre1[:, H:], b_trans=True, mask_src=h1[:, H:])
+        gemm(dpre2c, p["Wc2"], dpre1[:, H:], b_trans=True, mask_src=h1[:, H:], out_colsum=g["b1"][H:])
         # -- actor: d(a_loss)/d(logits) in one fused pass over the softmax output --
         dz = self._buf("dz", (M, self.ld_a))[:, :self.n_a]
         loss_row = self._buf("loss_row", (M,))
@@ -243,8 +246,7 @@ class ACNet:
         gemm(h2a, dz, g["Wa3"], a_trans=True, accumulate=True, colsum=g["ba3"])
         dpre2a = gemm(dz, p["Wa3"], self._buf("dpre2a", (M, H)), b_trans=True, mask_src=h2a)
         gemm(h1[:, :H], dpre2a, g["Wa2"], a_trans=True, accumulate=True, colsum=g["ba2"])
-        gemm(dpre2a, p["Wa2"], dpre1[:, :H], b_trans=True, mask_src=h1[:, :H])
-        gemm(None, dpre1, colsum=g["b1"], accumulate=True)                 # first-layer bias gradient
+        gemm(dpre2a, p["Wa2"], dpre1[:, :H], b_trans=True, mask_src=h1[:, :H], out_colsum=g["b1"][:H])   # + first-layer bias gradient
         rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
                                          self._stream())
         if rc:

@@ -41,6 +41,7 @@ struct GemmArgs {
     const float *mask_src; long long ld_mask;
     int accumulate;
     float *colsum;
+    float *out_colsum;                                // += column sums of the stored D (after bias / relu6 / mask)
     const float *dot_w; const float *dot_b; float *dot_out;
     int a_vec, b_vec;                                 // 16-byte loads legal for the operand
     unsigned int *err;
@@ -446,6 +447,7 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
     const float *bias = g.bias, *dot_w = g.dot_w, *mask_src = g.mask_src;
     float *D = g.D;
     const bool relu6 = g.relu6 != 0, accumulate = g.accumulate != 0;
+    float *out_colsum = g.out_colsum;
     const long long ldd = g.ldd, ld_mask = g.ld_mask;
     long long left = g.M - row_base;                              // rows of this warp that exist in D
     const int nrows = left >= 32 ? 32 : (left > 0 ? (int)left : 0);
@@ -475,6 +477,7 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
                 float *dp = D + row_base * ldd + col;
                 const float *mp = mask_src ? mask_src + row_base * ld_mask + col : nullptr;
                 const float *bp = buf + lane;
+                float csum = 0.f;
                 if (nrows == 32) {
                     for (int r8 = 0; r8 < 32; r8 += 8) {
                         float x[8], m[8];
@@ -488,6 +491,7 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
                         for (int q = 0; q < 8; q++) {
                             float y = relu6 ? fminf(fmaxf(x[q], 0.f), 6.f) : x[q];
                             y = (m[q] > 0.f && m[q] < 6.f) ? y : 0.f;
+                            csum += y;
                             if (accumulate) atomicAdd(dp, y); else *dp = y;
                             dp += ldd;
                         }
@@ -497,10 +501,12 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
                         float y = bp[rr * 33] + bcol;
                         if (relu6) y = fminf(fmaxf(y, 0.f), 6.f);
                         if (mp) { const float m = __ldg(mp); mp += ld_mask; y = (m > 0.f && m < 6.f) ? y : 0.f; }
+                        csum += y;
                         if (accumulate) atomicAdd(dp, y); else *dp = y;
                         dp += ldd;
                     }
                 }
+                if (out_colsum) atomicAdd(out_colsum + col, csum);
             }
             if (ones_here) atomicAdd(g.colsum + col, buf[(int)left * 33 + lane]);
         }

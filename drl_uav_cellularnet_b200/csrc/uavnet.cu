@@ -245,6 +245,22 @@ __global__ void __launch_bounds__(NET_THREADS) softmax_sample_kernel(const float
     }
 }
 
+// out[m, j] = dv[m] * w[j] * (0 < h[m, j] < 6): the critic's value-head data gradient through relu6 (a rank-1 product)
+__global__ void __launch_bounds__(NET_THREADS) rank1_mask_kernel(const float *__restrict__ dv, const float4 *__restrict__ w4,
+                                                                 const float4 *__restrict__ h4, long long M, int H4, float4 *__restrict__ out4) {
+    const long long total = M * H4;
+    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * NET_THREADS) {
+        const long long m = i / H4;
+        const int c = (int)(i - m * H4);
+        const float d = __ldg(dv + m);
+        const float4 w = __ldg(w4 + c), h = __ldg(h4 + i);
+        float4 o;
+        o.x = (h.x > 0.f && h.x < 6.f) ? d * w.x : 0.f; o.y = (h.y > 0.f && h.y < 6.f) ? d * w.y : 0.f;
+        o.z = (h.z > 0.f && h.z < 6.f) ? d * w.z : 0.f; o.w = (h.w > 0.f && h.w < 6.f) ? d * w.w : 0.f;
+        out4[i] = o;
+    }
+}
+
 // n-step value targets of the worker loop (main.py:217-227), one thread per env walking its T rewards backwards
 __global__ void __launch_bounds__(NET_THREADS) nstep_targets_kernel(const float *__restrict__ r, const uint8_t *__restrict__ done,
                                                                     const float *__restrict__ v_boot, int T, long long E, float gamma,
@@ -366,6 +382,13 @@ int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t se
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
+int uavnet_rank1_mask(const float *dv, const float *w, const float *h, int64_t M, int32_t H, float *out, void *stream) {
+    if (!dv || !w || !h || !out || M < 1 || H < 4 || (H & 3) || !aligned16(w) || !aligned16(h) || !aligned16(out)) return UAVNET_EINVAL;
+    rank1_mask_kernel<<<grid_for(M * (H / 4)), NET_THREADS, 0, (cudaStream_t)stream>>>(dv, (const float4 *)w, (const float4 *)h, M,
+                                                                                     H / 4, (float4 *)out);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
 int uavnet_nstep_targets(const float *rewards, const uint8_t *dones, const float *v_boot, int32_t T, int64_t E, float gamma,
                          float *out, void *stream) {
     if (!rewards || !dones || !v_boot || !out || T < 1 || E < 1) return UAVNET_EINVAL;
@@ -414,6 +437,7 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     if (d->colsum && !d->accumulate) return UAVNET_EINVAL;                  // the ones row accumulates like the rest
     if (d->accumulate && (d->bias || d->relu6 || d->dot_out)) return UAVNET_EINVAL;
     if (d->dot_out && (!d->dot_w || d->N > 256)) return UAVNET_EINVAL;
+    if (d->out_colsum && (d->accumulate || !d->D)) return UAVNET_EINVAL;
     if (d->precision != UAVNET_GEMM_TF32 && d->precision != UAVNET_GEMM_3XTF32) return UAVNET_EINVAL;
     const bool p3 = d->precision == UAVNET_GEMM_3XTF32;
     tc::GemmArgs g;
@@ -422,7 +446,7 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     g.B = d->B; g.ldb = d->ldb; g.b_trans = d->b_trans ? 1 : 0;
     g.D = d->D; g.ldd = d->ldd; g.M = d->M; g.N = d->N; g.K = d->K;
     g.bias = d->bias; g.relu6 = d->relu6; g.mask_src = d->mask_src; g.ld_mask = d->ld_mask; g.accumulate = d->accumulate;
-    g.colsum = d->colsum; g.dot_w = d->dot_w; g.dot_b = d->dot_b; g.dot_out = d->dot_out;
+    g.colsum = d->colsum; g.out_colsum = d->out_colsum; g.dot_w = d->dot_w; g.dot_b = d->dot_b; g.dot_out = d->dot_out;
     // N tile: as few tiles as possible, each a multiple of 16 columns, at most 256
     const int bn_max = 256;
     const long long rows = d->M + (d->colsum ? 1 : 0);

@@ -26,7 +26,7 @@ def _p(t: Optional[torch.Tensor]):
 def gemm(A: Optional[torch.Tensor], B: torch.Tensor, out: Optional[torch.Tensor] = None, *, a_trans: bool = False,
          b_trans: bool = False, bias: Optional[torch.Tensor] = None, relu6: bool = False,
          mask_src: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 0,
-         colsum: Optional[torch.Tensor] = None, dot_w: Optional[torch.Tensor] = None,
+         colsum: Optional[torch.Tensor] = None, out_colsum: Optional[torch.Tensor] = None, dot_w: Optional[torch.Tensor] = None,
          dot_b: Optional[torch.Tensor] = None, dot_out: Optional[torch.Tensor] = None, precision: str = "fp32",
          want_out: bool = True) -> Optional[torch.Tensor]:
     """out[M,N] (+)= op(A) . op(B) with the fused epilogue of uavnet_gemm.
@@ -64,7 +64,7 @@ def gemm(A: Optional[torch.Tensor], B: torch.Tensor, out: Optional[torch.Tensor]
         _chk(mask_src, "mask_src")
         d.mask_src, d.ld_mask = _p(mask_src), mask_src.stride(0)
     d.accumulate, d.split_k = int(accumulate), int(split_k)
-    d.colsum, d.dot_w, d.dot_b, d.dot_out = _p(colsum), _p(dot_w), _p(dot_b), _p(dot_out)
+    d.colsum, d.out_colsum, d.dot_w, d.dot_b, d.dot_out = _p(colsum), _p(out_colsum), _p(dot_w), _p(dot_b), _p(dot_out)
     d.precision = PRECISIONS[precision]
     stream = C.c_void_p(torch.cuda.current_stream(B.device).cuda_stream)
     rc = N.lib().uavnet_gemm(C.byref(d), stream)

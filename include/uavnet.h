@@ -50,6 +50,11 @@ int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t se
 int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
                           float *dz, int64_t ldz, float *loss_row, void *stream);
 
+/* out[m,j] = dv[m] * w[j] * (0 < h[m,j] < 6): the data gradient of the critic's value head (main.py:153, 200 -> 1)
+ * through the relu6 of its second layer -- a rank-1 product, memory-bound.  dv float32 [M], w float32 [H], h and out
+ * float32 [M,H] contiguous, H a multiple of 4. */
+int uavnet_rank1_mask(const float *dv, const float *w, const float *h, int64_t M, int32_t H, float *out, void *stream);
+
 /* Discounted n-step value targets of the worker loop (main.py:217-227), batched over envs: walking the rollout
  * backwards, v = r[t] + gamma * (done[t] ? 0 : v), starting from the bootstrap value v_boot of the state after the last
  * step.  rewards float32 [T,E], dones uint8 [T,E], v_boot float32 [E], out float32 [T,E]. */
@@ -93,6 +98,8 @@ int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_loca
  * a plain store or, with accumulate != 0, float REDs (D += ...) from split_k slices of K (0 = chosen to fill the GPU).
  * colsum (accumulate only): colsum[n] += sum_k op(B)[k,n] -- a row of ones appended to op(A), i.e. the bias gradient of
  * the layer comes out of the same pass; M may be 0 (column sums only).  D may be NULL when only dot_out / colsum is wanted.
+ * out_colsum (plain stores only): out_colsum[n] += sum_m D[m,n] of the values stored -- the bias gradient of the layer
+ * BELOW a data-gradient product comes out of its epilogue.
  * precision: UAVNET_GEMM_TF32 (operands rounded to 10 mantissa bits) or UAVNET_GEMM_3XTF32 (hi/lo split, three MMAs per
  * k-step: fp32-class accuracy).  Any M, N <= 65536, K, leading dimensions and alignments (16-byte aligned operands with
  * leading dimensions that are multiples of 4 take vector loads).  Only enqueues work; uavnet_gemm_check() synchronises
@@ -107,6 +114,7 @@ typedef struct uavnet_gemm_desc {
     const float *mask_src; int64_t ld_mask;
     int32_t accumulate; int32_t split_k;
     float *colsum;
+    float *out_colsum;
     const float *dot_w; const float *dot_b; float *dot_out;
     int32_t precision;
 } uavnet_gemm_desc;

@@ -72,6 +72,8 @@ def test_entry_points_reject_bad_arguments_without_a_gpu(native):
     assert L.uavnet_rmsprop(None, None, None, 4, 1e-4, 0.9, 1e-10, 1.0, 1, None) == -1
     assert L.uavnet_actor_head_bwd(None, None, None, 1, 625, 0.001, None, 625, None, None) == -1
     assert L.uavnet_gemm(None, None) == -1
+    assert L.uavnet_rank1_mask(None, None, None, 1, 4, None, None) == -1
+    assert L.uavnet_nstep_targets(None, None, None, 1, 1, 0.9, None, None) == -1
     d = native.GemmDesc()
     assert L.uavnet_gemm(C.byref(d), None) == -1                 # no operands
     assert L.uavnet_gemm_check() == 0                            # nothing launched: no device access
@@ -126,3 +128,28 @@ def test_n_step_targets_and_net_layout_on_cpu():
         v_s_ = rr + GAMMA * v_s_
         want.append(v_s_)
     assert np.allclose(v[:, 0].numpy(), want[::-1])
+
+
+def test_dense_wrapper_rejects_what_the_kernel_cannot_take():
+    """dense.gemm validates on the host before any device work (CPU tensors, wrong dtypes, non-contiguous rows)."""
+    import pytest
+    import torch
+    from drl_uav_cellularnet_b200 import dense
+    a = torch.zeros((4, 4))
+    with pytest.raises(ValueError):
+        dense.gemm(a, a)                                            # not on a CUDA device: there is no CPU path
+    assert set(dense.PRECISIONS) == {"tf32", "fp32", "3xtf32"}
+
+
+def test_n_step_targets_host_path_matches_the_worker_loop():
+    """n_step_targets on CPU float64 (the torch path): v = r + gamma v, cut at episode ends (main.py:217-227)"""
+    import numpy as np
+    import torch
+    from drl_uav_cellularnet_b200.a3c import GAMMA, n_step_targets
+    r = torch.tensor([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]], dtype=torch.float64)
+    done = torch.tensor([[False, False], [True, False], [False, False]])
+    vb = torch.tensor([10.0, 20.0], dtype=torch.float64)
+    got = n_step_targets(r, done, vb).numpy()
+    e0 = [1 + GAMMA * 3.0, 3.0, 5 + GAMMA * 10.0]
+    e1 = [2 + GAMMA * (4 + GAMMA * (6 + GAMMA * 20.0)), 4 + GAMMA * (6 + GAMMA * 20.0), 6 + GAMMA * 20.0]
+    assert np.allclose(got[:, 0], e0) and np.allclose(got[:, 1], e1)

@@ -110,6 +110,29 @@ def test_data_gradient_with_relu6_mask(dense):
     assert rel_err(out[:, :H], ref) < TOL["fp32"]
     assert float(out[5, 3]) == 0.0 and float(out[6, 4]) == 0.0
     assert (out[:, H:] == 7.0).all(), "columns outside the output slice were touched"
+    # the bias gradient of the layer below = column sums of what was stored, from the same epilogue
+    gb = torch.ones(H, device="cuda")
+    out2 = torch.empty((M, H), device="cuda")
+    dense.gemm(dy, W, out2, b_trans=True, mask_src=h[:, :H], out_colsum=gb)
+    assert torch.equal(out2, out[:, :H])
+    assert rel_err(gb, 1.0 + ref.sum(0)) < TOL["fp32"]
+
+
+def test_rank1_masked_product(dense):
+    """uavnet_rank1_mask: (dv (x) wc3) * relu6'(h2c), the value head's data gradient (main.py:153)"""
+    import ctypes as C
+    from drl_uav_cellularnet_b200 import _native as N
+    g = torch.Generator(device="cuda").manual_seed(8)
+    M, H = 5000, 200
+    dv = torch.randn(M, device="cuda", generator=g)
+    w = torch.randn(H, device="cuda", generator=g)
+    h = torch.rand((M, H), device="cuda", generator=g) * 8 - 1
+    out = torch.empty((M, H), device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    assert N.lib().uavnet_rank1_mask(vp(dv), vp(w), vp(h), M, H, vp(out), None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, (dv[:, None] * w[None, :]) * ((h > 0) & (h < 6)))
+    assert N.lib().uavnet_rank1_mask(vp(dv), vp(w), vp(h), M, 201, vp(out), None) == -1
 
 
 @pytest.mark.parametrize("split_k", [0, 1, 7])
