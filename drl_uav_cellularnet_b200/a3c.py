@@ -180,12 +180,14 @@ class ACNet:
         return h2c, v
 
     def sample_head(self, h2a: torch.Tensor, seed: int, row_offset: int, counter_dev: Optional[torch.Tensor], counter_add: int,
-                    prob_out: Optional[torch.Tensor] = None, action_out: Optional[torch.Tensor] = None):
+                    prob_out: Optional[torch.Tensor] = None, action_out: Optional[torch.Tensor] = None,
+                    logits_out: Optional[torch.Tensor] = None):
         """logits = h2a @ Wa3 + ba3, then softmax + np.random.choice(p=a_prob) in one kernel (uavnet_softmax_sample,
         Philox keyed by (seed, row_offset + row, *counter_dev + counter_add)) -> (prob [M, N_A], action int64 [M])"""
         M = h2a.shape[0]
         self._sync_transposed()
-        logits = self._gemm(h2a, self.pt["Wa3"], self._buf("logits", (M, self.n_a)), b_trans=True, bias=self.p["ba3"])
+        logits = self._gemm(h2a, self.pt["Wa3"], logits_out if logits_out is not None else self._buf("logits", (M, self.n_a)),
+                            b_trans=True, bias=self.p["ba3"])
         prob = prob_out if prob_out is not None else torch.empty_like(logits)
         action = action_out if action_out is not None else torch.empty(M, dtype=torch.int64, device=self.device)
         rc = self._lib.uavnet_softmax_sample(_ptr(logits), M, self.n_a, int(seed), int(row_offset), _ptr(counter_dev),
@@ -389,12 +391,29 @@ def n_step_targets(rewards: torch.Tensor, dones: torch.Tensor, v_boot: torch.Ten
 class A3CTrainer:
     """Synchronous batched restatement of Worker.work (main.py:182-271) for one rank: E envs, rollouts of
     UPDATE_GLOBAL_ITER steps, one update per rollout.  With torch.distributed initialised the gradient buffer is
-    all-reduced (NCCL over NVLink) before the optimiser pass -- the reference's push/pull (main.py:159-163)."""
+    all-reduced (NCCL over NVLink) before the optimiser pass -- the reference's push/pull (main.py:159-163).
+
+    ``env`` may be a list of BatchedMobiEnvironment handles with consecutive ``env_offset`` ranges (the reference's
+    independent workers, main.py:173): every handle rolls out on its own CUDA stream, so the short kernels of one
+    group's step (policy forward of 64 CTAs, the latency-bound env step) overlap the other groups'.  All draws are keyed
+    by the global env id, so the rollout is the same for any grouping."""
 
     def __init__(self, env, net: ACNet, rollout: int = UPDATE_GLOBAL_ITER, seed: int = 0):
-        self.env, self.net, self.T = env, net, int(rollout)
-        self.E, self.K = env.n_envs, env.nUE + env.nBS
-        dev = env.device
+        self.envs = list(env) if isinstance(env, (list, tuple)) else [env]
+        self.env = self.envs[0]
+        self.net, self.T = net, int(rollout)
+        self.K = self.env.nUE + self.env.nBS
+        dev = self.env.device
+        self.slices, lo = [], 0
+        for i, e in enumerate(self.envs):
+            if e.device != dev or e.nUE + e.nBS != self.K:
+                raise ValueError("all env handles must live on one device and have the same shape")
+            if i and e.env_offset != self.envs[i - 1].env_offset + self.envs[i - 1].n_envs:
+                raise ValueError("env handles must cover consecutive global env ranges (env_offset)")
+            self.slices.append(slice(lo, lo + e.n_envs))
+            lo += e.n_envs
+        self.E = lo
+        self.streams = [torch.cuda.Stream(device=dev) for _ in self.envs] if len(self.envs) > 1 else [None]
         self.seed = int(seed)
         self.gen = torch.Generator(device=dev).manual_seed(int(seed))
         self._draws = torch.zeros(1, dtype=torch.int32, device=dev)          # rollout steps sampled so far (Philox counter)
@@ -409,31 +428,49 @@ class A3CTrainer:
         self.buf_h1 = torch.empty((self.T, self.E, 2 * net.h), dtype=torch.float32, device=dev)
         self.buf_h2a = torch.empty((self.T, self.E, net.h), dtype=torch.float32, device=dev)
         self.buf_prob = torch.empty((self.T, self.E, net.n_a), dtype=torch.float32, device=dev)
+        self.buf_logits = torch.empty((self.E, net.n_a), dtype=torch.float32, device=dev)
         self.ep_return = torch.zeros(self.E, dtype=torch.float64, device=dev)
-        self.env.bind_obs_idx(self.buf_idx[0])
-        self.env.reset()
+        for e, sl in zip(self.envs, self.slices):
+            e.bind_obs_idx(self.buf_idx[0][sl])
+            e.reset()
         self.updates = 0
 
+    def _rollout_step(self, g: int, t: int):
+        env, net, sl = self.envs[g], self.net, self.slices[g]
+        h1 = net.first_layer(self.buf_idx[t][sl], self.buf_h1[t][sl])    # s_t, written there by the env itself
+        h2a = net.actor_hidden(h1, self.buf_h2a[t][sl])
+        # softmax + np.random.choice(p=a_prob) (main.py:149,165-169,195) fused; draws keyed by the GLOBAL env id
+        _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t][sl],
+                               action_out=self.buf_a[t][sl], logits_out=self.buf_logits[sl])
+        env.bind_obs_idx(self.buf_idx[t + 1][sl])
+        _, r, done, _ = env.step(a)                                      # main.py:198
+        self.buf_r[t][sl].copy_(r)
+        self.buf_done[t][sl].copy_(done)
+        self.ep_return[sl] += r
+        env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)
+
     def rollout(self):
-        env, net = self.env, self.net
-        for t in range(self.T):
-            idx = self.buf_idx[t]                                            # s_t, written there by the env itself
-            h1 = net.first_layer(idx, self.buf_h1[t])
-            h2a = net.actor_hidden(h1, self.buf_h2a[t])
-            # softmax + np.random.choice(p=a_prob) (main.py:149,165-169,195) fused; draws keyed by the GLOBAL env id
-            _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t],
-                                   action_out=self.buf_a[t])
-            env.bind_obs_idx(self.buf_idx[t + 1])
-            _, r, done, _ = env.step(a)                                      # main.py:198
-            self.buf_r[t].copy_(r)
-            self.buf_done[t].copy_(done)
-            self.ep_return += r
-            env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)
+        net = self.net
+        net._sync_transposed()                                               # before the streams fork
+        if len(self.envs) == 1:
+            for t in range(self.T):
+                self._rollout_step(0, t)
+        else:
+            cur = torch.cuda.current_stream(self.env.device)
+            for st in self.streams:
+                st.wait_stream(cur)
+            for t in range(self.T):                                          # issue order interleaves the groups
+                for g, st in enumerate(self.streams):
+                    with torch.cuda.stream(st):
+                        self._rollout_step(g, t)
+            for st in self.streams:
+                cur.wait_stream(st)
         self._draws += self.T                                                # next rollout: fresh Philox counters
         v_boot = net.value(self.buf_idx[self.T])                             # main.py:217-220
         vt = n_step_targets(self.buf_r, self.buf_done, v_boot, out=self.buf_vt)
         self.buf_idx[0].copy_(self.buf_idx[self.T])                          # the next rollout starts where this one ended
-        env.bind_obs_idx(self.buf_idx[0])
+        for e, sl in zip(self.envs, self.slices):
+            e.bind_obs_idx(self.buf_idx[0][sl])
         return vt
 
     def update(self, v_target: torch.Tensor):

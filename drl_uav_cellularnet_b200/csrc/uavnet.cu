@@ -112,16 +112,24 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
         const float *pr = prob + m * A;
         const int a = (int)a_his[m];
         const float t = td[m];
-        const float pa = pr[a];
-        const float ga = -t * inv_m / (pa + 1e-5f);
+        float pa, ga;
         float ent = 0.f, dot = 0.f;                       // sum p*lp (= -H), sum p*g
         float *dr = dz + m * ldz;
         if constexpr (PL > 0) {
             float pv[PL], gv[PL];                         // the row lives in registers between the two passes
 #pragma unroll
+            for (int k = 0; k < PL; k++) {                // all loads of the row in flight before anything is used
+                const int j = lane + 32 * k;
+                pv[k] = j < A ? __ldg(pr + j) : 0.f;
+            }
+            float cand = 0.f;                             // p[a] out of the registers: no second dependent load
+#pragma unroll
+            for (int k = 0; k < PL; k++) cand = (k == (a >> 5)) ? pv[k] : cand;
+            pa = __shfl_sync(0xffffffffu, cand, a & 31);
+            ga = -t * inv_m / (pa + 1e-5f);
+#pragma unroll
             for (int k = 0; k < PL; k++) {
                 const int j = lane + 32 * k;
-                pv[k] = j < A ? pr[j] : 0.f;
                 const float lp = __logf(pv[k] + 1e-5f);
                 gv[k] = bm * (lp + __fdividef(pv[k], pv[k] + 1e-5f)) + (j == a ? ga : 0.f);
                 ent += pv[k] * lp;
@@ -138,6 +146,8 @@ __global__ void __launch_bounds__(NET_THREADS) actor_head_bwd_kernel(const float
                 if (j < A) dr[j] = pv[k] * (gv[k] - dot);
             }
         } else {
+            pa = pr[a];
+            ga = -t * inv_m / (pa + 1e-5f);
             for (int j = lane; j < A; j += 32) {
                 const float p = pr[j];
                 const float lp = __logf(p + 1e-5f);

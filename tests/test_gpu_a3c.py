@@ -197,6 +197,35 @@ def test_actor_npz_round_trip(pkg, tmp_path):
     assert torch.equal(a.forward(idx, "actor")[0], b.forward(idx, "actor")[0])
 
 
+def test_grouped_rollout_on_streams_equals_the_single_handle_rollout(pkg):
+    """Env handles with consecutive global ranges, each on its own stream: same rollout, same update as one handle
+    (all draws are keyed by the global env id) -- eager and replayed as one CUDA graph."""
+    from drl_uav_cellularnet_b200.a3c import A3CTrainer, ACNet
+    E, G = 48, 3
+    mk = lambda n, off: pkg.BatchedMobiEnvironment(n, 4, 40, 100, "group", seed=9, obs="none", env_offset=off, max_step=13)  # noqa: E731
+    one = A3CTrainer(mk(E, 0), ACNet(50000, 625, "cuda:0"), seed=4)
+    grp = A3CTrainer([mk(E // G, g * (E // G)) for g in range(G)], ACNet(50000, 625, "cuda:0"), seed=4)
+    assert torch.equal(one.net.flat, grp.net.flat)
+    for it in range(3):
+        grp.net.flat.copy_(one.net.flat)          # gradient REDs arrive in any order: re-align the last bits
+        grp.net.ms.copy_(one.net.ms)
+        la, lc = one.train_iteration()
+        ga, gc = grp.train_iteration()
+        torch.cuda.synchronize()
+        for name in ("buf_idx", "buf_a", "buf_r", "buf_done", "buf_h1", "buf_h2a", "buf_prob", "buf_vt"):
+            assert torch.equal(getattr(one, name), getattr(grp, name)), (it, name)
+        assert abs(float(la) - float(ga)) < 1e-6 and abs(float(lc) - float(gc)) < 1e-6
+    assert torch.allclose(one.net.flat, grp.net.flat, rtol=0, atol=1e-6)      # gradient REDs arrive in any order
+    with pytest.raises(ValueError):
+        A3CTrainer([mk(8, 0), mk(8, 9)], grp.net)                             # ranges must be consecutive
+    grp.capture(warmup=1)
+    a, c = grp.train_iteration_graph()
+    torch.cuda.synchronize()
+    assert torch.isfinite(a) and torch.isfinite(c)
+    for e in grp.envs:
+        assert e.check() == 0
+
+
 def test_trainer_iterations_run_and_learn_signal(pkg):
     """A few synchronous A3C iterations on 64 envs: finite losses, parameters move, gradients are consumed, episodes
     restart at MAXSTEP, and the critic loss on a fixed batch drops when the same batch is replayed (sanity of the
