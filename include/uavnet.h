@@ -8,7 +8,9 @@
  * (200x200, 200x625, 200x1) and their gradients run on the tcgen05 tensor cores through uavnet_gemm.
  *
  * Plain C types, raw device pointers, the stream is a cudaStream_t passed as void*.  Every entry point returns 0 or a
- * negative UAVNET_E* code and only enqueues work on the stream.
+ * negative UAVNET_E* code and only enqueues work on the stream.  One process per GPU (the launch model of this
+ * library): the entry points keep per-process state for the current device (function attributes, the gemm error word)
+ * and are not thread-safe.
  */
 #ifndef UAVNET_H
 #define UAVNET_H
