@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
         if (AM == OP_TMA) tma_load_2d(dst, &g.tmap_a, kc, (int)m0, fb);
         if (BM_ == OP_TMA) tma_load_2d(dst + A_TILE_BYTES, &g.tmap_b, kc, n0, fb);
     };
-    if (ANY_TMA && tid == 0) {
+    const bool probe_mma = ANY_TMA && (g.dbg & 2);            // tuning probe: MMAs on whatever is in shared memory, no loads
+    if (ANY_TMA && tid == 0 && !probe_mma) {
         for (int c = 0; c < g.stages - 1 && c < nchunks; c++) tma_issue(c);
     }
 
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
                 __syncthreads();
             }
             if (tid == 0) {
-                if (ANY_TMA) mbar_wait(smem_u32(&full[i % g.stages]), (uint32_t)((i / g.stages) & 1), &dead, g.err);
+                if (ANY_TMA && !probe_mma) mbar_wait(smem_u32(&full[i % g.stages]), (uint32_t)((i / g.stages) & 1), &dead, g.err);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // thread-staged tiles are K-major without swizzle: 256 bytes per k-step of 8, LBO 128, SBO 1024;
                 // TMA tiles carry the 128-byte swizzle: 32 bytes per k-step inside the row
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
                 }
                 mma_commit(smem_u32(&bars[i % g.stages]));       // the stage is free once these MMAs have read it
                 if (i == nchunks - 1) mma_commit(smem_u32(&bars[MAX_STAGES]));
-                if (ANY_TMA) {
+                if (ANY_TMA && !probe_mma) {
                     const int c = i + g.stages - 1;              // refill the stage chunk i - 1 used
                     if (c < nchunks) {
                         if (c >= g.stages) mbar_wait(smem_u32(&bars[c % g.stages]), (uint32_t)(((c / g.stages) - 1) & 1), &dead, g.err);
@@ -454,53 +455,55 @@ __global__ void __launch_bounds__(NTHR, PREC3X ? 1 : 2) gemm_kernel(const __grid
     const bool ones_here = g.colsum && left >= 0 && left < 32;    // the appended row of ones lands in this warp's rows
     float dot = 0.f;
     for (int c0 = half * 32; c0 < bn_eff; c0 += 64) {
+        const int col = n0 + c0 + lane;
+        const bool col_ok = col < g.N && c0 + lane < bn_eff;
+        // the relu6' mask of the chunk's 32 rows is requested before the accumulators are touched: 32 loads in flight per
+        // lane while tensor memory is read and transposed (8 in flight made the epilogue a latency chain)
+        float m[32];
+        const bool mask_all = mask_src && col_ok && nrows == 32;
+        if (mask_all) {
+            const float *mp = mask_src + row_base * ld_mask + col;
+#pragma unroll
+            for (int q = 0; q < 32; q++) m[q] = __ldg(mp + (long long)q * ld_mask);
+        }
         float v[32];
         tmem_ld32(tmem + ((uint32_t)lane_base << 16) + (uint32_t)c0, v);
         if (dot_w) {                                               // critic: relu6(. + bias) . w3 per row
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-                const int col = n0 + c0 + j;
-                if (col < g.N) {
-                    float x = v[j] + (bias ? __ldg(bias + col) : 0.f);
+                const int cj = n0 + c0 + j;
+                if (cj < g.N) {
+                    float x = v[j] + (bias ? __ldg(bias + cj) : 0.f);
                     if (relu6) x = fminf(fmaxf(x, 0.f), 6.f);
-                    dot += x * __ldg(dot_w + col);
+                    dot += x * __ldg(dot_w + cj);
                 }
             }
         }
 #pragma unroll
         for (int j = 0; j < 32; j++) buf[lane * 33 + j] = v[j];
         __syncwarp();
-        const int col = n0 + c0 + lane;
-        if (col < g.N && c0 + lane < bn_eff) {
+        if (col_ok) {
             if (D && nrows > 0) {
                 const float bcol = bias ? __ldg(bias + col) : 0.f;
                 float *dp = D + row_base * ldd + col;
-                const float *mp = mask_src ? mask_src + row_base * ld_mask + col : nullptr;
                 const float *bp = buf + lane;
                 float csum = 0.f;
                 if (nrows == 32) {
-                    for (int r8 = 0; r8 < 32; r8 += 8) {
-                        float x[8], m[8];
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {              // 8 rows in flight: mask loads, then stores
-                            x[q] = bp[(r8 + q) * 33] + bcol;
-                            m[q] = 1.f;
-                            if (mp) { m[q] = __ldg(mp); mp += ld_mask; }
-                        }
-#pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            float y = relu6 ? fminf(fmaxf(x[q], 0.f), 6.f) : x[q];
-                            y = (m[q] > 0.f && m[q] < 6.f) ? y : 0.f;
-                            csum += y;
-                            if (accumulate) atomicAdd(dp, y); else *dp = y;
-                            dp += ldd;
-                        }
+                    for (int q = 0; q < 32; q++) {
+                        float y = bp[q * 33] + bcol;
+                        if (relu6) y = fminf(fmaxf(y, 0.f), 6.f);
+                        if (mask_all) y = (m[q] > 0.f && m[q] < 6.f) ? y : 0.f;
+                        csum += y;
+                        if (accumulate) atomicAdd(dp, y); else *dp = y;
+                        dp += ldd;
                     }
                 } else {
+                    const float *mp = mask_src ? mask_src + row_base * ld_mask + col : nullptr;
                     for (int rr = 0; rr < nrows; rr++) {
                         float y = bp[rr * 33] + bcol;
                         if (relu6) y = fminf(fmaxf(y, 0.f), 6.f);
-                        if (mp) { const float m = __ldg(mp); mp += ld_mask; y = (m > 0.f && m < 6.f) ? y : 0.f; }
+                        if (mp) { const float mm = __ldg(mp); mp += ld_mask; y = (mm > 0.f && mm < 6.f) ? y : 0.f; }
                         csum += y;
                         if (accumulate) atomicAdd(dp, y); else *dp = y;
                         dp += ldd;
