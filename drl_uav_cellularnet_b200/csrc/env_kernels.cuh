@@ -728,11 +728,21 @@ __device__ __forceinline__ void issue_zero_stream(float *obs_env, const float *z
 #ifndef UAVENV_MINB
 #define UAVENV_MINB 3
 #endif
-constexpr int NT_SMALL = 128;   // CTA size for handles without a dense observation stream and <= 64 UEs per env
+#ifndef UAVENV_NT_SMALL
+#define UAVENV_NT_SMALL 64
+#endif
+// CTA size for handles without a dense observation stream and <= 64 UEs per env.  That step is a latency chain per UE
+// (Philox -> Box-Muller -> lg2/ex2 -> SINR -> handover), so it wants resident warps, not registers: measured on B200 for
+// 8192 envs (bench.py --obs none): 128 threads x 6 CTAs/SM 72.9 us, x 8 59.4, x 10 55.4, x 16 49.0; 64 threads x 16
+// CTAs/SM (64 registers, no spills) 45.8 us, x 24 45.8, x 32 46.5.
+constexpr int NT_SMALL = UAVENV_NT_SMALL;
 #ifndef UAVENV_MINB_WIDE
 #define UAVENV_MINB_WIDE 3
 #endif
-constexpr int min_blocks(int nb, bool f64, int nt) { return f64 ? 1 : (nb > 8 ? UAVENV_MINB_WIDE : (nt == NT_SMALL ? 6 : UAVENV_MINB)); }
+#ifndef UAVENV_MINB_SMALL
+#define UAVENV_MINB_SMALL 16
+#endif
+constexpr int min_blocks(int nb, bool f64, int nt) { return f64 ? 1 : (nb > 8 ? UAVENV_MINB_WIDE : (nt == NT_SMALL ? UAVENV_MINB_SMALL : UAVENV_MINB)); }
 
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
 //   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move

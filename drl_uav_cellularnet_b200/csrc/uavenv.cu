@@ -85,7 +85,7 @@ env_kernel_fn pick_nb(int nBS) {
 int plan_kernel(uavenv_t *h) {
     const bool f64 = h->cfg.precision == UAVENV_PREC_FP64_PARITY;
     /* Without a dense observation to stream (obs NONE / INCREMENTAL: the policy reads obs_idx) the step is pure
-     * latency-bound arithmetic: small envs then run in 128-thread CTAs, twice as many resident per SM. */
+     * latency-bound arithmetic: small envs then run in NT_SMALL-thread CTAs, many more resident per SM. */
     const bool small = !f64 && h->cfg.obs_mode != UAVENV_OBS_F32 && h->d.nUE <= 64;
     h->threads = small ? NT_SMALL : CTA_THREADS;
     /* two builds of every kernel: the lean one, and one that can also write the full SINR matrix / the applied fading
