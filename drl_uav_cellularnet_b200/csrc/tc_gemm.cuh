@@ -45,7 +45,7 @@ struct GemmArgs {
     const float *dot_w; const float *dot_b; float *dot_out;
     int a_vec, b_vec;                                 // 16-byte loads legal for the operand
     unsigned int *err;
-    int dbg;                                          // descriptor experiments (UAVNET_GEMM_DBG), 0 in production
+    int dbg;                                          // UAVNET_GEMM_DBG, 0 in production; bit 1: MMA-rate probe (no operand loads)
     alignas(64) CUtensorMap tmap_a;                   // operand mode TMA: [rows, K] float32, box 32 x 128 (A) / 32 x BN (B),
     alignas(64) CUtensorMap tmap_b;                   // 128-byte swizzle
 };

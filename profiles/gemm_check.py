@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """uavnet_gemm against a float64 product of the same operands, case by case (prints, does not assert):
-    python profiles/gemm_check.py [--dbg-sweep]"""
+    python profiles/gemm_check.py
+(Round 1 used this with UAVNET_GEMM_DBG = 0..15 to swap the LBO / SBO fields of the MN-major descriptors: every variant
+returned zeros, see profiles/r1/NOTES.md section 8; the knob no longer exists.)"""
 import json
 import os
 import subprocess
@@ -55,7 +57,7 @@ if __name__ == "__main__":
     if "--child" in sys.argv:
         print(json.dumps(run_cases()))
     else:
-        sweep = [0] + list(range(1, 16))
+        sweep = [0]
         for dbg in sweep:
             env = dict(os.environ, UAVNET_GEMM_DBG=str(dbg))
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True, text=True, timeout=600)
