@@ -443,10 +443,11 @@ class A3CTrainer:
         _, a = net.sample_head(h2a, self.seed, env.env_offset, self._draws, t, prob_out=self.buf_prob[t][sl],
                                action_out=self.buf_a[t][sl], logits_out=self.buf_logits[sl])
         env.bind_obs_idx(self.buf_idx[t + 1][sl])
-        _, r, done, _ = env.step(a)                                      # main.py:198
-        self.buf_r[t][sl].copy_(r)
-        self.buf_done[t][sl].copy_(done)
-        self.ep_return[sl] += r
+        _, r, _, _ = env.step(a)                                         # main.py:198
+        rc = net._lib.uavnet_rollout_record(_ptr(r), _ptr(env.done_u8), env.n_envs, _ptr(self.buf_r[t][sl]),
+                                            _ptr(self.buf_done[t][sl]), _ptr(self.ep_return[sl]), net._stream())
+        if rc:
+            raise RuntimeError("uavnet_rollout_record failed (%d)" % rc)
         env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)
 
     def rollout(self):

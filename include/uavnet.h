@@ -57,6 +57,12 @@ int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *
  * float32 [M,H] contiguous, H a multiple of 4. */
 int uavnet_rank1_mask(const float *dv, const float *w, const float *h, int64_t M, int32_t H, float *out, void *stream);
 
+/* Bookkeeping of one rollout step (main.py:199-211: ep_r += r, buffer_r.append(r)) for E envs in one launch:
+ * reward_out[e] = (float) reward[e] (the env kernel's float64 reward), done_out[e] = done[e], ep_return[e] += reward[e]
+ * (ep_return may be NULL). */
+int uavnet_rollout_record(const double *reward, const uint8_t *done, int64_t E, float *reward_out, uint8_t *done_out,
+                          double *ep_return, void *stream);
+
 /* Discounted n-step value targets of the worker loop (main.py:217-227), batched over envs: walking the rollout
  * backwards, v = r[t] + gamma * (done[t] ? 0 : v), starting from the bootstrap value v_boot of the state after the last
  * step.  rewards float32 [T,E], dones uint8 [T,E], v_boot float32 [E], out float32 [T,E]. */
