@@ -38,6 +38,7 @@ cases = [
     ("wgrad 200x625x81920 +colsum", lambda: dense.gemm(h2, dz, gW3, a_trans=True, accumulate=True, colsum=gb3, precision=args.prec), 2.0 * M * A * H),
     ("wgrad 200x200x81920 +colsum", lambda: dense.gemm(h1[:, :H], h2, gW2, a_trans=True, accumulate=True, colsum=gb2, precision=args.prec), 2.0 * M * H * H),
     ("fwd 8192x200x200 W^T bias relu6 (all TMA)", lambda: dense.gemm(h1s[:, :H], W2, o200s, b_trans=True, bias=b2, relu6=True, precision=args.prec), 2.0 * E * H * H),
+    ("dgrad 81920x200x200 mask + out_colsum", lambda: dense.gemm(h2, W2, o400[:, :H], b_trans=True, mask_src=h1[:, :H], out_colsum=gb2, precision=args.prec), 2.0 * M * H * H),
     ("colsum 400 of 81920", lambda: dense.gemm(None, h1, colsum=torch.zeros(2 * H, device=dev), accumulate=True, precision=args.prec), 2.0 * M * 2 * H),
 ]
 out = []
