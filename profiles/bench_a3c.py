@@ -74,4 +74,8 @@ if rank == 0:
                       "value_graph": steps / (ms_graph * 1e-3) if args.graph else None, "tf32": bool(args.tf32), "groups": args.groups, "p2p_push": bool(args.p2p), "params": net.n_params,
                       "allreduce_bytes": net.n_flat * 4 if world > 1 else 0}))
 if world > 1:
-    torch.distributed.destroy_process_group()
+    # no process-group teardown: with NCCL collectives captured in the iteration's CUDA graph (and peer mappings open)
+    # destroy_process_group() did not return on 2 B200s; the numbers are out, leave without it
+    udist.barrier()
+    sys.stdout.flush()
+    os._exit(0)
