@@ -4,11 +4,14 @@
 // accumulation with float REDs).  sm_100a only.
 //
 // Shape of the problem: K is 200 or 625 for the forward / data-gradient GEMMs and 81 920 (the rollout batch) for the
-// weight gradients; N is 200, 625 or 1.  None of the operand shapes is TMA-friendly (625-float rows are not 16-byte
-// multiples, operands are slices of wider activations, the weight gradients read A transposed), so the 256 threads of a
-// CTA stage the operand tiles themselves: global -> registers (next chunk in flight) -> shared memory in the canonical
-// no-swizzle K-major UMMA layout (8 x 16-byte core matrices; transposed sources are transposed on the way in),
-// fence.proxy.async, one elected thread issues the MMAs of the chunk and commits them to the stage's mbarrier.
+// weight gradients; N is 200, 625 or 1.  Operand staging is chosen per operand (OP_* below):
+//   * row-major, 16-byte aligned sources (activations, dz, weights kept as [N,K]) arrive by TMA: 2-D tensor maps, boxes
+//     of 32 x 128 / 32 x BN floats with the 128-byte swizzle, one thread issues the copies and the MMAs;
+//   * everything TMA cannot take (625-float rows, 4-byte aligned slices, the transposed reads X^T . dY of the weight
+//     gradients, the hi/lo split of 3xTF32) is staged by the 256 threads: global -> registers (next chunk in flight) ->
+//     shared memory in the canonical no-swizzle K-major UMMA layout (8 x 16-byte core matrices; transposed sources are
+//     transposed on the way in), fence.proxy.async, then one elected thread issues the MMAs of the chunk.
+// Either way the MMAs of a chunk are committed to the stage's mbarrier (tcgen05.commit), which frees the stage.
 //
 // fp32 accuracy: kind::tf32 reads 10 mantissa bits of every operand.  PREC3X stages every tile twice -- hi = the top 19
 // bits, lo = a - hi -- and issues hi.hi + hi.lo + lo.hi into the same accumulator (3xTF32: ~2e-7 relative, what the
