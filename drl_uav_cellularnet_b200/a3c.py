@@ -415,7 +415,6 @@ class A3CTrainer:
         self.E = lo
         self.streams = [torch.cuda.Stream(device=dev) for _ in self.envs] if len(self.envs) > 1 else [None]
         self.seed = int(seed)
-        self.gen = torch.Generator(device=dev).manual_seed(int(seed))
         self._draws = torch.zeros(1, dtype=torch.int32, device=dev)          # rollout steps sampled so far (Philox counter)
         # T + 1 slots: the env writes the state after step t straight into slot t + 1 (bind_obs_idx); slot T is the
         # bootstrap state and becomes slot 0 of the next rollout
@@ -490,12 +489,13 @@ class A3CTrainer:
     def train_iteration(self):
         return self.update(self.rollout())
 
-    # ---- one CUDA graph per iteration: ~250 small launches (env step, reset, GEMMs, softmax, sampling, ...) replayed
+    # ---- one CUDA graph per iteration: ~100 launches (env step, reset, dense products, softmax + sampling, ...) replayed
     # ---- without Python or launch latency between them
     def capture(self, warmup: int = 2):
         """Capture ``train_iteration`` into a CUDA graph (after `warmup` eager iterations on a side stream).
-        The env / net / trainer buffers are all persistent, so the captured pointers stay valid; the sampling
-        generator is registered with the graph so that every replay draws fresh actions."""
+        The env / net / trainer buffers are all persistent, so the captured pointers stay valid; the sampling kernel
+        reads its Philox draw counter from device memory (``self._draws``, advanced inside the graph), so every replay
+        draws fresh actions.  The stream forks of a grouped rollout are captured with it."""
         dev = self.env.device
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
