@@ -84,3 +84,19 @@ def test_rmsprop_is_the_tf1_rule():
     m2 = 0.9 * m1 + 0.1 * g2 * g2
     assert np.allclose(ms, m2)
     assert np.allclose(p, p0 - 1e-4 * g1 / np.sqrt(m1 + 1e-10) - 1e-4 * g2 / np.sqrt(m2 + 1e-10))
+
+
+def test_committed_vectors_are_the_oracles_answers():
+    """tests/golden/acnet_oracle_vectors.npz (oracle/make_acnet_vectors.py): oracle-generated known answers for a small
+    net, frozen so that kernel tests compare against numbers that do not move; regenerating must reproduce them."""
+    import os
+    from oracle import make_acnet_vectors as mk
+    path = os.path.join(os.path.dirname(__file__), "golden", "acnet_oracle_vectors.npz")
+    got, want = mk.build(), np.load(path)
+    assert set(got) == set(want.files)
+    for k in want.files:
+        assert np.allclose(np.asarray(got[k], dtype=np.float64), want[k].astype(np.float64), rtol=1e-12, atol=1e-14), k
+    p = {k[2:]: want[k] for k in want.files if k.startswith("p_")}
+    s = orc.dense_from_idx(want["idx"], int(want["n_s"]))
+    _, _, cache = orc.forward(p, s)
+    assert (cache["h1a"] == 6.0).any() and (cache["h1a"] == 0.0).any() and (cache["h2a"] == 0.0).any()

@@ -357,3 +357,34 @@ def test_softmax_sample_kernel_matches_inverse_cdf(pkg):
     ctr += 1
     _, a4 = net.sample_head(hh, seed, 0, ctr, 0)
     assert not torch.equal(a2, a4)
+
+
+@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: not yet run on a B200 (an XPASS is the expected outcome)")
+def test_small_net_against_the_oracles_known_answers(pkg):
+    """ACNet(600, 25, hidden=40) against tests/golden/acnet_oracle_vectors.npz (oracle/acnet_oracle.py, float64):
+    probabilities / values within 1e-5, losses within 1e-5, every gradient within 1e-4 of its largest entry."""
+    import os
+    from drl_uav_cellularnet_b200.a3c import ACNet
+    w = np.load(os.path.join(os.path.dirname(__file__), "golden", "acnet_oracle_vectors.npz"))
+    n_s, n_a, H = int(w["n_s"]), int(w["n_a"]), int(w["hidden"])
+    net = ACNet(n_s, n_a, "cuda:0", hidden=H)
+    f32 = lambda k: torch.from_numpy(w[k].astype(np.float32)).cuda()  # noqa: E731
+    with torch.no_grad():
+        net.p["W1"][:, :H].copy_(f32("p_la")); net.p["W1"][:, H:].copy_(f32("p_lc"))
+        net.p["b1"][:H].copy_(f32("p_la_b")); net.p["b1"][H:].copy_(f32("p_lc_b"))
+        for mine, theirs in (("Wa2", "la2"), ("ba2", "la2_b"), ("Wa3", "ap"), ("ba3", "ap_b"), ("Wc2", "lc2"), ("bc2", "lc2_b"),
+                             ("Wc3", "v"), ("bc3", "v_b")):
+            net.p[mine].copy_(f32("p_" + theirs))
+    idx = torch.from_numpy(w["idx"]).cuda()
+    prob, v, _ = net.forward(idx)
+    assert float((prob.double().cpu() - torch.from_numpy(w["a_prob"])).abs().max()) < 1e-5
+    assert float((v.double().cpu() - torch.from_numpy(w["v"])).abs().max()) < 1e-4
+    a_loss, c_loss = net.accumulate_grads(idx, torch.from_numpy(w["a_his"]).cuda(), f32("v_target"))
+    assert abs(float(a_loss) - float(w["a_loss"])) < 1e-5 and abs(float(c_loss) - float(w["c_loss"])) < 1e-5 * max(1.0, float(w["c_loss"]))
+    G = net.g
+    pairs = [(G["W1"][:, :H], "la"), (G["b1"][:H], "la_b"), (G["Wa2"], "la2"), (G["ba2"], "la2_b"), (G["Wa3"], "ap"), (G["ba3"], "ap_b"),
+             (G["W1"][:, H:], "lc"), (G["b1"][H:], "lc_b"), (G["Wc2"], "lc2"), (G["bc2"], "lc2_b"), (G["Wc3"], "v"), (G["bc3"], "v_b")]
+    for mine, name in pairs:
+        ref = torch.from_numpy(w["g_" + name]).reshape(mine.shape)
+        scale = float(ref.abs().max()) + 1e-12
+        assert float((mine.double().cpu() - ref).abs().max()) <= 1e-4 * scale, name
