@@ -76,6 +76,6 @@ if rank == 0:
 if world > 1:
     # no process-group teardown: with NCCL collectives captured in the iteration's CUDA graph (and peer mappings open)
     # destroy_process_group() did not return on 2 B200s; the numbers are out, leave without it
-    udist.barrier()
+    torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(0)
