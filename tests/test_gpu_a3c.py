@@ -359,7 +359,6 @@ def test_softmax_sample_kernel_matches_inverse_cdf(pkg):
     assert not torch.equal(a2, a4)
 
 
-@pytest.mark.xfail(strict=False, reason="written after round 1's GPU budget was spent: not yet run on a B200 (an XPASS is the expected outcome)")
 def test_small_net_against_the_oracles_known_answers(pkg):
     """ACNet(600, 25, hidden=40) against tests/golden/acnet_oracle_vectors.npz (oracle/acnet_oracle.py, float64):
     probabilities / values within 1e-5, losses within 1e-5, every gradient within 1e-4 of its largest entry."""
