@@ -100,3 +100,31 @@ def test_committed_vectors_are_the_oracles_answers():
     s = orc.dense_from_idx(want["idx"], int(want["n_s"]))
     _, _, cache = orc.forward(p, s)
     assert (cache["h1a"] == 6.0).any() and (cache["h1a"] == 0.0).any() and (cache["h2a"] == 0.0).any()
+
+
+def test_gradients_agree_with_central_differences():
+    """independent of autograd: a few coordinates of every parameter by central differences of the oracle's own losses
+    (away from the relu6 kinks the losses are smooth; step 1e-6, agreement to 1e-6 relative)"""
+    rs = np.random.RandomState(7)
+    n_s, n_a, H, M, K = 40, 5, 6, 17, 5
+    p = orc.init_params(n_s, n_a, hidden=H, seed=7)
+    for k in p:
+        if k.endswith("_b"):
+            p[k] = rs.normal(0.0, 0.3, size=p[k].shape)
+    s = orc.dense_from_idx(rs.randint(0, n_s, size=(M, K)), n_s)
+    a_his, v_target = rs.randint(0, n_a, size=M), rs.normal(size=M)
+    _, _, g = orc.losses_and_grads(p, s, a_his, v_target)
+    eps = 1e-6
+    for name in orc.ACTOR + orc.CRITIC:
+        which = 0 if name in orc.ACTOR else 1
+        flat = p[name].reshape(-1)
+        for i in rs.choice(flat.size, size=min(4, flat.size), replace=False):
+            old = flat[i]
+            flat[i] = old + eps
+            up = orc.losses_and_grads(p, s, a_his, v_target)[which]
+            flat[i] = old - eps
+            dn = orc.losses_and_grads(p, s, a_his, v_target)[which]
+            flat[i] = old
+            fd = (up - dn) / (2 * eps)
+            an = g[name].reshape(-1)[i]
+            assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)) + 1e-9, (name, i, fd, an)
