@@ -497,6 +497,7 @@ class A3CTrainer:
         reads its Philox draw counter from device memory (``self._draws``, advanced inside the graph), so every replay
         draws fresh actions.  The stream forks of a grouped rollout are captured with it."""
         dev = self.env.device
+        warmup = max(1, int(warmup))      # first launches set function attributes / allocate the error word: not capturable
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
