@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="default", choices=sorted(WORKLOADS))
     ap.add_argument("--envs", type=int, default=0, help="environments per GPU (0 = the workload's: 4096 / 1024)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "fp64"])
+    ap.add_argument("--precision", default="fp32_guarded", choices=["fp32_guarded", "fp32", "fp64"])
     ap.add_argument("--obs", default="f32", choices=["f32", "f32_incremental", "none"])
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 500)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -292,7 +292,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "f64", "data": "synthetic",
+            "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
             "ue_steps_per_s": value * N_UE,
             "config": {"workload": "%s: %d batched envs per GPU, %d UAV-BS x %d UE, grid 100, group-reference "
                                    "mobility (float64), Philox fading, random %s actions, obs=%s, reset every 2000 steps"

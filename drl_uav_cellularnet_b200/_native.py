@@ -14,7 +14,7 @@ MAX_GROUPS = 32
 
 MOB_GROUP, MOB_TRACE = 0, 1
 FADE_PHILOX, FADE_INJECTED, FADE_NONE = 0, 1, 2
-PREC_FP32_FAST, PREC_FP64_PARITY = 0, 1
+PREC_FP32_FAST, PREC_FP64_PARITY, PREC_FP32_GUARDED = 0, 1, 2
 OBS_NONE, OBS_F32, OBS_F32_INCREMENTAL = 0, 1, 3
 OK, EINVAL, ECUDA, ETRACE, ENOMEM, EACTION = 0, -1, -2, -3, -4, -5
 ERR_ACTION, ERR_TRACE, ERR_CLAMP = 1, 2, 4
@@ -36,6 +36,7 @@ class Cfg(C.Structure):
         ("shadow_mean", C.c_double), ("shadow_sd", C.c_double),
         ("ho_thresh_db", C.c_double), ("out_thresh_db", C.c_double),
         ("v_min", C.c_double), ("v_max", C.c_double), ("aggregation", C.c_double),
+        ("guard_db", C.c_double),
     ]
 
 
@@ -72,7 +73,7 @@ GEMM_TF32, GEMM_3XTF32 = 0, 1
 SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
-    "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_get_cfg", "uavenv_last_error",
+    "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_guard_hits", "uavenv_get_cfg", "uavenv_last_error",
     "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
     "uavnet_p2p_rmsprop", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record",
     "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
@@ -106,6 +107,7 @@ def lib():
     L.uavenv_get_state.argtypes = [vp, vp, C.c_int64]
     L.uavenv_set_state.argtypes = [vp, vp, C.c_int64]
     L.uavenv_check.argtypes = [vp, P(C.c_uint32), vp]
+    L.uavenv_guard_hits.argtypes = [vp, P(C.c_int64), vp]
     L.uavenv_get_cfg.argtypes = [vp]
     L.uavenv_get_cfg.restype = P(Cfg)
     L.uavenv_last_error.argtypes = [vp]

@@ -28,6 +28,7 @@ namespace uavk {
 constexpr int MAX_BS = 32;
 constexpr int MAX_GROUPS = 32;
 constexpr int CTA_THREADS = 256;
+constexpr int GUARD_LIST = 64;
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_CTOR = 2 };
 enum { MOB_GROUP = 0, MOB_TRACE = 1 };
@@ -54,6 +55,9 @@ __device__ __forceinline__ uint32_t ho_pack(int cur, int f0, int f1, int f2, int
            ((uint32_t)depth << 20) | ((uint32_t)outp << 22);
 }
 
+// FP32_GUARDED: the UE's decision is pending (set only between the UE loop and the guard phase of one launch)
+constexpr uint32_t HO_PENDING = 1u << 28;
+
 // Everything that is fixed for the lifetime of a handle.  Passed by value as a __grid_constant__ parameter.
 struct DevCfg {
     int E, nBS, nUE, G, nG;
@@ -76,6 +80,11 @@ struct DevCfg {
     float f_Pdb;            // 10 log10(P)
     float f_db_k;           // 10 log10(2):             10 log10(x) = f_db_k * log2(x)
     float f_N, f_sh_mean, f_sh_sd;
+    // FP32_GUARDED: a UE whose fp32 SINR row is within guard_db (dB) of a decision boundary -- top-2 gap (argmax),
+    // best - current - ho_thr (handover), serving SINR - out_thr (outage) -- is re-evaluated in float64 with the
+    // reference operation order, so every decision equals the FP64_PARITY kernel's.  0 = off (FP32_FAST).
+    float guard_db;
+    unsigned long long *guard_hits;   // [1] UEs re-evaluated so far (diagnostic)
     // persistent state (device)
     double2 *xy;            // [E,nUE] float UE positions (x, y): one 16-byte load (ue_mobility.py:434-435)
     double *th_u;           // [E,nUE] last theta uniform, injected-mobility runs only
@@ -123,6 +132,11 @@ struct EnvShared {
     double red_sinr[CTA_THREADS / 32];
     int red_out[CTA_THREADS / 32], red_ho[CTA_THREADS / 32];
     int ok, blocked;
+    // FP32_GUARDED, more than 4 BSs: UEs waiting for their float64 re-evaluation by a whole warp (lane = BS), and the
+    // serving SINR of those UEs as an order-independent fixed-point sum (2^-32 dB units)
+    int guard_n;
+    int guard_ue[GUARD_LIST];
+    long long guard_sum;
 };
 
 // U(MIN,MAX,.) = rand*(MAX-MIN)+MIN (ue_mobility.py:408), no fused multiply-add
@@ -424,17 +438,135 @@ __device__ __forceinline__ T ho_decide(const DevCfg &c, int mode, int best, T be
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// float64 building blocks in the reference's operation order (no fma contraction), shared by the FP64_PARITY kernels
+// and the FP32_GUARDED re-evaluation so that both produce the same bits.
+//   received power P * 10^((gain - loss - fading - eq_loss) / 10) of one (UE, BS) pair (channel.py:220-247,264)
+__device__ __forceinline__ double pair_power_f64(const DevCfg &c, int cx, int cy, int bx, int by, double fade) {
+    const double ax = __dadd_rn(__dmul_rn((double)cx, c.grid_width), -__dmul_rn((double)bx, c.grid_width));
+    const double ay = __dadd_rn(__dmul_rn((double)cy, c.grid_width), -__dmul_rn((double)by, c.grid_width));
+    const double d = sqrt(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));                 // :220-226
+    double loss = 0.0;
+    if (d > c.pl_dis) loss = __dadd_rn(c.pl_a, __dmul_rn(c.pl_b, log10(d)));                // :230-235
+    const double gdb = __dadd_rn(__dadd_rn(__dadd_rn(c.ant_gain, -loss), -fade), -c.eq_loss);  // :245
+    return __dmul_rn(c.P, pow(10.0, gdb / 10.0));                                           // :246, :264
+}
+//   10 log10(p / (N + interference)) (channel.py:266-268)
+__device__ __forceinline__ double sinr_db_f64(const DevCfg &c, double p, double interf) {
+    return __dmul_rn(10.0, log10(p / __dadd_rn(c.N, interf)));
+}
+
+// FP32_GUARDED re-evaluation of one UE's row by ONE thread (the thread-per-UE mapping, and the overflow case of the
+// guard list): the FP64_PARITY arithmetic with run-time loops.  Interference sums: index order for nBS <= 8,
+// prefix + suffix beyond (what env_kernel<NB, true> does for the same nBS).  Rare (about 5e-4 of the UE-steps at the
+// default guard), so it is kept out of line and off the fp32 kernels' register budget.
+__device__ __noinline__ void ue_row_f64(const DevCfg &c, const double *fading_row, const int *bsx, const int *bsy,
+                                        uint32_t genv, int u, int cx, int cy, uint32_t epoch, int cur, int *best_out,
+                                        double *bestS_out, double *curS_out) {
+    const int nBS = c.nBS, cpu = (nBS + 3) >> 2;
+    double p[MAX_BS];
+    double z[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int b = 0; b < nBS; b++) {
+        double fade = 0.0;
+        if (c.fading == FADE_INJECTED) fade = fading_row[b];
+        else if (c.fading == FADE_PHILOX) {
+            if ((b & 3) == 0) normal4_f64(philox4x32_10(genv, (uint32_t)(u * cpu + (b >> 2)), epoch, DOM_FADING, c.k0, c.k1), z);
+            fade = __dadd_rn(c.sh_mean, __dmul_rn(c.sh_sd, z[b & 3]));
+        }
+        p[b] = pair_power_f64(c, cx, cy, bsx[b], bsy[b], fade);
+    }
+    int best = 0;
+    double bestS = -1.0e300, curS = 0.0, pre = 0.0;
+    for (int b = 0; b < nBS; b++) {
+        double interf;
+        if (nBS > 8) {
+            // suffix sums are accumulated from the top (p[nBS-1] + ... + p[b+1]): recomputed per b to keep that order
+            double sf = 0.0;
+            for (int j = nBS - 1; j > b; j--) sf = __dadd_rn(sf, p[j]);
+            interf = __dadd_rn(pre, sf);
+            pre = __dadd_rn(pre, p[b]);
+        } else {
+            interf = 0.0;
+            for (int j = 0; j < nBS; j++) if (j != b) interf = __dadd_rn(interf, p[j]);
+        }
+        const double S = sinr_db_f64(c, p[b], interf);
+        if (b == 0 || S > bestS) { bestS = S; best = b; }               // first maximum (np.argmax)
+        if (b == cur) curS = S;
+    }
+    *best_out = best; *bestS_out = bestS; *curS_out = curS;
+    atomicAdd(c.guard_hits, 1ull);
+}
+
+// The same re-evaluation by a whole warp, lane = BS (the 4-BSs-per-lane mapping of more than 4 BSs, where one
+// thread walking 32 BSs in float64 would stall its warp for tens of microseconds).  All 32 lanes call; every lane
+// returns the UE's (best server, its SINR, SINR of the current cell).
+__device__ __noinline__ void ue_row_f64_warp(const DevCfg &c, const double *fading_row, const int *bsx, const int *bsy,
+                                             uint32_t genv, int u, int cx, int cy, uint32_t epoch, int cur, int *best_out,
+                                             double *bestS_out, double *curS_out) {
+    const int lane = threadIdx.x & 31, nBS = c.nBS, cpu = (nBS + 3) >> 2, b = lane;
+    double p = 0.0;
+    if (b < nBS) {
+        double fade = 0.0;
+        if (c.fading == FADE_INJECTED) fade = fading_row[b];
+        else if (c.fading == FADE_PHILOX) {
+            double z[4];
+            normal4_f64(philox4x32_10(genv, (uint32_t)(u * cpu + (b >> 2)), epoch, DOM_FADING, c.k0, c.k1), z);
+            const int k = b & 3;
+            const double zk = k == 0 ? z[0] : (k == 1 ? z[1] : (k == 2 ? z[2] : z[3]));
+            fade = __dadd_rn(c.sh_mean, __dmul_rn(c.sh_sd, zk));
+        }
+        p = pair_power_f64(c, cx, cy, bsx[b], bsy[b], fade);
+    }
+    double interf = 0.0;
+    if (nBS > 8) {
+        double pre = 0.0, suf = 0.0;
+        for (int j = 0; j < nBS; j++) { const double pj = __shfl_sync(0xffffffffu, p, j); if (j < b) pre = __dadd_rn(pre, pj); }
+        for (int j = nBS - 1; j >= 0; j--) { const double pj = __shfl_sync(0xffffffffu, p, j); if (j > b) suf = __dadd_rn(suf, pj); }
+        interf = __dadd_rn(pre, suf);
+    } else {
+        for (int j = 0; j < nBS; j++) { const double pj = __shfl_sync(0xffffffffu, p, j); if (j != b) interf = __dadd_rn(interf, pj); }
+    }
+    const double S = b < nBS ? sinr_db_f64(c, p, interf) : -1.0e300;
+    int best = b;
+    double bestS = S;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double oS = __shfl_xor_sync(0xffffffffu, bestS, o);
+        const int oB = __shfl_xor_sync(0xffffffffu, best, o);
+        if (oS > bestS || (oS == bestS && oB < best)) { bestS = oS; best = oB; }
+    }
+    *best_out = best; *bestS_out = bestS;
+    *curS_out = __shfl_sync(0xffffffffu, S, cur);
+    if (lane == 0) atomicAdd(c.guard_hits, 1ull);
+}
+
+// FP32_GUARDED: true if a decision ho_decide would take from these fp32 values could differ from the one taken on the
+// float64 values, given |fp32 - float64| < guard_db / 2 per SINR: the argmax (top-2 gap), and per mode the outage
+// compare and the handover-threshold compare (channel.py:141,156-159,170; reset / ctor: :92-93,116).
+__device__ __forceinline__ bool guard_needed(const DevCfg &c, int mode, int best, int cur, float bestS, float second,
+                                             float curS) {
+    const float g = c.guard_db;
+    bool need = (bestS - second) < g;
+    if (mode == MODE_STEP) {
+        need |= fabsf(curS - (float)c.out_thr) < g;
+        need |= (best != cur) && fabsf((bestS - curS) - (float)c.ho_thr) < g;
+    } else {
+        need |= fabsf(bestS - (float)c.out_thr) < g;
+    }
+    return need;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 template <bool F64> struct Real { using T = float; };
 template <> struct Real<true> { using T = double; };
 
 // The channel pass of one UE against all BSs + its handover-word update.
 // NB: compile-time bound on nBS (register arrays).  Returns the serving-cell SINR (pre-handover cell,
 // channel.py:145-146) and updates `word`; flags receive new-outage / handover events.
-template <int NB, bool F64, bool DIAG>
+template <int NB, bool F64, bool DIAG, bool GUARD>
 __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c, const CallArgs &a,
                                                                  const EnvShared &s, int e, uint32_t genv, int u,
                                                                  int cx, int cy, uint32_t epoch, int mode,
-                                                                 uint32_t &word, int &new_out, int &did_ho) {
+                                                                 uint32_t &word, int &new_out, int &did_ho, bool &pending) {
     using T = typename Real<F64>::T;
     const int nBS = c.nBS;
     const size_t pair0 = ((size_t)e * c.nUE + u) * nBS;
@@ -481,13 +613,7 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
         for (int b = 0; b < NB; b++) {
             p[b] = 0.0;
             if (b < nBS) {
-                const double ax = __dadd_rn(__dmul_rn((double)cx, c.grid_width), -__dmul_rn((double)s.bsx[b], c.grid_width));
-                const double ay = __dadd_rn(__dmul_rn((double)cy, c.grid_width), -__dmul_rn((double)s.bsy[b], c.grid_width));
-                const double d = sqrt(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)));     // :220-226
-                double loss = 0.0;
-                if (d > c.pl_dis) loss = __dadd_rn(c.pl_a, __dmul_rn(c.pl_b, log10(d)));    // :230-235
-                const double gdb = __dadd_rn(__dadd_rn(__dadd_rn(c.ant_gain, -loss), -fade[b]), -c.eq_loss);  // :245
-                p[b] = __dmul_rn(c.P, pow(10.0, gdb / 10.0));                               // :246, :264
+                p[b] = pair_power_f64(c, cx, cy, s.bsx[b], s.bsy[b], fade[b]);
             }
         }
         double pre[NB], suf[NB];
@@ -509,7 +635,7 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 #pragma unroll
                 for (int j = 0; j < NB; j++) if (j != b && j < nBS) interf = __dadd_rn(interf, p[j]);
             }
-            S[b] = b < nBS ? __dmul_rn(10.0, log10(p[b] / __dadd_rn(c.N, interf))) : -1.0e300;  // :266-268
+            S[b] = b < nBS ? sinr_db_f64(c, p[b], interf) : -1.0e300;
         }
     } else {
         // fp32 log-domain form: gdb[b] = g0 - (a + k log2 q) - fade;  p = 2^(gdb*ek + log2 P);
@@ -563,6 +689,14 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
     T curS = S[0];
 #pragma unroll
     for (int b = 1; b < NB; b++) if (b == cur) curS = S[b];            // serving SINR of the PRE-handover cell
+    if constexpr (!F64 && GUARD) {
+        // FP32_GUARDED: is any decision of this UE within guard_db of its boundary?  Then no decision is taken here: the
+        // caller queues the UE for the float64 re-evaluation after the UE loop (env_kernel, "guard phase").
+        float second = -3.0e38f;
+#pragma unroll
+        for (int b = 0; b < NB; b++) if (b != best) second = fmaxf(second, S[b]);
+        if (guard_needed(c, mode, best, cur, bestS, second, curS)) { pending = true; return curS; }
+    }
     return ho_decide<T>(c, mode, best, bestS, curS, word, new_out, did_ho);
 }
 
@@ -573,10 +707,10 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 // never total - own; the best server is a shuffle argmax with lowest-index tie break.  All lanes of a
 // group end up with the same (best server, its SINR, SINR of the current cell); the handover / outage decisions are
 // taken by the caller, once per UE.  `u` must be clamped to a valid UE on every lane (shuffles need the whole warp).
-template <int NB, bool DIAG, bool FULL>
+template <int NB, bool DIAG, bool FULL, bool GUARD>
 __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs &a, const EnvShared &s, int e,
                                                  uint32_t genv, int u, int cx, int cy, uint32_t epoch, uint32_t word,
-                                                 int &best_out, float &bestS_out) {
+                                                 int &best_out, float &bestS_out, float &second_out) {
     constexpr int LPU = NB / 4;                                        // lanes per UE
     static_assert(NB == 8 || NB == 16 || NB == 32, "quad mapping");
     const int lane = threadIdx.x & 31, q = lane & (LPU - 1), gbase = lane & ~(LPU - 1);
@@ -636,15 +770,30 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
     // first maximum inside the quad, then a butterfly argmax over the group: ties to the lower BS index
     // (np.argmax, channel.py:141)
     int best = b0;
-    float bestS = S0;
-    if (S1 > bestS) { bestS = S1; best = b0 + 1; }
-    if (S2 > bestS) { bestS = S2; best = b0 + 2; }
-    if (S3 > bestS) { bestS = S3; best = b0 + 3; }
+    float bestS = S0, second = -3.0e38f;
+    if constexpr (GUARD) {
+        // FP32_GUARDED: the runner-up travels with the maximum (the top-2 gap decides whether the argmax can be trusted)
+        if (S1 > bestS) { second = bestS; bestS = S1; best = b0 + 1; } else second = fmaxf(second, S1);
+        if (S2 > bestS) { second = bestS; bestS = S2; best = b0 + 2; } else second = fmaxf(second, S2);
+        if (S3 > bestS) { second = bestS; bestS = S3; best = b0 + 3; } else second = fmaxf(second, S3);
 #pragma unroll
-    for (int o = 1; o < LPU; o <<= 1) {
-        const float oS = __shfl_xor_sync(0xffffffffu, bestS, o);
-        const int oB = __shfl_xor_sync(0xffffffffu, best, o);
-        if (oS > bestS || (oS == bestS && oB < best)) { bestS = oS; best = oB; }
+        for (int o = 1; o < LPU; o <<= 1) {
+            const float oS = __shfl_xor_sync(0xffffffffu, bestS, o);
+            const float o2 = __shfl_xor_sync(0xffffffffu, second, o);
+            const int oB = __shfl_xor_sync(0xffffffffu, best, o);
+            if (oS > bestS || (oS == bestS && oB < best)) { second = fmaxf(bestS, o2); bestS = oS; best = oB; }
+            else second = fmaxf(second, oS);
+        }
+    } else {
+        if (S1 > bestS) { bestS = S1; best = b0 + 1; }
+        if (S2 > bestS) { bestS = S2; best = b0 + 2; }
+        if (S3 > bestS) { bestS = S3; best = b0 + 3; }
+#pragma unroll
+        for (int o = 1; o < LPU; o <<= 1) {
+            const float oS = __shfl_xor_sync(0xffffffffu, bestS, o);
+            const int oB = __shfl_xor_sync(0xffffffffu, best, o);
+            if (oS > bestS || (oS == bestS && oB < best)) { bestS = oS; best = oB; }
+        }
     }
     // SINR of the UE's current (pre-handover) cell lives on lane cur/4 of the group
     const int cur = word & 31, ks = cur & 3;
@@ -652,6 +801,7 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
     const float curS = __shfl_sync(0xffffffffu, mineS, gbase | ((cur >> 2) & (LPU - 1)));
     best_out = best;
     bestS_out = bestS;
+    second_out = second;
     return curS;                                                       // the decisions (ho_decide) are the caller's
 }
 
@@ -746,7 +896,7 @@ constexpr int min_blocks(int nb, bool f64, int nt) { return f64 ? 1 : (nb > 8 ? 
 
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
 //   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
-template <int NB, bool F64, int NT, bool DIAG>
+template <int NB, bool F64, int NT, bool DIAG, bool GUARD>
 __global__ void __launch_bounds__(NT, min_blocks(NB, F64, NT))
 env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a) {
     using T = typename Real<F64>::T;
@@ -842,7 +992,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             }
             if (lane == 0) s.blocked = blocked;
         }
-        if (lane == 0) s.ok = ok;
+        if (lane == 0) { s.ok = ok; s.guard_n = 0; s.guard_sum = 0; }
     }
     if (warp == WARP_GRP && group_tick && lane < c.nG) mob_group_load(s, group_row_load(c, e, lane), lane);
     // the state of this thread's first UE is requested before the barrier: its HBM / L2 latency overlaps the BS warp's
@@ -932,19 +1082,28 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             }
             if (mode != MODE_STEP) word = 0u;
             int best;
-            float bestS;
+            float bestS, second;
             const float curS = full_bs
-                ? ue_channel_quad<NB, DIAG, true>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS)
-                : ue_channel_quad<NB, DIAG, false>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS);
+                ? ue_channel_quad<NB, DIAG, true, GUARD>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS, second)
+                : ue_channel_quad<NB, DIAG, false, GUARD>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS, second);
+            const bool guarded = GUARD && guard_needed(c, mode, best, (int)(word & 31), bestS, second, curS);
             if (stage) {
-                // hand (best server, its SINR, current-cell SINR) to the per-UE decision pass below
+                // hand (best server, its SINR, current-cell SINR, FP32_GUARDED: re-evaluate?) to the per-UE decision
+                // pass below
                 if (live && q == 0) {
-                    reinterpret_cast<int2 *>(stage + u)[0].y = (int)(word | ((uint32_t)best << 23));
+                    reinterpret_cast<int2 *>(stage + u)[0].y = (int)(word | ((uint32_t)best << 23) | (guarded ? HO_PENDING : 0u));
                     reinterpret_cast<int2 *>(stage + u)[1] = make_int2(__float_as_int(bestS), __float_as_int(curS));
                 }
             } else {
                 int new_out, did_ho;
-                const float srvS = ho_decide<float>(c, mode, best, bestS, curS, word, new_out, did_ho);
+                float srvS;
+                if (guarded && live && q == 0) {
+                    double bS, cS;
+                    int bb;
+                    ue_row_f64(c, c.fading == FADE_INJECTED ? a.fading + i * nBS : nullptr, s.bsx, s.bsy, genv, u, cell.x,
+                               cell.y, (uint32_t)epoch, (int)(word & 31), &bb, &bS, &cS);
+                    srvS = (float)ho_decide<double>(c, mode, bb, bS, cS, word, new_out, did_ho);
+                } else srvS = ho_decide<float>(c, mode, best, bestS, curS, word, new_out, did_ho);
                 if (live && q == 0) {
                     sum_sinr += (double)srvS;
                     cnt_out += new_out;
@@ -968,7 +1127,15 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 uint32_t word = (uint32_t)sv.y & 0x7fffffu;
                 const int best = ((uint32_t)sv.y >> 23) & 31;
                 int new_out, did_ho;
-                const float srvS = ho_decide<float>(c, mode, best, __int_as_float(sv.z), __int_as_float(sv.w), word, new_out, did_ho);
+                float srvS;
+                if (GUARD && ((uint32_t)sv.y & HO_PENDING)) {
+                    // FP32_GUARDED: a warp re-evaluates this UE in float64 after the pass (phase D); the mark stays in
+                    // the staging word, which is how phase D finds the UEs if the list overflows
+                    const int slot = atomicAdd(&s.guard_n, 1);
+                    if (slot < GUARD_LIST) s.guard_ue[slot] = u;
+                    continue;
+                }
+                srvS = ho_decide<float>(c, mode, best, __int_as_float(sv.z), __int_as_float(sv.w), word, new_out, did_ho);
                 sum_sinr += (double)srvS;
                 cnt_out += new_out;
                 cnt_ho += did_ho;
@@ -980,6 +1147,39 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = srvS;
                 if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = lin;
                 if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
+            }
+            if constexpr (GUARD) {
+                // ---- (D) FP32_GUARDED: the listed UEs, one warp per UE, lane = BS, float64 in the reference's order
+                __syncthreads();
+                const int n_g = s.guard_n;
+                const bool listed = n_g <= GUARD_LIST;                   // else: every warp scans its share of the UEs
+                for (int k = warp; k < (listed ? n_g : nUE); k += NW) {
+                    const int u = listed ? s.guard_ue[k] : k;
+                    const size_t i = (size_t)e * nUE + u;
+                    const int4 sv = stage[u];
+                    if (!listed && !((uint32_t)sv.y & HO_PENDING)) continue;
+                    const short2 cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
+                    uint32_t word = (uint32_t)sv.y & 0x7fffffu;
+                    double bS, cS;
+                    int bb, new_out, did_ho;
+                    ue_row_f64_warp(c, c.fading == FADE_INJECTED ? a.fading + i * nBS : nullptr, s.bsx, s.bsy, genv, u, cell.x,
+                                    cell.y, (uint32_t)epoch, (int)(word & 31), &bb, &bS, &cS);
+                    const double srvS = ho_decide<double>(c, mode, bb, bS, cS, word, new_out, did_ho);
+                    if (lane == 0) {
+                        // order-independent fixed-point sum: the list order is not deterministic, the result must be
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&s.guard_sum), (unsigned long long)__double2ll_rn(srvS * 4294967296.0));
+                        cnt_out += new_out;
+                        cnt_ho += did_ho;
+                        const int srv = word & 31;
+                        const int lin = ((1 + srv) * G + cell.x) * G + cell.y;
+                        stk(c.ho + i, word, keep);
+                        reinterpret_cast<int2 *>(stage + u)[0].y = (int)word;
+                        if (a.serving) a.serving[i] = (uint8_t)srv;
+                        if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = (float)srvS;
+                        if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = lin;
+                        if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
+                    }
+                }
             }
         }
     } else {
@@ -1001,10 +1201,19 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             cell = make_short2((short)xy.x, (short)xy.y);
         }
         if (mode != MODE_STEP) word = 0u;
-        int new_out, did_ho;
-        const T curS = ue_channel_pass<NB, F64, DIAG>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
-                                                      new_out, did_ho);
+        int new_out = 0, did_ho = 0;
+        bool pending = false;
+        const T curS = ue_channel_pass<NB, F64, DIAG, GUARD>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, mode, word,
+                                                      new_out, did_ho, pending);
         if (mode != MODE_CTOR || c.mobility == MOB_TRACE) stk_cell(c.ue_cell, i, cell, keep);
+        if (a.ue_xy) stk_cell(a.ue_xy, i, cell, keep);
+        if (GUARD && pending) {
+            // FP32_GUARDED: decision deferred to the guard phase; the handover word keeps its pre-step value + a mark
+            const int slot = atomicAdd(&s.guard_n, 1);
+            if (slot < GUARD_LIST) s.guard_ue[slot] = u;
+            stk(c.ho + i, word | HO_PENDING, keep);
+            continue;
+        }
         stk(c.ho + i, word, keep);
         sum_sinr += (double)curS;
         cnt_out += new_out;
@@ -1013,7 +1222,6 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // per-call outputs live at the same addresses every step: kept in L2 like the state
         if (a.serving) stk(a.serving + i, (uint8_t)srv, keep);
         if (a.serving_sinr) stk(reinterpret_cast<T *>(a.serving_sinr) + i, curS, keep);
-        if (a.ue_xy) stk_cell(a.ue_xy, i, cell, keep);
         if (a.obs_idx) stk(a.obs_idx + (size_t)e * (nUE + nBS) + u, ((1 + srv) * G + cell.x) * G + cell.y, keep);
         if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
     }
@@ -1031,6 +1239,42 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     if (bulk_ok && warp == WARP_TMA) bulk_wait_all();                  // the zeros have landed
     __syncthreads();                                                   // barrier 2
 
+    if constexpr (GUARD && NB <= 4) {
+        // ---- guard phase (FP32_GUARDED, thread-per-UE mapping): the UEs whose fp32 row was within guard_db of a decision
+        // boundary are re-evaluated in float64 now that the UE loop's registers are dead (the call costs the hot loop
+        // nothing), one warp per UE with lane = BS: a lone thread walking the row's float64 log10 / pow chains would hold
+        // its CTA for tens of microseconds.  CTA-uniform branch, taken by about 2 % of the CTAs at the default guard.
+        const int n_g = s.guard_n;
+        if (n_g > 0) {
+            const bool listed = n_g <= GUARD_LIST;                       // else: every warp scans its share for the marks
+            for (int k = warp; k < (listed ? n_g : nUE); k += NW) {
+                const int u = listed ? s.guard_ue[k] : k;
+                const size_t i = (size_t)e * nUE + u;
+                uint32_t word = ldk(c.ho + i, keep);
+                if (!(word & HO_PENDING)) continue;
+                word &= ~HO_PENDING;
+                const short2 cell = ldk_cell(c.ue_cell, i, keep);
+                double bS, cS;
+                int bb, new_out, did_ho;
+                ue_row_f64_warp(c, c.fading == FADE_INJECTED ? a.fading + i * nBS : nullptr, s.bsx, s.bsy, genv, u, cell.x,
+                                cell.y, (uint32_t)epoch, (int)(word & 31), &bb, &bS, &cS);
+                const double srvS = ho_decide<double>(c, mode, bb, bS, cS, word, new_out, did_ho);
+                if (lane == 0) {
+                    stk(c.ho + i, word, keep);
+                    // order-independent accumulation: the list order is not deterministic, the results must be
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&s.guard_sum), (unsigned long long)__double2ll_rn(srvS * 4294967296.0));
+                    if (new_out) atomicAdd(&s.red_out[0], 1);
+                    if (did_ho) atomicAdd(&s.red_ho[0], 1);
+                    const int srv = word & 31;
+                    if (a.serving) stk(a.serving + i, (uint8_t)srv, keep);
+                    if (a.serving_sinr) stk(reinterpret_cast<float *>(a.serving_sinr) + i, (float)srvS, keep);
+                    if (a.obs_idx) stk(a.obs_idx + (size_t)e * (nUE + nBS) + u, ((1 + srv) * G + cell.x) * G + cell.y, keep);
+                    if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
+                }
+            }
+            __syncthreads();
+        }
+    }
     if (warp == WARP_GRP && group_tick) mob_group_finish(c, s, e, genv, tick - 1, inj, lane);
     {
         // the dense observation gets its non-zero cells (UEs on the plane of their post-handover serving BS, BSs on
@@ -1058,6 +1302,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         double tot = 0.0;
         int no = 0, nh = 0;
         for (int w = 0; w < NW; w++) { tot += s.red_sinr[w]; no += s.red_out[w]; nh += s.red_ho[w]; }
+        if constexpr (!F64 && GUARD) tot += (double)s.guard_sum * (1.0 / 4294967296.0);   // FP32_GUARDED re-evaluated UEs
         const double mean = tot / (double)nUE;                         // channel.py:216
         if (mode == MODE_STEP) {
             step_n += 1;                                               // mobile_env.py:179

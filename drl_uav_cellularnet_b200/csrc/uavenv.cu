@@ -69,12 +69,12 @@ int use_device(uavenv_t *h) {
 
 typedef void (*env_kernel_fn)(const DevCfg, const CallArgs);
 
-template <bool F64, int NT, bool DIAG>
+template <bool F64, int NT, bool DIAG, bool GUARD>
 env_kernel_fn pick_nb(int nBS) {
-    if (nBS <= 4) return env_kernel<4, F64, NT, DIAG>;
-    if (nBS <= 8) return env_kernel<8, F64, NT, DIAG>;
-    if (nBS <= 16) return env_kernel<16, F64, NT, DIAG>;
-    return env_kernel<32, F64, NT, DIAG>;
+    if (nBS <= 4) return env_kernel<4, F64, NT, DIAG, GUARD>;
+    if (nBS <= 8) return env_kernel<8, F64, NT, DIAG, GUARD>;
+    if (nBS <= 16) return env_kernel<16, F64, NT, DIAG, GUARD>;
+    return env_kernel<32, F64, NT, DIAG, GUARD>;
 }
 
 /* Launch plan of the step kernel (one CTA per env): the zero tile the TMA warp streams from and the CTAs per SM.
@@ -90,9 +90,13 @@ int plan_kernel(uavenv_t *h) {
     h->threads = small ? NT_SMALL : CTA_THREADS;
     /* two builds of every kernel: the lean one, and one that can also write the full SINR matrix / the applied fading
      * (uavenv_out.sinr_all / fading_used; selected on the first call that passes either pointer) */
-    if (small) { h->kernel = (void *)pick_nb<false, NT_SMALL, false>(h->d.nBS); h->kernel_diag = (void *)pick_nb<false, NT_SMALL, true>(h->d.nBS); }
-    else if (f64) { h->kernel = (void *)pick_nb<true, CTA_THREADS, false>(h->d.nBS); h->kernel_diag = (void *)pick_nb<true, CTA_THREADS, true>(h->d.nBS); }
-    else { h->kernel = (void *)pick_nb<false, CTA_THREADS, false>(h->d.nBS); h->kernel_diag = (void *)pick_nb<false, CTA_THREADS, true>(h->d.nBS); }
+    const bool guard = h->cfg.precision == UAVENV_PREC_FP32_GUARDED;
+    const int nb = h->d.nBS;
+    if (small && guard) { h->kernel = (void *)pick_nb<false, NT_SMALL, false, true>(nb); h->kernel_diag = (void *)pick_nb<false, NT_SMALL, true, true>(nb); }
+    else if (small) { h->kernel = (void *)pick_nb<false, NT_SMALL, false, false>(nb); h->kernel_diag = (void *)pick_nb<false, NT_SMALL, true, false>(nb); }
+    else if (f64) { h->kernel = (void *)pick_nb<true, CTA_THREADS, false, false>(nb); h->kernel_diag = (void *)pick_nb<true, CTA_THREADS, true, false>(nb); }
+    else if (guard) { h->kernel = (void *)pick_nb<false, CTA_THREADS, false, true>(nb); h->kernel_diag = (void *)pick_nb<false, CTA_THREADS, true, true>(nb); }
+    else { h->kernel = (void *)pick_nb<false, CTA_THREADS, false, false>(nb); h->kernel_diag = (void *)pick_nb<false, CTA_THREADS, true, false>(nb); }
     const int64_t n_cells = (int64_t)(h->d.nBS + 1) * h->d.G * h->d.G;
     int dev_smem = 0, n_sm = 0;
     CU(h, cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
@@ -212,6 +216,7 @@ int uavenv_cfg_default(uavenv_cfg *c, int32_t n_envs, int32_t n_bs, int32_t n_ue
     c->ho_thresh_db = 1;       /* channel.py:82 */
     c->out_thresh_db = 0;      /* channel.py:7 */
     c->v_min = 0; c->v_max = 1; c->aggregation = 0.8;    /* mobile_env.py:76 */
+    c->guard_db = 1e-3;
     return UAVENV_OK;
 }
 
@@ -252,9 +257,11 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
     if (cfg->n_act < 2 || cfg->n_act > 9) return fail(h, UAVENV_EINVAL, "n_act must be in [2,9]%s");
     if (cfg->mobility != UAVENV_MOB_GROUP && cfg->mobility != UAVENV_MOB_TRACE)
         return fail(h, UAVENV_EINVAL, "mobility model not defined%s");   /* sys.exit at mobile_env.py:91 */
-    if (cfg->fading < 0 || cfg->fading > 2 || (cfg->precision != 0 && cfg->precision != 1) ||
+    if (cfg->fading < 0 || cfg->fading > 2 || (cfg->precision < 0 || cfg->precision > 2) ||
         (cfg->obs_mode != UAVENV_OBS_NONE && cfg->obs_mode != UAVENV_OBS_F32 && cfg->obs_mode != UAVENV_OBS_F32_INCREMENTAL))
         return fail(h, UAVENV_EINVAL, "bad fading / precision / obs_mode%s");
+    if (cfg->precision == UAVENV_PREC_FP32_GUARDED && !(cfg->guard_db > 0 && cfg->guard_db <= 1))
+        return fail(h, UAVENV_EINVAL, "guard_db must be in (0, 1] dB%s");
     if (nG < 1 || nG > UAVENV_MAX_GROUPS) return fail(h, UAVENV_EINVAL, "n_groups must be in [1,32]%s");
     int64_t tot = 0;
     for (int g = 0; g < nG; g++) {
@@ -293,6 +300,7 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
     d.f_Pdb = (float)(10.0 * log10(d.P));
     d.f_db_k = (float)(10.0 * log10(2.0));
     d.f_N = (float)d.N; d.f_sh_mean = (float)cfg->shadow_mean; d.f_sh_sd = (float)cfg->shadow_sd;
+    d.guard_db = cfg->precision == UAVENV_PREC_FP32_GUARDED ? (float)cfg->guard_db : 0.f;
 
     const int64_t nu = (int64_t)E * nUE;
     Field f[F_COUNT] = {
@@ -305,8 +313,8 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
     }
     CU(h, cudaMalloc(&h->init_bs, nBS * 4));
     CU(h, cudaMalloc(&h->ue_group, nUE));
-    CU(h, cudaMalloc(&h->err_flags, 4));
-    CU(h, cudaMemset(h->err_flags, 0, 4));
+    CU(h, cudaMalloc(&h->err_flags, 16));                 /* [0] sticky flags, [8..16) FP32_GUARDED re-evaluation count */
+    CU(h, cudaMemset(h->err_flags, 0, 16));
     CU(h, cudaMalloc(&h->h_action, (size_t)E * 8));
     CU(h, cudaMalloc(&h->h_reward, (size_t)E * 8));
     CU(h, cudaMalloc(&h->h_mean, (size_t)E * 8));
@@ -347,6 +355,7 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
     d.init_bs = (const int16_t *)h->init_bs; d.ue_group = (const uint8_t *)h->ue_group;
     d.trace = nullptr; d.trace_T = 0; d.trace_per_env = 0;
     d.err_flags = (uint32_t *)h->err_flags;
+    d.guard_hits = (unsigned long long *)((char *)h->err_flags + 8);
 
     {
         int rc = plan_kernel(h);
@@ -526,6 +535,18 @@ int uavenv_check(uavenv_t *h, uint32_t *flags_out, void *stream) {
     if (f & 1u) return fail(h, UAVENV_EACTION, "an action was outside [0, n_act^n_bs) (or a digit >= n_act); those envs were not stepped%s");
     if (f & 8u) return fail(h, UAVENV_ECUDA, "bounds-check build: an observation index fell outside the env's observation%s");
     if (f & 2u) return fail(h, UAVENV_ETRACE, "trace exhausted (step_n past the end of the trace); those envs were not stepped%s");
+    return UAVENV_OK;
+}
+
+int uavenv_guard_hits(uavenv_t *h, int64_t *hits_out, void *stream) {
+    if (!h || !hits_out) return UAVENV_EINVAL;
+    int rc = use_device(h);
+    if (rc) return rc;
+    unsigned long long v = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(h, cudaMemcpyAsync(&v, (char *)h->err_flags + 8, 8, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    *hits_out = (int64_t)v;
     return UAVENV_OK;
 }
 

@@ -29,7 +29,7 @@ StepInfo = namedtuple("info_tup", ["r_dissect", "step_n", "ue_loc", "bs_loc", "o
 
 _MOBILITY = {"group": N.MOB_GROUP, "read_trace": N.MOB_TRACE}
 _FADING = {"philox": N.FADE_PHILOX, "injected": N.FADE_INJECTED, "none": N.FADE_NONE}
-_PRECISION = {"fp32": N.PREC_FP32_FAST, "fp64": N.PREC_FP64_PARITY}
+_PRECISION = {"fp32": N.PREC_FP32_FAST, "fp64": N.PREC_FP64_PARITY, "fp32_guarded": N.PREC_FP32_GUARDED}
 _OBS = {"none": N.OBS_NONE, "f32": N.OBS_F32, "f32_incremental": N.OBS_F32_INCREMENTAL}
 _STATE_FIELDS = [("xy", np.float64), ("theta_u", np.float64), ("group", np.float64),
                  ("counters", np.int32), ("bs_xy", np.int16), ("ue_cell", np.int16), ("ho_word", np.uint32)]
@@ -288,6 +288,15 @@ class BatchedMobiEnvironment:
         if rc:
             self._raise(rc, "check")
         return int(f.value)
+
+    @property
+    def guard_hits(self) -> int:
+        """precision="fp32_guarded": UEs re-evaluated in float64 so far (uavenv_guard_hits). Synchronises."""
+        v = C.c_int64(0)
+        rc = self._lib.uavenv_guard_hits(self._h, C.byref(v), self._stream())
+        if rc:
+            self._raise(rc, "guard_hits")
+        return int(v.value)
 
     @property
     def launch_plan(self) -> dict:

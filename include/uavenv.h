@@ -40,7 +40,12 @@ enum { UAVENV_FADE_PHILOX = 0,    /* N(mean,sd) per (UE,BS) pair per pass from P
        UAVENV_FADE_INJECTED = 1,  /* caller supplies float64 fading[E,nUE,nBS] for every pass (parity replay) */
        UAVENV_FADE_NONE = 2 };
 enum { UAVENV_PREC_FP32_FAST = 0, /* fp32 + MUFU intrinsics, log-domain SINR */
-       UAVENV_PREC_FP64_PARITY = 1 }; /* float64, reference operation order; decision-exact replay */
+       UAVENV_PREC_FP64_PARITY = 1, /* float64, reference operation order; decision-exact replay */
+       UAVENV_PREC_FP32_GUARDED = 2 }; /* the fp32 pass; a UE whose row is within cfg.guard_db of a decision boundary (top-2
+                                          gap of the argmax, handover threshold, outage threshold: channel.py:141,156-159,170)
+                                          is re-evaluated in float64 inside the same kernel, so serving BS / handover /
+                                          outage decisions equal FP64_PARITY's bit for bit; SINR / reward stay fp32-accurate
+                                          (1e-3 dB / 1e-5 relative, BASELINE.json north_star) */
 enum { UAVENV_OBS_NONE = 0,
        UAVENV_OBS_F32 = 1,        /* float32 [E, nBS+1, G, G], fully rewritten every step (mobile_env.py:107,169-170,194) */
        UAVENV_OBS_F32_INCREMENTAL = 3 }; /* float32; the caller keeps the SAME buffer between calls and never writes it:
@@ -72,6 +77,9 @@ typedef struct uavenv_cfg {
     double out_thresh_db;        /* OUT_THRESH 0 */
     double v_min, v_max;         /* group velocity (0,1) */
     double aggregation;          /* 0.8 */
+    double guard_db;             /* FP32_GUARDED: width of the re-evaluation band in dB.  Default 1e-3: a decision compares two
+                                    SINRs, so the band must exceed twice the largest |fp32 - float64| SINR difference; measured
+                                    2.6e-5 dB at the reference sizes, 1.0e-4 dB at 32 BS x 2048 UE (profiles/r2/parity_stats.json) */
 } uavenv_cfg;
 
 /* Optional per-call inputs; device pointers; NULL = not supplied. */
@@ -156,6 +164,9 @@ int uavenv_set_state(uavenv_t *h, const void *host_buf, int64_t bytes);
 /* Sticky device-side error flags since the last check (bit0 action out of range, bit1 trace exhausted,
  * bit2 UE cell clamped from G to G-1).  Synchronises the stream. */
 int uavenv_check(uavenv_t *h, uint32_t *flags_out, void *stream);
+
+/* FP32_GUARDED diagnostic: UEs re-evaluated in float64 since the handle was created.  Synchronises the stream. */
+int uavenv_guard_hits(uavenv_t *h, int64_t *hits_out, void *stream);
 
 /* Diagnostic: the launch plan of the step kernel -- CTAs (one per env), threads per CTA, bytes of the zeroed
  * shared-memory tile the TMA warp streams the observation from (0: plain stores + atomics fallback for odd sizes)
