@@ -72,11 +72,11 @@ GEMM_TF32, GEMM_3XTF32 = 0, 1
 # every symbol include/uavenv.h and include/uavnet.h declare
 SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
-    "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
+    "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_step_host_state", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_guard_hits", "uavenv_get_cfg", "uavenv_last_error",
     "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
     "uavnet_p2p_rmsprop", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record",
-    "uavenv_launch_count", "uavenv_version", "uavenv_diag_fill", "uavenv_launch_plan", "uavenv_diag_fill_ring", "uavenv_diag_fill_env",
+    "uavenv_launch_count", "uavenv_version", "uavenv_launch_plan",
 ]
 
 _lib = None
@@ -100,6 +100,7 @@ def lib():
     for f in (L.uavenv_ctor_pass, L.uavenv_reset, L.uavenv_step):
         f.argtypes = [vp, P(In), P(Out), vp]
     L.uavenv_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    L.uavenv_step_host_state.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.uavenv_coverage_map.argtypes = [vp, vp, vp, vp, vp]
     L.uavenv_state_bytes.argtypes = [vp]
     L.uavenv_state_bytes.restype = C.c_int64
@@ -116,8 +117,6 @@ def lib():
     L.uavenv_launch_count.restype = C.c_int64
     L.uavenv_version.restype = C.c_char_p
     L.uavenv_launch_plan.argtypes = [vp, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_int32)]
-    L.uavenv_diag_fill_ring.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
-    L.uavenv_diag_fill_env.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
     L.uavnet_sparse_fwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.uavnet_sparse_bwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp]
     L.uavnet_softmax_sample.argtypes = [vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
@@ -128,11 +127,30 @@ def lib():
     L.uavnet_p2p_free.argtypes = [vp]
     L.uavnet_p2p_rmsprop.argtypes = [P(vp), P(vp), vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp]
     L.uavnet_rmsprop.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, vp]
-    L.uavenv_diag_fill.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp]
     L.uavnet_gemm.argtypes = [P(GemmDesc), vp]
     L.uavnet_gemm_check.argtypes = []
     L.uavnet_rank1_mask.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
-    L.uavnet_rollout_record.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
+    L.uavnet_rollout_record.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp]
     L.uavnet_nstep_targets.argtypes = [vp, vp, vp, C.c_int32, C.c_int64, C.c_float, vp, vp]
     _lib = L
     return L
+
+
+# ---- diagnostics library (include/uavenv_diag.h): not part of the product boundary ----
+DIAG_SO = os.path.join(PKG, "libuavenv_diag.so")
+DIAG_SYMBOLS = ["uavenv_diag_fill", "uavenv_diag_fill_ring", "uavenv_diag_fill_env"]
+_diag = None
+
+
+def diag_lib():
+    global _diag
+    if _diag is None:
+        if not os.path.isfile(DIAG_SO):
+            raise ImportError("%s is missing: build it with `python -m drl_uav_cellularnet_b200.build`" % DIAG_SO)
+        L = C.CDLL(DIAG_SO)
+        vp = C.c_void_p
+        L.uavenv_diag_fill.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, vp]
+        L.uavenv_diag_fill_ring.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.uavenv_diag_fill_env.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp]
+        _diag = L
+    return _diag

@@ -428,7 +428,8 @@ class A3CTrainer:
         self.buf_h2a = torch.empty((self.T, self.E, net.h), dtype=torch.float32, device=dev)
         self.buf_prob = torch.empty((self.T, self.E, net.n_a), dtype=torch.float32, device=dev)
         self.buf_logits = torch.empty((self.E, net.n_a), dtype=torch.float32, device=dev)
-        self.ep_return = torch.zeros(self.E, dtype=torch.float64, device=dev)
+        self.ep_return = torch.zeros(self.E, dtype=torch.float64, device=dev)       # ep_r of the running episodes
+        self.ep_finished = torch.full((self.E,), float("nan"), dtype=torch.float64, device=dev)   # return of each env's last finished episode
         for e, sl in zip(self.envs, self.slices):
             e.bind_obs_idx(self.buf_idx[0][sl])
             e.reset()
@@ -444,7 +445,8 @@ class A3CTrainer:
         env.bind_obs_idx(self.buf_idx[t + 1][sl])
         _, r, _, _ = env.step(a)                                         # main.py:198
         rc = net._lib.uavnet_rollout_record(_ptr(r), _ptr(env.done_u8), env.n_envs, _ptr(self.buf_r[t][sl]),
-                                            _ptr(self.buf_done[t][sl]), _ptr(self.ep_return[sl]), net._stream())
+                                            _ptr(self.buf_done[t][sl]), _ptr(self.ep_return[sl]), _ptr(self.ep_finished[sl]),
+                                            net._stream())
         if rc:
             raise RuntimeError("uavnet_rollout_record failed (%d)" % rc)
         env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)

@@ -17,6 +17,10 @@ CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "libuavenv.so")
 SOURCES = ["uavenv.cu", "uavnet.cu"]
 HEADERS = ["env_kernels.cuh", "philox.cuh", "tc_gemm.cuh", os.path.join(ROOT, "include", "uavenv.h"), os.path.join(ROOT, "include", "uavnet.h")]
+# diagnostics of the observation stream (include/uavenv_diag.h): a library of its own, not part of the product C-ABI
+DIAG_SO = os.path.join(PKG, "libuavenv_diag.so")
+DIAG_SOURCES = ["uavenv_diag.cu"]
+DIAG_HEADERS = ["env_kernels.cuh", "philox.cuh", os.path.join(ROOT, "include", "uavenv_diag.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -31,12 +35,23 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: cannot build libuavenv.so")
 
 
-def up_to_date() -> bool:
-    if not os.path.isfile(SO):
+def up_to_date(so: str = SO, sources=SOURCES, headers=HEADERS) -> bool:
+    if not os.path.isfile(so):
         return False
-    t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
+    t = os.path.getmtime(so)
+    deps = [os.path.join(CSRC, s) for s in sources] + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in headers]
     return all(os.path.getmtime(d) <= t for d in deps)
+
+
+def build_diag(force: bool = False) -> str:
+    """libuavenv_diag.so (include/uavenv_diag.h): the zero-fill kernels behind profiles/write_ceiling.py etc."""
+    if not force and up_to_date(DIAG_SO, DIAG_SOURCES, DIAG_HEADERS):
+        return DIAG_SO
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", DIAG_SO] + [os.path.join(CSRC, s) for s in DIAG_SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return DIAG_SO
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = SO) -> str:
@@ -57,3 +72,4 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = SO)
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_diag(force="--force" in sys.argv))

@@ -34,7 +34,7 @@ struct uavenv {
     // device allocations
     void *xy, *th_u, *grp, *ctr, *bs_xy, *ue_cell, *ho, *init_bs, *ue_group, *trace, *err_flags;
     // step_host staging (device)
-    void *h_action, *h_reward, *h_mean, *h_nout, *h_done;
+    void *h_action, *h_reward, *h_mean, *h_nout, *h_done, *h_idx;
     Field fields[F_COUNT];
     bool ctor_done;
     // launch plan of the persistent step kernel
@@ -384,7 +384,7 @@ void uavenv_destroy(uavenv_t *h) {
     cudaGetDevice(&cur);
     if (cur != h->device) cudaSetDevice(h->device);
     void *p[] = {h->xy, h->th_u, h->grp, h->ctr, h->bs_xy, h->ue_cell, h->ho, h->init_bs, h->ue_group,
-                 h->trace, h->err_flags, h->h_action, h->h_reward, h->h_mean, h->h_nout, h->h_done};
+                 h->trace, h->err_flags, h->h_action, h->h_reward, h->h_mean, h->h_nout, h->h_done, h->h_idx};
     for (void *q : p) if (q) cudaFree(q);
     delete h;
 }
@@ -422,8 +422,8 @@ static void *pinned_alias(const void *p) {
     return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
-int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
-                     double *mean_sinr_host, int32_t *n_out_host, void *stream) {
+static int step_host_impl(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
+                          double *mean_sinr_host, int32_t *n_out_host, int32_t *obs_idx_host, void *stream) {
     if (!h || !action_host) return fail(h, UAVENV_EINVAL, "step_host: action_host is NULL%s");
     int rc = use_device(h);
     if (rc) return rc;
@@ -452,14 +452,31 @@ int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, dou
     out.done = done_host ? (uint8_t *)(dn ? dn : h->h_done) : nullptr;
     out.mean_sinr = mean_sinr_host ? (double *)(ms ? ms : h->h_mean) : nullptr;
     out.n_out = n_out_host ? (int32_t *)(no ? no : h->h_nout) : nullptr;
+    const size_t idx_bytes = E * (size_t)(h->d.nUE + h->d.nBS) * 4;
+    if (obs_idx_host) {
+        /* the sparse state goes through device staging + one copy: 4 (nUE + nBS) bytes per env */
+        if (!h->h_idx) CU(h, cudaMalloc(&h->h_idx, idx_bytes));
+        out.obs_idx = (int32_t *)h->h_idx;
+    }
     rc = run_env(h, MODE_STEP, &in, &out, stream);
     if (rc) return rc;
     if (reward_host && !rw) CU(h, cudaMemcpyAsync(reward_host, h->h_reward, E * 8, cudaMemcpyDeviceToHost, st));
     if (done_host && !dn) CU(h, cudaMemcpyAsync(done_host, h->h_done, E, cudaMemcpyDeviceToHost, st));
     if (mean_sinr_host && !ms) CU(h, cudaMemcpyAsync(mean_sinr_host, h->h_mean, E * 8, cudaMemcpyDeviceToHost, st));
     if (n_out_host && !no) CU(h, cudaMemcpyAsync(n_out_host, h->h_nout, E * 4, cudaMemcpyDeviceToHost, st));
+    if (obs_idx_host) CU(h, cudaMemcpyAsync(obs_idx_host, h->h_idx, idx_bytes, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     return UAVENV_OK;
+}
+
+int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
+                     double *mean_sinr_host, int32_t *n_out_host, void *stream) {
+    return step_host_impl(h, action_host, obs_dev, reward_host, done_host, mean_sinr_host, n_out_host, nullptr, stream);
+}
+
+int uavenv_step_host_state(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
+                           double *mean_sinr_host, int32_t *n_out_host, int32_t *obs_idx_host, void *stream) {
+    return step_host_impl(h, action_host, obs_dev, reward_host, done_host, mean_sinr_host, n_out_host, obs_idx_host, stream);
 }
 
 int uavenv_coverage_map(uavenv_t *h, const int16_t *bs_xy_dev, const double *fading_dev, void *out_dev, void *stream) {
@@ -548,43 +565,6 @@ int uavenv_guard_hits(uavenv_t *h, int64_t *hits_out, void *stream) {
     CU(h, cudaStreamSynchronize(st));
     *hits_out = (int64_t)v;
     return UAVENV_OK;
-}
-
-int uavenv_diag_fill(void *dst_dev, int64_t bytes, int64_t bytes_per_cta, int32_t mode, void *stream) {
-    if (!dst_dev || bytes < 16 || (bytes & 15) || bytes_per_cta < 16 || (bytes_per_cta & 15) || (mode != 0 && mode != 1) ||
-        ((uintptr_t)dst_dev & 15))
-        return UAVENV_EINVAL;
-    const int64_t grid = (bytes + bytes_per_cta - 1) / bytes_per_cta;
-    if (grid > 0x7fffffffLL) return UAVENV_EINVAL;
-    fill_kernel<<<(unsigned)grid, CTA_THREADS, 0, (cudaStream_t)stream>>>((char *)dst_dev, (unsigned long long)bytes,
-                                                                          (unsigned long long)bytes_per_cta, mode);
-    return cudaGetLastError() == cudaSuccess ? UAVENV_OK : UAVENV_ECUDA;
-}
-
-int uavenv_diag_fill_ring(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t ring,
-                          int32_t tile_bytes, int32_t flags, void *stream) {
-    if (!dst_dev || bytes < 16 || (bytes & 15) || bytes_per_chunk < 16 || (bytes_per_chunk & 15) || grid < 1 || ring < 1 ||
-        ring > 32 || tile_bytes < 128 || (tile_bytes & 127) || ((uintptr_t)dst_dev & 15))
-        return UAVENV_EINVAL;
-    const size_t dyn = (size_t)ring * tile_bytes;
-    if (dyn > 200 * 1024) return UAVENV_EINVAL;
-    if (cudaFuncSetAttribute((const void *)fill_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn) != cudaSuccess)
-        return UAVENV_ECUDA;
-    fill_ring_kernel<<<grid, 128, dyn, (cudaStream_t)stream>>>((char *)dst_dev, (unsigned long long)bytes,
-                                                               (unsigned long long)bytes_per_chunk, ring, tile_bytes, flags);
-    return cudaGetLastError() == cudaSuccess ? UAVENV_OK : UAVENV_ECUDA;
-}
-
-int uavenv_diag_fill_env(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t tile_bytes,
-                         int32_t flags, int32_t n_red, void *stream) {
-    if (!dst_dev || bytes < 16 || (bytes & 15) || bytes_per_chunk < 16 || (bytes_per_chunk & 15) || grid < 1 ||
-        tile_bytes < 128 || (tile_bytes & 127) || tile_bytes > 200 * 1024 || n_red < 0 || ((uintptr_t)dst_dev & 15))
-        return UAVENV_EINVAL;
-    if (cudaFuncSetAttribute((const void *)fill_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_bytes) != cudaSuccess)
-        return UAVENV_ECUDA;
-    fill_env_kernel<<<grid, 128, tile_bytes, (cudaStream_t)stream>>>((char *)dst_dev, (unsigned long long)bytes,
-                                                                     (unsigned long long)bytes_per_chunk, tile_bytes, flags, n_red);
-    return cudaGetLastError() == cudaSuccess ? UAVENV_OK : UAVENV_ECUDA;
 }
 
 int uavenv_launch_plan(const uavenv_t *h, int32_t *grid, int32_t *threads, int32_t *tile_bytes, int32_t *ctas_per_sm) {

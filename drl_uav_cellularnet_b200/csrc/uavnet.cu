@@ -302,13 +302,21 @@ __global__ void __launch_bounds__(NET_THREADS) rank1_mask_kernel(const float *__
 // one rollout step's bookkeeping (main.py:199-211: ep_r += r; buffer_r.append(r)) in one launch
 __global__ void __launch_bounds__(NET_THREADS) rollout_record_kernel(const double *__restrict__ r, const uint8_t *__restrict__ done,
                                                                      long long E, float *__restrict__ r_out,
-                                                                     uint8_t *__restrict__ done_out, double *__restrict__ ep_return) {
+                                                                     uint8_t *__restrict__ done_out, double *__restrict__ ep_return,
+                                                                     double *__restrict__ ep_finished) {
     const long long e = (long long)blockIdx.x * NET_THREADS + threadIdx.x;
     if (e >= E) return;
     const double x = r[e];
+    const uint8_t d = done[e];
     r_out[e] = (float)x;
-    done_out[e] = done[e];
-    if (ep_return) ep_return[e] += x;
+    done_out[e] = d;
+    if (ep_return) {
+        const double tot = ep_return[e] + x;                     // ep_r += r (main.py:199)
+        if (d) {                                                  // episode over: GLOBAL_RUNNING_R gets ep_r, ep_r = 0 (:188,246-252)
+            if (ep_finished) ep_finished[e] = tot;
+            ep_return[e] = 0.0;
+        } else ep_return[e] = tot;
+    }
 }
 
 // n-step value targets of the worker loop (main.py:217-227), one thread per env walking its T rewards backwards
@@ -324,9 +332,50 @@ __global__ void __launch_bounds__(NET_THREADS) nstep_targets_kernel(const float 
     }
 }
 
-int grid_for(long long items) {
+// ---- per-device host state.  One process usually drives one GPU, but nothing here assumes it: every entry point
+// switches to the device that owns its first pointer argument (like uavenv's use_device), and the SM count, the gemm
+// error word and the function attributes are kept per device ordinal.
+constexpr int MAX_DEVICES = 64;
+struct DeviceState {
+    int n_sm;                     // cudaDevAttrMultiProcessorCount (0 = not queried yet)
+    unsigned int *gemm_err;       // device word, sticky: a CTA gave up on an mbarrier (protocol error)
+    bool gemm_attr_done[18];
+};
+DeviceState g_dev[MAX_DEVICES];
+
+// make the device that owns `p` current; returns its ordinal (or the current device if p is not a device pointer)
+int use_device_of(const void *p, void *stream) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return 0; }
+    static int n_dev = -1;
+    if (n_dev < 0 && cudaGetDeviceCount(&n_dev) != cudaSuccess) { cudaGetLastError(); n_dev = 1; }
+    // a stream that is being captured already lives on the right device; pointer queries are kept out of captures
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (n_dev > 1 && cudaStreamIsCapturing((cudaStream_t)stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    if (p && n_dev > 1 && cap == cudaStreamCaptureStatusNone) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) == cudaSuccess) {
+            if ((at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) && at.device != cur && at.device >= 0) {
+                if (cudaSetDevice(at.device) == cudaSuccess) cur = at.device;
+            }
+        } else cudaGetLastError();
+    }
+    return cur < MAX_DEVICES ? cur : 0;
+}
+
+int sm_count(int dev) {
+    DeviceState &d = g_dev[dev];
+    if (d.n_sm <= 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+        d.n_sm = n;
+    }
+    return d.n_sm;
+}
+
+int grid_for(long long items, int dev) {
     long long g = (items + NET_THREADS - 1) / NET_THREADS;
-    const long long cap = 148LL * 8 * 4;          // a few waves of 8 CTAs per SM; the kernels are grid-stride
+    const long long cap = (long long)sm_count(dev) * 8 * 4;   // a few waves of 8 CTAs per SM; the kernels are grid-stride
     if (g > cap) g = cap;
     return (int)(g < 1 ? 1 : g);
 }
@@ -343,7 +392,8 @@ int uavnet_sparse_fwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
     if (!idx || !W || !out || M < 1 || K < 1 || n_rows < 1 || H < 4 || (H & 3) || !aligned16(W) || !aligned16(out) ||
         (b && !aligned16(b)))
         return UAVNET_EINVAL;
-    sparse_fwd_kernel<<<grid_for(M * (H / 4)), NET_THREADS, 0, (cudaStream_t)stream>>>(
+    const int dev = use_device_of(idx, stream);
+    sparse_fwd_kernel<<<grid_for(M * (H / 4), dev), NET_THREADS, 0, (cudaStream_t)stream>>>(
         idx, M, K, (const float4 *)W, (const float4 *)b, H / 4, (float4 *)out, relu6);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
@@ -352,7 +402,8 @@ int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
                       void *stream) {
     if (!idx || !dpre || !dW || M < 1 || K < 1 || n_rows < 1 || H < 4 || (H & 3) || !aligned16(dpre) || !aligned16(dW))
         return UAVNET_EINVAL;
-    sparse_bwd_kernel<<<grid_for(M * (H / 4)), NET_THREADS, 0, (cudaStream_t)stream>>>(idx, M, K, (const float4 *)dpre,
+    const int dev = use_device_of(idx, stream);
+    sparse_bwd_kernel<<<grid_for(M * (H / 4), dev), NET_THREADS, 0, (cudaStream_t)stream>>>(idx, M, K, (const float4 *)dpre,
                                                                                     H / 4, (float4 *)dW);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
@@ -360,7 +411,8 @@ int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
 int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,
                           float *dz, int64_t ldz, float *loss_row, void *stream) {
     if (!prob || !a_his || !td || !dz || M < 1 || A < 1 || ldz < A) return UAVNET_EINVAL;
-    const int grid = grid_for(M * 32);
+    const int dev = use_device_of(prob, stream);
+    const int grid = grid_for(M * 32, dev);
     const float inv_m = 1.0f / (float)M;
     const long long *ah = (const long long *)a_his;
     cudaStream_t st = (cudaStream_t)stream;
@@ -419,7 +471,8 @@ int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_loca
     const long long n4 = n >> 2, per4 = (n4 + world - 1) / world;
     const long long lo4 = (long long)rank * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
     if (lo4 >= hi4) return UAVNET_OK;
-    p2p_rmsprop_kernel<<<grid_for(hi4 - lo4), NET_THREADS, 0, (cudaStream_t)stream>>>(pp, ms_local, lo4, hi4, rank, world, lr,
+    const int dev = use_device_of(ms_local, stream);
+    p2p_rmsprop_kernel<<<grid_for(hi4 - lo4, dev), NET_THREADS, 0, (cudaStream_t)stream>>>(pp, ms_local, lo4, hi4, rank, world, lr,
                                                                                      decay, eps, 1.0f / (float)world);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
@@ -427,8 +480,9 @@ int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_loca
 int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t seed, uint32_t row_offset,
                           const uint32_t *counter_dev, uint32_t counter_add, float *prob, int64_t *action, void *stream) {
     if (!logits || M < 1 || A < 1 || (!prob && !action)) return UAVNET_EINVAL;
+    const int dev = use_device_of(logits, stream);
     const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
-    const int grid = grid_for(M * 32);
+    const int grid = grid_for(M * 32, dev);
     cudaStream_t st = (cudaStream_t)stream;
     long long *act = (long long *)action;
     if (A <= 256) softmax_sample_kernel<8><<<grid, NET_THREADS, 0, st>>>(logits, M, A, s0, s1, row_offset, counter_dev, counter_add, prob, act);
@@ -439,22 +493,25 @@ int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t se
 
 int uavnet_rank1_mask(const float *dv, const float *w, const float *h, int64_t M, int32_t H, float *out, void *stream) {
     if (!dv || !w || !h || !out || M < 1 || H < 4 || (H & 3) || !aligned16(w) || !aligned16(h) || !aligned16(out)) return UAVNET_EINVAL;
-    rank1_mask_kernel<<<grid_for(M * (H / 4)), NET_THREADS, 0, (cudaStream_t)stream>>>(dv, (const float4 *)w, (const float4 *)h, M,
+    const int dev = use_device_of(dv, stream);
+    rank1_mask_kernel<<<grid_for(M * (H / 4), dev), NET_THREADS, 0, (cudaStream_t)stream>>>(dv, (const float4 *)w, (const float4 *)h, M,
                                                                                      H / 4, (float4 *)out);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
 int uavnet_rollout_record(const double *reward, const uint8_t *done, int64_t E, float *reward_out, uint8_t *done_out,
-                          double *ep_return, void *stream) {
+                          double *ep_return, double *ep_finished, void *stream) {
     if (!reward || !done || !reward_out || !done_out || E < 1) return UAVNET_EINVAL;
+    use_device_of(reward, stream);
     rollout_record_kernel<<<(unsigned)((E + NET_THREADS - 1) / NET_THREADS), NET_THREADS, 0, (cudaStream_t)stream>>>(
-        reward, done, E, reward_out, done_out, ep_return);
+        reward, done, E, reward_out, done_out, ep_return, ep_finished);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
 int uavnet_nstep_targets(const float *rewards, const uint8_t *dones, const float *v_boot, int32_t T, int64_t E, float gamma,
                          float *out, void *stream) {
     if (!rewards || !dones || !v_boot || !out || T < 1 || E < 1) return UAVNET_EINVAL;
+    use_device_of(rewards, stream);
     nstep_targets_kernel<<<(unsigned)((E + NET_THREADS - 1) / NET_THREADS), NET_THREADS, 0, (cudaStream_t)stream>>>(
         rewards, dones, v_boot, T, E, gamma, out);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
@@ -463,7 +520,8 @@ int uavnet_nstep_targets(const float *rewards, const uint8_t *dones, const float
 int uavnet_rmsprop(float *param, float *grad, float *ms, int64_t n, float lr, float decay, float eps, float grad_scale,
                    int32_t zero_grad, void *stream) {
     if (!param || !grad || !ms || n < 1 || !aligned16(param) || !aligned16(grad) || !aligned16(ms)) return UAVNET_EINVAL;
-    rmsprop_kernel<<<grid_for((n + 3) / 4), NET_THREADS, 0, (cudaStream_t)stream>>>(param, grad, ms, n, lr, decay, eps,
+    const int dev = use_device_of(param, stream);
+    rmsprop_kernel<<<grid_for((n + 3) / 4, dev), NET_THREADS, 0, (cudaStream_t)stream>>>(param, grad, ms, n, lr, decay, eps,
                                                                                    grad_scale, zero_grad);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
@@ -486,7 +544,6 @@ static bool make_tmap(tmap_encode_t encode, CUtensorMap *map, const float *base,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static unsigned int *g_gemm_err = nullptr;          // device word, sticky: a CTA gave up on an mbarrier (protocol error)
 
 int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     if (!d || !d->B || d->M < 0 || d->N < 1 || d->K < 1 || d->N > 65536) return UAVNET_EINVAL;
@@ -503,6 +560,8 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     if (d->out_colsum && (d->accumulate || !d->D)) return UAVNET_EINVAL;
     if (d->precision != UAVNET_GEMM_TF32 && d->precision != UAVNET_GEMM_3XTF32) return UAVNET_EINVAL;
     const bool p3 = d->precision == UAVNET_GEMM_3XTF32;
+    const int dev = use_device_of(d->B, stream);
+    DeviceState &ds = g_dev[dev];
     tc::GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.A = d->A; g.lda = d->lda; g.a_trans = d->a_trans ? 1 : 0;
@@ -533,7 +592,7 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     long long split = d->split_k;
     if (!d->accumulate) split = 1;
     else if (split == 0) {                          // fill the GPU about twice
-        split = (2 * 148) / (tiles_m * tiles_n);
+        split = (2 * sm_count(dev)) / (tiles_m * tiles_n);
         if (split < 1) split = 1;
     }
     if (split > chunks) split = chunks;
@@ -547,11 +606,11 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("UAVNET_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     g.dbg = dbg;
-    if (!g_gemm_err) {
-        if (cudaMalloc(&g_gemm_err, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); g_gemm_err = nullptr; return UAVNET_ECUDA; }
-        cudaMemset(g_gemm_err, 0, sizeof(unsigned int));
+    if (!ds.gemm_err) {
+        if (cudaMalloc(&ds.gemm_err, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); ds.gemm_err = nullptr; return UAVNET_ECUDA; }
+        cudaMemset(ds.gemm_err, 0, sizeof(unsigned int));
     }
-    g.err = g_gemm_err;
+    g.err = ds.gemm_err;
     // staging mode per operand: TMA boxes for row-major, 16-byte aligned operands (one MMA per k-step only: the hi/lo
     // split of 3xTF32 needs the data in registers), threads otherwise
     static int no_tma = -1;
@@ -580,25 +639,35 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
         UAVK_G(false, 2, 0), UAVK_G(false, 2, 1), UAVK_G(false, 2, 2),
         UAVK_G(true, 0, 0), UAVK_G(true, 0, 1), nullptr, UAVK_G(true, 1, 0), UAVK_G(true, 1, 1), nullptr, nullptr, nullptr, nullptr};
 #undef UAVK_G
-    static bool attr_done[18] = {false};
     const int which = (p3 ? 9 : 0) + am * 3 + bm;
     if (!kerns[which]) return UAVNET_EINVAL;
-    if (!attr_done[which]) {
+    if (!ds.gemm_attr_done[which]) {
         if (cudaFuncSetAttribute(kerns[which], cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
             cudaGetLastError();
             return UAVNET_ECUDA;
         }
-        attr_done[which] = true;
+        ds.gemm_attr_done[which] = true;
     }
     kerns[which]<<<(unsigned)grid, tc::NTHR, smem, (cudaStream_t)stream>>>(g);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
 int uavnet_gemm_check(void) {
-    if (!g_gemm_err) return 0;
-    unsigned int v = 0;
-    if (cudaMemcpy(&v, g_gemm_err, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return UAVNET_ECUDA; }
-    return (int)v;
+    // any device this process launched uavnet_gemm on
+    int cur = 0, bad = 0;
+    cudaGetDevice(&cur);
+    for (int dv = 0; dv < MAX_DEVICES; dv++) {
+        if (!g_dev[dv].gemm_err) continue;
+        unsigned int v = 0;
+        if (cudaSetDevice(dv) != cudaSuccess || cudaMemcpy(&v, g_dev[dv].gemm_err, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();
+            cudaSetDevice(cur);
+            return UAVNET_ECUDA;
+        }
+        bad |= (int)v;
+    }
+    cudaSetDevice(cur);
+    return bad;
 }
 
 }  // extern "C"

@@ -64,6 +64,13 @@ class BatchedMobiEnvironment:
                  init_bs_xy=None, diagnostics: bool = False, **overrides):
         if mobility_model not in _MOBILITY:
             raise ValueError("mobility model not defined")                 # sys.exit at mobile_env.py:91
+        # what __deepcopy__ needs to build a twin handle (copy.deepcopy(env), gradient.py:15)
+        self._ctor = dict(n_envs=n_envs, nBS=nBS, nUE=nUE, grid_n=grid_n, mobility_model=mobility_model, fading=fading,
+                          precision=precision, obs=obs, seed=seed, env_offset=env_offset, device=device,
+                          group_sizes=None if group_sizes is None else list(group_sizes),
+                          init_bs_xy=None if init_bs_xy is None else np.array(init_bs_xy), diagnostics=diagnostics,
+                          trace_per_env=trace_per_env, **overrides)
+        self._trace_np = None
         if not torch.cuda.is_available():
             raise RuntimeError("drl_uav_cellularnet_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self._lib = N.lib()
@@ -137,6 +144,36 @@ class BatchedMobiEnvironment:
                 self.ctor_pass()
 
     # -- lifetime -----------------------------------------------------------------------------------------
+    _OUT_TENSORS = ("obs", "reward", "mean_sinr", "n_out", "n_ho", "n_blocked", "step_n", "done_u8", "serving", "serving_sinr",
+                    "ue_xy", "bs_xy", "bs_digits", "_own_obs_idx", "sinr_all", "fading_used")
+
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(env) (gradient.py:15: a virtual env for the look-ahead step): a second handle with the same
+        configuration, the same state blob (uavenv_get_state / uavenv_set_state), the same trace and copies of the
+        last outputs.  Draws are keyed by (seed, env id, pass counter), and the counters are part of the state, so the
+        twin's next step sees exactly the fading / movement the original's next step will see (the reference's twin
+        shares the global numpy stream instead and sees the draws that come next in it)."""
+        kw = dict(self._ctor)
+        kw.pop("trace_per_env")
+        if kw["mobility_model"] == "group":
+            kw["warmup_ticks"] = -1                     # no warm-up: the state is copied below
+        kw["device"] = self.device.index
+        twin = BatchedMobiEnvironment(kw.pop("n_envs"), kw.pop("nBS"), kw.pop("nUE"), kw.pop("grid_n"), kw.pop("mobility_model"),
+                                      trace=self._trace_np, trace_per_env=getattr(self, "_trace_per_env", False),
+                                      **{k: v for k, v in kw.items()}) if self._trace_np is not None or kw["mobility_model"] == "group" \
+            else None
+        if twin is None:
+            raise RuntimeError("deepcopy of a read_trace env needs its trace")
+        torch.cuda.synchronize(self.device)
+        twin.set_state(self.get_state())
+        for name in self._OUT_TENSORS:
+            src, dst = getattr(self, name), getattr(twin, name)
+            if src is not None and dst is not None:
+                dst.copy_(src)
+        twin._ctor_done = self._ctor_done
+        memo[id(self)] = twin
+        return twin
+
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
             self._lib.uavenv_destroy(self._h)
@@ -198,6 +235,7 @@ class BatchedMobiEnvironment:
         if rc:
             self._raise(rc, "set_trace")
         self.trace_len = tr.shape[0]
+        self._trace_np, self._trace_per_env = tr, bool(per_env)
 
     def bind_obs_idx(self, buf: Optional[torch.Tensor] = None):
         """Redirect the sparse observation (uavenv_out.obs_idx) to a caller-owned int32 [E, nUE + nBS] buffer, e.g. the
@@ -244,21 +282,29 @@ class BatchedMobiEnvironment:
     step_test = step
 
     def step_host(self, action_host: torch.Tensor, reward_host: torch.Tensor, done_host: Optional[torch.Tensor] = None,
-                  mean_sinr_host: Optional[torch.Tensor] = None, n_out_host: Optional[torch.Tensor] = None):
+                  mean_sinr_host: Optional[torch.Tensor] = None, n_out_host: Optional[torch.Tensor] = None,
+                  obs_idx_host: Optional[torch.Tensor] = None):
         """uavenv_step_host: int64 [E] actions in (pinned) HOST memory in, reward/done/... in HOST memory out;
-        the copies and the stream synchronisation are inside the call.  The observation stays on the device."""
+        the copies and the stream synchronisation are inside the call.  The dense observation stays on the device;
+        obs_idx_host (int32 [E, nUE + nBS], uavenv_step_host_state) also returns the state to the host in sparse form."""
         for t in (action_host, reward_host, done_host, mean_sinr_host, n_out_host):
             if t is not None and (t.is_cuda or not t.is_contiguous() or t.numel() != self.n_envs):
                 raise ValueError("step_host takes contiguous host tensors of n_envs elements")
+        if obs_idx_host is not None and (obs_idx_host.is_cuda or not obs_idx_host.is_contiguous() or obs_idx_host.dtype != torch.int32
+                                         or obs_idx_host.numel() != self.n_envs * (self.nUE + self.nBS)):
+            raise ValueError("obs_idx_host must be a contiguous int32 host tensor of n_envs * (nUE + nBS) elements")
         key = tuple(0 if t is None else t.data_ptr() for t in (action_host, reward_host, done_host, mean_sinr_host,
-                                                               n_out_host))
+                                                               n_out_host, obs_idx_host))
         args = self._host_args.get(key)
         if args is None:                      # ctypes argument objects are cached per buffer set (hot loop)
             if len(self._host_args) > 64:
                 self._host_args.clear()
             args = self._host_args[key] = (_ptr(action_host), _ptr(self.obs), _ptr(reward_host), _ptr(done_host),
-                                           _ptr(mean_sinr_host), _ptr(n_out_host))
-        rc = self._lib.uavenv_step_host(self._h, *args, self._stream())
+                                           _ptr(mean_sinr_host), _ptr(n_out_host), _ptr(obs_idx_host))
+        if obs_idx_host is None:
+            rc = self._lib.uavenv_step_host(self._h, *args[:6], self._stream())
+        else:
+            rc = self._lib.uavenv_step_host_state(self._h, *args, self._stream())
         if rc:
             self._raise(rc, "step_host")
         return self.obs
@@ -380,6 +426,20 @@ class MobiEnvironment:
         self.state = np.zeros((nBS + 1, grid_n, grid_n))                           # mobile_env.py:107
         self.step_n = 0
         self.channel = _ChannelView(self)
+
+    def __deepcopy__(self, memo):
+        """virtual_env = deepcopy(actual_env) (gradient.py:15)"""
+        import copy
+        twin = MobiEnvironment.__new__(MobiEnvironment)
+        twin.nBS, twin.nUE, twin.grid_n, twin.bs_h = self.nBS, self.nUE, self.grid_n, self.bs_h
+        twin.mobility_model = self.mobility_model
+        twin._b = copy.deepcopy(self._b, memo)
+        twin.action_space_dim, twin.observation_space_dim = self.action_space_dim, self.observation_space_dim
+        twin.state = np.array(self.state)
+        twin.step_n = self.step_n
+        twin.channel = _ChannelView(twin)
+        memo[id(self)] = twin
+        return twin
 
     def SetBsH(self, h):                                                           # mobile_env.py:111
         self.bs_h = h

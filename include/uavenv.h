@@ -145,6 +145,12 @@ int uavenv_step(uavenv_t *h, const uavenv_in *in, const uavenv_out *out, void *s
 int uavenv_step_host(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
                      double *mean_sinr_host, int32_t *n_out_host, void *stream);
 
+/* The same, and the step's STATE is returned to the host too, in sparse form: obs_idx_host int32 [E, nUE + nBS] (see
+ * uavenv_out.obs_idx) -- what a host-side policy consumes of gym's `state` (mobile_env.py:194) without moving the dense
+ * 4 (nBS+1) G^2 bytes per env over PCIe. */
+int uavenv_step_host_state(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
+                           double *mean_sinr_host, int32_t *n_out_host, int32_t *obs_idx_host, void *stream);
+
 /* LTEChannel.GetSinrInArea (channel.py:411-433; main_test.py:89): per env the coverage map out[e, x, y] = downlink SINR (dB)
  * of cell (x, y) from its nearest BS, row / column 0 zero; out is float32 (fast) / float64 (parity) [E, G, G].
  * bs_xy_dev: int16 [E,nBS,2] BS cells, NULL = the envs' current BS cells.  fading_dev: float64 [E, (G-1)^2, nBS] draws in
@@ -172,24 +178,6 @@ int uavenv_guard_hits(uavenv_t *h, int64_t *hits_out, void *stream);
  * shared-memory tile the TMA warp streams the observation from (0: plain stores + atomics fallback for odd sizes)
  * and resident CTAs per SM. */
 int uavenv_launch_plan(const uavenv_t *h, int32_t *grid, int32_t *threads, int32_t *tile_bytes, int32_t *ctas_per_sm);
-
-/* Diagnostic (no reference counterpart): zero-fill `bytes` bytes (multiple of 16, 16-byte aligned device pointer) with
- * the store mechanism of the step kernel's observation stream -- mode 0: st.global.v4, mode 1: cp.async.bulk from a
- * zeroed shared-memory tile -- one CTA per bytes_per_cta.  bench.py uses it to measure the box's write-only HBM
- * ceiling beside the step kernel. */
-int uavenv_diag_fill(void *dst_dev, int64_t bytes, int64_t bytes_per_cta, int32_t mode, void *stream);
-
-/* Diagnostic: the store-warp pattern of the step kernel in isolation -- `grid` persistent CTAs, one warp each, a ring
- * of `ring` shared-memory tiles of tile_bytes, chunk c (bytes_per_chunk) handled by CTA c % grid.  flags bit0: proxy
- * fence per tile, bit1: rotate the issuing lane. */
-int uavenv_diag_fill_ring(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t ring,
-                          int32_t tile_bytes, int32_t flags, void *stream);
-
-/* Diagnostic: the observation pattern of the step kernel's store warp in isolation -- per chunk: bulk copies of one
- * constant zero tile, then (flags bit0) n_red float REDs into the chunk whose copies have completed (the previous one,
- * or with flags bit1 the chunk itself). */
-int uavenv_diag_fill_env(void *dst_dev, int64_t bytes, int64_t bytes_per_chunk, int32_t grid, int32_t tile_bytes,
-                         int32_t flags, int32_t n_red, void *stream);
 
 const uavenv_cfg *uavenv_get_cfg(const uavenv_t *h);
 const char *uavenv_last_error(const uavenv_t *h);

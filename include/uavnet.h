@@ -9,8 +9,9 @@
  *
  * Plain C types, raw device pointers, the stream is a cudaStream_t passed as void*.  Every entry point returns 0 or a
  * negative UAVNET_E* code and only enqueues work on the stream.  One process per GPU (the launch model of this
- * library): the entry points keep per-process state for the current device (function attributes, the gemm error word)
- * and are not thread-safe.
+ * library), but a process may drive several: every entry point makes the device that owns its first pointer argument
+ * current, and the host-side state (SM count, function attributes, the gemm error word) is kept per device ordinal.  Not
+ * thread-safe.
  */
 #ifndef UAVNET_H
 #define UAVNET_H
@@ -58,10 +59,11 @@ int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *
 int uavnet_rank1_mask(const float *dv, const float *w, const float *h, int64_t M, int32_t H, float *out, void *stream);
 
 /* Bookkeeping of one rollout step (main.py:199-211: ep_r += r, buffer_r.append(r)) for E envs in one launch:
- * reward_out[e] = (float) reward[e] (the env kernel's float64 reward), done_out[e] = done[e], ep_return[e] += reward[e]
- * (ep_return may be NULL). */
+ * reward_out[e] = (float) reward[e] (the env kernel's float64 reward), done_out[e] = done[e], ep_return[e] += reward[e];
+ * where done[e], the finished episode's return goes to ep_finished[e] and ep_return[e] restarts at 0 (ep_r of
+ * main.py:188,246-252).  ep_return / ep_finished may be NULL. */
 int uavnet_rollout_record(const double *reward, const uint8_t *done, int64_t E, float *reward_out, uint8_t *done_out,
-                          double *ep_return, void *stream);
+                          double *ep_return, double *ep_finished, void *stream);
 
 /* Discounted n-step value targets of the worker loop (main.py:217-227), batched over envs: walking the rollout
  * backwards, v = r[t] + gamma * (done[t] ? 0 : v), starting from the bootstrap value v_boot of the state after the last

@@ -12,7 +12,7 @@ import torch  # noqa: E402
 
 from drl_uav_cellularnet_b200 import _native as N  # noqa: E402
 
-L = N.lib()
+L = N.diag_lib()          # libuavenv_diag.so (include/uavenv_diag.h)
 nbytes = 4096 * 5 * 100 * 100 * 4
 buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda:0")
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)

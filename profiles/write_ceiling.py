@@ -13,7 +13,7 @@ import torch  # noqa: E402
 
 from drl_uav_cellularnet_b200 import _native as N  # noqa: E402
 
-L = N.lib()
+L = N.diag_lib()          # libuavenv_diag.so (include/uavenv_diag.h)
 dev = torch.device("cuda", 0)
 nbytes = 4096 * 5 * 100 * 100 * 4
 buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)

@@ -66,7 +66,7 @@ def test_entry_points_reject_bad_arguments_without_a_gpu(native):
     assert L.uavenv_reset(None, None, None, None) == native.EINVAL
     assert L.uavenv_check(None, None, None) == native.EINVAL
     assert L.uavenv_launch_plan(None, None, None, None, None) == native.EINVAL
-    assert L.uavenv_diag_fill(None, 1024, 1024, 0, None) == native.EINVAL
+    assert native.diag_lib().uavenv_diag_fill(None, 1024, 1024, 0, None) == -1      # diagnostics library (uavenv_diag.h)
     assert L.uavnet_sparse_fwd(None, 1, 1, 1, None, None, 4, None, 1, None) == -1
     assert L.uavnet_sparse_bwd(None, 1, 1, 1, None, 4, None, None) == -1
     assert L.uavnet_rmsprop(None, None, None, 4, 1e-4, 0.9, 1e-10, 1.0, 1, None) == -1
@@ -74,7 +74,7 @@ def test_entry_points_reject_bad_arguments_without_a_gpu(native):
     assert L.uavnet_gemm(None, None) == -1
     assert L.uavnet_rank1_mask(None, None, None, 1, 4, None, None) == -1
     assert L.uavnet_nstep_targets(None, None, None, 1, 1, 0.9, None, None) == -1
-    assert L.uavnet_rollout_record(None, None, 1, None, None, None, None) == -1
+    assert L.uavnet_rollout_record(None, None, 1, None, None, None, None, None) == -1
     d = native.GemmDesc()
     assert L.uavnet_gemm(C.byref(d), None) == -1                 # no operands
     assert L.uavnet_gemm_check() == 0                            # nothing launched: no device access

@@ -148,6 +148,98 @@ def test_state_clone_what_if_step(pkg):
     assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(srv1, i2["serving"])
 
 
+def _choose_act_gradient(virtual_env_after_step):
+    """gradient.py:19-35 on the virtual env AFTER its look-ahead step_test(624): per BS the direction whose UEs have the
+    lowest mean serving SINR (nanargmin over x+, x-, y+, y-), joint action MSB first"""
+    import warnings
+    sinr, bs_loc, ue_loc = virtual_env_after_step
+    act = np.zeros(len(bs_loc))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                      # mean of an empty slice -> nan, as in the reference
+        for b in range(len(bs_loc)):
+            g = np.array([np.mean(sinr[ue_loc[:, 0] > bs_loc[b][0]]), np.mean(sinr[ue_loc[:, 0] <= bs_loc[b][0]]),
+                          np.mean(sinr[ue_loc[:, 1] > bs_loc[b][1]]), np.mean(sinr[ue_loc[:, 1] <= bs_loc[b][1]])])
+            act[b] = np.nanargmin(g)
+    return int(act[3] + act[2] * 5 + act[1] * 25 + act[0] * 125)
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32_guarded"])
+def test_deepcopy_look_ahead_matches_cloned_oracle(pkg, precision):
+    """gradient.py:14-37 through the drop-in class: `virtual_env = deepcopy(actual_env)`, `virtual_env.step_test(624)`,
+    read `channel.current_BS_sinr / bsLoc / ueLoc`, derive the action, step the ACTUAL env with it -- against the oracle,
+    whose clone is a second oracle env replaying the same history (draws are keyed by counters, so a replay is a clone).
+    Decisions bit-exact; the actual env must not notice the virtual step."""
+    import copy
+    from oracle import mobi_oracle as orc
+    seed, T = 99, 40
+    cfg = orc.default_cfg()
+    trace = orc.make_trace(cfg, 7, 3, 2 * T + 8)
+    env = pkg.MobiEnvironment(4, 40, 100, "read_trace", trace=trace, precision=precision, seed=seed)
+
+    def make_oracle(history):
+        o = orc.OracleEnv(cfg, mobility=orc.MOB_TRACE, fading=orc.FADE_PHILOX, seed=seed, env_id=0, trace=trace)
+        o.reset()
+        for a in history:
+            o.step(a)
+        return o
+
+    s = env.reset()
+    oenv = make_oracle([])
+    history = []
+    for t in range(T):
+        venv = copy.deepcopy(env)                                         # gradient.py:15
+        assert venv is not env and venv._b is not env._b
+        assert np.array_equal(venv.channel.current_BS_sinr, env.channel.current_BS_sinr)
+        venv.step_test(624, False)                                        # :17 BSs stay, UEs move
+        voe = make_oracle(history)
+        voe.step(624)
+        assert np.array_equal(venv.channel.current_BS, voe.current_BS), t
+        assert np.array_equal(venv.ueLoc, voe.ue_xy) and np.array_equal(venv.bsLoc[:, :2], voe.bs_xy), t
+        tol = 1e-9 if precision == "fp64" else 1e-3
+        assert np.max(np.abs(venv.channel.current_BS_sinr - voe.current_BS_sinr)) < tol, t
+        action = _choose_act_gradient((venv.channel.current_BS_sinr, venv.bsLoc, venv.ueLoc))
+        o_action = _choose_act_gradient((voe.current_BS_sinr, voe.bs_xy, voe.ue_xy))
+        if precision == "fp64":
+            assert action == o_action, t
+        s, r, d, info = env.step_test(action, False)                      # gradient.py:61
+        os_, orw, od, oi = oenv.step(action)
+        history.append(action)
+        assert np.array_equal(env.channel.current_BS, oenv.current_BS), t
+        assert np.array_equal(s, os_), t
+        assert int(env._b.n_out[0]) == oi["n_out"] and int(env._b.n_ho[0]) == oi["n_ho"], t
+        assert info.step_n == t + 1 == oi["step_n"]
+
+
+def test_deepcopy_batched_group_env_is_independent(pkg):
+    """the batched class clones too (group mobility: positions, group state, phase counters): twin and original produce
+    the same next step, and stepping one leaves the other untouched"""
+    import copy
+    env = pkg.BatchedMobiEnvironment(5, 4, 40, 100, "group", seed=5, precision="fp32_guarded")
+    env.reset()
+    for t in range(3):
+        env.step(np.arange(5) * 100 + t)
+    twin = copy.deepcopy(env)
+    assert torch.equal(twin.obs, env.obs) and torch.equal(twin.serving, env.serving)
+    a = np.array([624, 0, 311, 17, 500])
+    o1, r1, _, i1 = twin.step(a)
+    before = env.get_state()
+    twin.step(a)
+    twin.step(a)
+    after = env.get_state()
+    for k in before:
+        assert np.array_equal(before[k], after[k]), k
+    o2, r2, _, i2 = env.step(a)
+    twin2 = copy.deepcopy(env)
+    assert torch.equal(twin2.reward, r2)
+    # first step of the twin == the same step of the original
+    env3 = pkg.BatchedMobiEnvironment(5, 4, 40, 100, "group", seed=5, precision="fp32_guarded")
+    env3.reset()
+    for t in range(3):
+        env3.step(np.arange(5) * 100 + t)
+    o3, r3, _, i3 = env3.step(a)
+    assert torch.equal(r3, r2) and torch.equal(i3["serving"], i2["serving"]) and torch.equal(o3, o2)
+
+
 @pytest.mark.parametrize("nBS,nUE,G", [(4, 40, 25), (3, 17, 10), (4, 40, 100), (6, 100, 64)])
 def test_observation_paths_agree_with_oracle(pkg, nBS, nUE, G):
     """The dense observation through every code path -- TMA zero stream + count REDs (whole float4s per env),
