@@ -134,6 +134,7 @@ struct EnvShared {
     int ok, blocked;
     // FP32_GUARDED, more than 4 BSs: UEs waiting for their float64 re-evaluation by a whole warp (lane = BS), and the
     // serving SINR of those UEs as an order-independent fixed-point sum (2^-32 dB units)
+    int next_chunk;               // fp32, more than 4 BSs: the next chunk of 32 UEs a warp will take
     int guard_n;
     int guard_ue[GUARD_LIST];
     long long guard_sum;
@@ -455,50 +456,11 @@ __device__ __forceinline__ double sinr_db_f64(const DevCfg &c, double p, double 
     return __dmul_rn(10.0, log10(p / __dadd_rn(c.N, interf)));
 }
 
-// FP32_GUARDED re-evaluation of one UE's row by ONE thread (the thread-per-UE mapping, and the overflow case of the
-// guard list): the FP64_PARITY arithmetic with run-time loops.  Interference sums: index order for nBS <= 8,
-// prefix + suffix beyond (what env_kernel<NB, true> does for the same nBS).  Rare (about 5e-4 of the UE-steps at the
-// default guard), so it is kept out of line and off the fp32 kernels' register budget.
-__device__ __noinline__ void ue_row_f64(const DevCfg &c, const double *fading_row, const int *bsx, const int *bsy,
-                                        uint32_t genv, int u, int cx, int cy, uint32_t epoch, int cur, int *best_out,
-                                        double *bestS_out, double *curS_out) {
-    const int nBS = c.nBS, cpu = (nBS + 3) >> 2;
-    double p[MAX_BS];
-    double z[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int b = 0; b < nBS; b++) {
-        double fade = 0.0;
-        if (c.fading == FADE_INJECTED) fade = fading_row[b];
-        else if (c.fading == FADE_PHILOX) {
-            if ((b & 3) == 0) normal4_f64(philox4x32_10(genv, (uint32_t)(u * cpu + (b >> 2)), epoch, DOM_FADING, c.k0, c.k1), z);
-            fade = __dadd_rn(c.sh_mean, __dmul_rn(c.sh_sd, z[b & 3]));
-        }
-        p[b] = pair_power_f64(c, cx, cy, bsx[b], bsy[b], fade);
-    }
-    int best = 0;
-    double bestS = -1.0e300, curS = 0.0, pre = 0.0;
-    for (int b = 0; b < nBS; b++) {
-        double interf;
-        if (nBS > 8) {
-            // suffix sums are accumulated from the top (p[nBS-1] + ... + p[b+1]): recomputed per b to keep that order
-            double sf = 0.0;
-            for (int j = nBS - 1; j > b; j--) sf = __dadd_rn(sf, p[j]);
-            interf = __dadd_rn(pre, sf);
-            pre = __dadd_rn(pre, p[b]);
-        } else {
-            interf = 0.0;
-            for (int j = 0; j < nBS; j++) if (j != b) interf = __dadd_rn(interf, p[j]);
-        }
-        const double S = sinr_db_f64(c, p[b], interf);
-        if (b == 0 || S > bestS) { bestS = S; best = b; }               // first maximum (np.argmax)
-        if (b == cur) curS = S;
-    }
-    *best_out = best; *bestS_out = bestS; *curS_out = curS;
-    atomicAdd(c.guard_hits, 1ull);
-}
-
-// The same re-evaluation by a whole warp, lane = BS (the 4-BSs-per-lane mapping of more than 4 BSs, where one
-// thread walking 32 BSs in float64 would stall its warp for tens of microseconds).  All 32 lanes call; every lane
-// returns the UE's (best server, its SINR, SINR of the current cell).
+// FP32_GUARDED re-evaluation of one UE's row by a whole warp, lane = BS, in the FP64_PARITY arithmetic: interference sums
+// in index order for nBS <= 8, prefix + suffix beyond (what env_kernel<NB, true> does for the same nBS).  A lone thread
+// walking the row's float64 log10 / pow chains would hold its CTA for tens of microseconds.  Rare (about 5e-4 of the
+// UE-steps at the default guard) and kept out of line, off the fp32 kernels' register budget.  All 32 lanes call; every
+// lane returns the UE's (best server, its SINR, SINR of the current cell).
 __device__ __noinline__ void ue_row_f64_warp(const DevCfg &c, const double *fading_row, const int *bsx, const int *bsy,
                                              uint32_t genv, int u, int cx, int cy, uint32_t epoch, int cur, int *best_out,
                                              double *bestS_out, double *curS_out) {
@@ -708,7 +670,7 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 // group end up with the same (best server, its SINR, SINR of the current cell); the handover / outage decisions are
 // taken by the caller, once per UE.  `u` must be clamped to a valid UE on every lane (shuffles need the whole warp).
 template <int NB, bool DIAG, bool FULL, bool GUARD>
-__device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs &a, const EnvShared &s, int e,
+__device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs &a, const int (&bx4)[4], const int (&by4)[4], int e,
                                                  uint32_t genv, int u, int cx, int cy, uint32_t epoch, uint32_t word,
                                                  int &best_out, float &bestS_out, float &second_out) {
     constexpr int LPU = NB / 4;                                        // lanes per UE
@@ -736,7 +698,7 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
         gdb[k] = 0.f; p[k] = 0.f;
         const int b = b0 + k;
         if (FULL || b < nBS) {
-            const int dx = cx - s.bsx[b], dy = cy - s.bsy[b];
+            const int dx = cx - bx4[k], dy = cy - by4[k];
             const float qd = c.f_q_scale * (float)(dx * dx + dy * dy);
             const float loss = qd > c.f_q_min ? fmaf(c.f_loss_k, __log2f(qd), c.f_loss_a) : 0.f;
             gdb[k] = c.f_g0 - loss - fade[k];
@@ -744,9 +706,15 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
         }
     }
     const float quad = (p[0] + p[1]) + (p[2] + p[3]);
-    float others = 0.f;                                                // quad sums of the other lanes of the group
+    // quad sums of the OTHER lanes of the group: an exclusive butterfly (log2(LPU) shuffles) -- at every level a lane
+    // adds its partner's partial sum to `others` and to its own partial sum; only sums of positive terms, never a difference
+    float others = 0.f, part = quad;
 #pragma unroll
-    for (int r = 1; r < LPU; r++) others += __shfl_sync(0xffffffffu, quad, gbase | ((q + r) & (LPU - 1)));
+    for (int o = 1; o < LPU; o <<= 1) {
+        const float t = __shfl_xor_sync(0xffffffffu, part, o);
+        others += t;
+        part += t;
+    }
     // exclude-self sums inside the quad: (others + the other three)
     const float i0 = others + ((p[1] + p[2]) + p[3]), i1 = others + ((p[0] + p[2]) + p[3]);
     const float i2 = others + ((p[0] + p[1]) + p[3]), i3 = others + ((p[0] + p[1]) + p[2]);
@@ -924,7 +892,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     const double *inj = (group_tick && a.inject_mob) ? a.mob_u + (size_t)e * (nUE + 3 * c.nG) : nullptr;
 
     // ---- phase 0 (no barrier yet): zero stream (one warp) | action + BS move (one warp) | group state (one warp) ----
-    if (bulk_ok && warp == WARP_TMA) {
+    if (bulk_ok && warp == WARP_TMA && !(NB > 4 && !F64)) {
         // The observation's zeros start streaming before anything has been read from HBM: the warp zeroes the tile,
         // publishes it to the async proxy and issues the env's bulk copies.  (An env whose action turns out to be
         // invalid keeps its state but its observation is zeroed.)
@@ -991,7 +959,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             }
             if (lane == 0) s.blocked = blocked;
         }
-        if (lane == 0) { s.ok = ok; s.guard_n = 0; s.guard_sum = 0; }
+        if (lane == 0) { s.ok = ok; s.guard_n = 0; s.guard_sum = 0; s.next_chunk = 0; }
     }
     if (warp == WARP_GRP && group_tick && lane < c.nG) mob_group_load(s, group_row_load(c, e, lane), lane);
     // the state of this thread's first UE is requested before the barrier: its HBM / L2 latency overlaps the BS warp's
@@ -1000,7 +968,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     uint32_t word_0 = 0u;
     double2 p_0 = make_double2(0.0, 0.0);
     double thu_0 = 0.0;
-    if (tid < nUE) {
+    if (tid < nUE && !(NB > 4 && !F64)) {
         const size_t i0 = (size_t)e * nUE + tid;
         cell_0 = ldk_cell(c.ue_cell, i0, keep);
         word_0 = ldk(c.ho + i0, keep);
@@ -1023,164 +991,124 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     double sum_sinr = 0.0;
     int cnt_out = 0, cnt_ho = 0;
     if constexpr (!F64 && NB > 4) {
-        // ---- more than 4 BSs, fp32: two mappings.  (A) thread = UE: movement.  Each UE's (cell, handover word) is
-        // staged through shared memory (coalesced HBM loads here, no global load left in pass B); if the env's UEs do
-        // not fit, HBM is the staging area.
-        int4 *stage = a.cells_off >= 0 ? reinterpret_cast<int4 *>(dyn_smem + a.cells_off) : nullptr;
-        // software-pipelined: the next UE's state is requested before the current one is computed
-        const bool need_word = mode == MODE_STEP || incremental;
-        size_t i_n = (size_t)e * nUE + tid;
-        short2 cell_n = cell_0;                                         // first stage: requested before barrier 1
-        uint32_t word_n = need_word ? word_0 : 0u;
-        double2 p_n = p_0;
-        double thu_n = thu_0;
-        for (int u = tid; u < nUE; u += NT) {
-            const size_t i = i_n;
-            short2 cell = cell_n;
-            const uint32_t word0 = word_n;
-            const double2 p = p_n;
-            const double thu = thu_n;
-            if (u + NT < nUE) {
-                i_n = i + NT;
-                cell_n = ldk_cell(c.ue_cell, i_n, keep);
-                if (need_word) word_n = ldk(c.ho + i_n, keep);
-                if (group_tick) { p_n = ldk(c.xy + i_n, keep); if (inj) thu_n = ldk(c.th_u + i_n, keep); }
-            }
-            if (incremental) {
-                // the cell of the previous step leaves its association plane
-                obs_add(obs_env, (long long)(((size_t)(1 + (word0 & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
-            }
-            if (group_tick) cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, thu, keep);
-            else if (tr) {
-                const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
-                cell = make_short2((short)xy.x, (short)xy.y);
-            }
-            if (mode != MODE_CTOR || c.mobility == MOB_TRACE) stk_cell(c.ue_cell, i, cell, keep);
-            if (stage) stage[u] = make_int4((int)((uint32_t)(uint16_t)cell.x | ((uint32_t)(uint16_t)cell.y << 16)), (int)word0, 0, 0);
-            if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[i] = cell;
+        // ---- more than 4 BSs, fp32: every WARP runs the whole pipeline for chunks of 32 UEs that it draws from a shared
+        // counter -- (A) lane = UE: movement -> cell;  (B) NB/4 lanes = one UE, lane = 4 BSs: channel pass with shuffle
+        // reductions (ue_channel_quad), 32 / (NB/4) UEs at a time;  (C) lane = UE again: handover / outage decisions and the
+        // per-UE outputs, coalesced.  Between the passes only the warp synchronises (a 512-byte staging area per warp),
+        // so the warps of a CTA drift apart and the float64 movement of one overlaps the fp32 / MUFU channel pass of
+        // another.  (The first version ran the passes CTA-wide with a barrier between them: 28 % of all warp cycles were
+        // barrier stalls, profiles/r2/NOTES.md.)  Which warp takes which chunk is not deterministic; every per-env result
+        // is: sums are accumulated in fixed point.
+        __shared__ int4 wstage_all[NW * 32];
+        int4 *wst = wstage_all + warp * 32;
+        // flat observation index of every UE for the count REDs after barrier 2 (if the env's UEs fit; else HBM is re-read)
+        int32_t *lin_arr = a.cells_off >= 0 ? reinterpret_cast<int32_t *>(dyn_smem + a.cells_off) : nullptr;
+        if (bulk_ok && warp == WARP_TMA) {
+            // The zero stream is issued only now: with tens of bulk copies per env the ISSUE can block on the TMA queue for
+            // tens of microseconds (three CTAs per SM share it), and before barrier 1 the whole CTA would wait for it.
+            float4 *z4 = reinterpret_cast<float4 *>(zero_tile);
+            for (int i = lane; i < (int)(tile_bytes / 16); i += 32) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fence_proxy_async_smem();
+            __syncwarp();
+            issue_zero_stream(obs_env, zero_tile, tile_bytes, (uint32_t)n_cells * 4u, lane, c.err_flags);
         }
-        __syncthreads();
-        // ---- (B) NB/4 lanes = one UE, lane = 4 BSs: channel pass with shuffle reductions (ue_channel_quad)
         constexpr int LPU = NB / 4, UPW = 32 / LPU;
         const int q = lane & (LPU - 1);
         const bool full_bs = nBS == NB;
-        for (int base = warp * UPW; base < nUE; base += NW * UPW) {
-            const int uu = base + lane / LPU;
-            const bool live = uu < nUE;
-            const int u = live ? uu : nUE - 1;
-            const size_t i = (size_t)e * nUE + u;
-            short2 cell;
-            uint32_t word;
-            if (stage) {
-                const int2 sv = *reinterpret_cast<const int2 *>(stage + u);
-                cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
-                word = (uint32_t)sv.y;
-            } else {
-                cell = ldk_cell(c.ue_cell, i, keep);
-                word = ldk(c.ho + i, keep);
-            }
-            if (mode != MODE_STEP) word = 0u;
-            int best;
-            float bestS, second;
-            const float curS = full_bs
-                ? ue_channel_quad<NB, DIAG, true, GUARD>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS, second)
-                : ue_channel_quad<NB, DIAG, false, GUARD>(c, a, s, e, genv, u, cell.x, cell.y, (uint32_t)epoch, word, best, bestS, second);
-            const bool guarded = GUARD && guard_needed(c, mode, best, (int)(word & 31), bestS, second, curS);
-            if (stage) {
-                // hand (best server, its SINR, current-cell SINR, FP32_GUARDED: re-evaluate?) to the per-UE decision
-                // pass below
-                if (live && q == 0) {
-                    reinterpret_cast<int2 *>(stage + u)[0].y = (int)(word | ((uint32_t)best << 23) | (guarded ? HO_PENDING : 0u));
-                    reinterpret_cast<int2 *>(stage + u)[1] = make_int2(__float_as_int(bestS), __float_as_int(curS));
+        const bool need_word = mode == MODE_STEP || incremental;
+        // this lane's four BS cells stay in registers for the whole call
+        int bx4[4], by4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = min(4 * q + k, nBS - 1);
+            bx4[k] = s.bsx[b]; by4[k] = s.bsy[b];
+        }
+        const int n_chunks = (nUE + 31) >> 5;
+        long long acc_fix = 0;                                         // serving SINR, 2^-32 dB units
+        for (;;) {
+            int ch = 0;
+            if (lane == 0) ch = atomicAdd(&s.next_chunk, 1);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch >= n_chunks) break;
+            const int u0 = ch << 5, uA = u0 + lane;
+            const bool liveA = uA < nUE;
+            const size_t iA = (size_t)e * nUE + (liveA ? uA : 0);
+            // ---- (A) lane = UE: movement
+            {
+                short2 cell = make_short2(0, 0);
+                uint32_t word0 = 0u;
+                if (liveA) {
+                    cell = ldk_cell(c.ue_cell, iA, keep);
+                    if (need_word) word0 = ldk(c.ho + iA, keep);
+                    if (incremental)       // the cell of the previous step leaves its association plane
+                        obs_add(obs_env, (long long)(((size_t)(1 + (word0 & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
+                    if (group_tick) {
+                        const double2 p = ldk(c.xy + iA, keep);
+                        const double thu = inj ? ldk(c.th_u + iA, keep) : 0.0;
+                        cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, uA, p.x, p.y, thu, keep);
+                    } else if (tr) {
+                        const int2 xy = reinterpret_cast<const int2 *>(tr)[uA];
+                        cell = make_short2((short)xy.x, (short)xy.y);
+                    }
+                    if (mode != MODE_CTOR || c.mobility == MOB_TRACE) stk_cell(c.ue_cell, iA, cell, keep);
+                    if (a.ue_xy) reinterpret_cast<short2 *>(a.ue_xy)[iA] = cell;
                 }
-            } else {
-                int new_out, did_ho;
-                float srvS;
-                if (guarded && live && q == 0) {
-                    double bS, cS;
-                    int bb;
-                    ue_row_f64(c, c.fading == FADE_INJECTED ? a.fading + i * nBS : nullptr, s.bsx, s.bsy, genv, u, cell.x,
-                               cell.y, (uint32_t)epoch, (int)(word & 31), &bb, &bS, &cS);
-                    srvS = (float)ho_decide<double>(c, mode, bb, bS, cS, word, new_out, did_ho);
-                } else srvS = ho_decide<float>(c, mode, best, bestS, curS, word, new_out, did_ho);
+                wst[lane] = make_int4((int)((uint32_t)(uint16_t)cell.x | ((uint32_t)(uint16_t)cell.y << 16)), (int)word0, 0, 0);
+            }
+            __syncwarp();
+            // ---- (B) NB/4 lanes = one UE, lane = 4 BSs
+            const int last_slot = min(31, nUE - 1 - u0);               // shuffles need every lane on a valid UE
+#pragma unroll 1
+            for (int j = 0; j < LPU; j++) {
+                const int slot_raw = j * UPW + lane / LPU;
+                const bool live = slot_raw <= last_slot;
+                const int slot = live ? slot_raw : last_slot;
+                const int2 sv = *reinterpret_cast<const int2 *>(wst + slot);
+                const int cx = sv.x & 0xffff, cy = (int)((uint32_t)sv.x >> 16);
+                uint32_t word = mode == MODE_STEP ? (uint32_t)sv.y : 0u;
+                int best;
+                float bestS, second;
+                const float curS = full_bs
+                    ? ue_channel_quad<NB, DIAG, true, GUARD>(c, a, bx4, by4, e, genv, u0 + slot, cx, cy, (uint32_t)epoch, word, best, bestS, second)
+                    : ue_channel_quad<NB, DIAG, false, GUARD>(c, a, bx4, by4, e, genv, u0 + slot, cx, cy, (uint32_t)epoch, word, best, bestS, second);
+                const bool guarded = GUARD && guard_needed(c, mode, best, (int)(word & 31), bestS, second, curS);
                 if (live && q == 0) {
-                    sum_sinr += (double)srvS;
+                    // (best server, its SINR, current-cell SINR, FP32_GUARDED: re-evaluate?) for the decision pass
+                    reinterpret_cast<int2 *>(wst + slot)[0].y = (int)(word | ((uint32_t)best << 23) | (guarded ? HO_PENDING : 0u));
+                    reinterpret_cast<int2 *>(wst + slot)[1] = make_int2(__float_as_int(bestS), __float_as_int(curS));
+                }
+            }
+            __syncwarp();
+            // ---- (C) lane = UE: handover / outage decisions once per UE, per-UE outputs coalesced
+            if (liveA) {
+                const int4 sv = wst[lane];
+                const int cx = sv.x & 0xffff, cy = (int)((uint32_t)sv.x >> 16);
+                uint32_t word = (uint32_t)sv.y & 0x7fffffu;
+                if (GUARD && ((uint32_t)sv.y & HO_PENDING)) {
+                    // FP32_GUARDED: decision deferred to the guard phase; the handover word keeps its pre-step value + a mark
+                    const int slot = atomicAdd(&s.guard_n, 1);
+                    if (slot < GUARD_LIST) s.guard_ue[slot] = uA;
+                    stk(c.ho + iA, word | HO_PENDING, keep);
+                } else {
+                    const int best = ((uint32_t)sv.y >> 23) & 31;
+                    int new_out, did_ho;
+                    const float srvS = ho_decide<float>(c, mode, best, __int_as_float(sv.z), __int_as_float(sv.w), word, new_out, did_ho);
+                    acc_fix += __double2ll_rn((double)srvS * 4294967296.0);
                     cnt_out += new_out;
                     cnt_ho += did_ho;
                     const int srv = word & 31;
-                    stk(c.ho + i, word, keep);
-                    if (a.serving) a.serving[i] = (uint8_t)srv;
-                    if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = srvS;
-                    if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = ((1 + srv) * G + cell.x) * G + cell.y;
-                    if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
+                    const int lin = ((1 + srv) * G + cx) * G + cy;
+                    stk(c.ho + iA, word, keep);
+                    if (lin_arr) lin_arr[uA] = lin;
+                    if (a.serving) a.serving[iA] = (uint8_t)srv;
+                    if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[iA] = srvS;
+                    if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + uA] = lin;
+                    if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
                 }
             }
+            __syncwarp();                                              // the staging area is reused by the next chunk
         }
-        if (stage) {
-            // ---- (C) thread = UE again: handover / outage decisions once per UE, per-UE outputs coalesced
-            __syncthreads();
-            for (int u = tid; u < nUE; u += NT) {
-                const size_t i = (size_t)e * nUE + u;
-                const int4 sv = stage[u];
-                const short2 cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
-                uint32_t word = (uint32_t)sv.y & 0x7fffffu;
-                const int best = ((uint32_t)sv.y >> 23) & 31;
-                int new_out, did_ho;
-                float srvS;
-                if (GUARD && ((uint32_t)sv.y & HO_PENDING)) {
-                    // FP32_GUARDED: a warp re-evaluates this UE in float64 after the pass (phase D); the mark stays in
-                    // the staging word, which is how phase D finds the UEs if the list overflows
-                    const int slot = atomicAdd(&s.guard_n, 1);
-                    if (slot < GUARD_LIST) s.guard_ue[slot] = u;
-                    continue;
-                }
-                srvS = ho_decide<float>(c, mode, best, __int_as_float(sv.z), __int_as_float(sv.w), word, new_out, did_ho);
-                sum_sinr += (double)srvS;
-                cnt_out += new_out;
-                cnt_ho += did_ho;
-                const int srv = word & 31;
-                const int lin = ((1 + srv) * G + cell.x) * G + cell.y;
-                stk(c.ho + i, word, keep);
-                reinterpret_cast<int2 *>(stage + u)[0].y = (int)word;       // the count REDs after barrier 2 read (cell, serving)
-                if (a.serving) a.serving[i] = (uint8_t)srv;
-                if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = srvS;
-                if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = lin;
-                if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
-            }
-            if constexpr (GUARD) {
-                // ---- (D) FP32_GUARDED: the listed UEs, one warp per UE, lane = BS, float64 in the reference's order
-                __syncthreads();
-                const int n_g = s.guard_n;
-                const bool listed = n_g <= GUARD_LIST;                   // else: every warp scans its share of the UEs
-                for (int k = warp; k < (listed ? n_g : nUE); k += NW) {
-                    const int u = listed ? s.guard_ue[k] : k;
-                    const size_t i = (size_t)e * nUE + u;
-                    const int4 sv = stage[u];
-                    if (!listed && !((uint32_t)sv.y & HO_PENDING)) continue;
-                    const short2 cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
-                    uint32_t word = (uint32_t)sv.y & 0x7fffffu;
-                    double bS, cS;
-                    int bb, new_out, did_ho;
-                    ue_row_f64_warp(c, c.fading == FADE_INJECTED ? a.fading + i * nBS : nullptr, s.bsx, s.bsy, genv, u, cell.x,
-                                    cell.y, (uint32_t)epoch, (int)(word & 31), &bb, &bS, &cS);
-                    const double srvS = ho_decide<double>(c, mode, bb, bS, cS, word, new_out, did_ho);
-                    if (lane == 0) {
-                        // order-independent fixed-point sum: the list order is not deterministic, the result must be
-                        atomicAdd(reinterpret_cast<unsigned long long *>(&s.guard_sum), (unsigned long long)__double2ll_rn(srvS * 4294967296.0));
-                        cnt_out += new_out;
-                        cnt_ho += did_ho;
-                        const int srv = word & 31;
-                        const int lin = ((1 + srv) * G + cell.x) * G + cell.y;
-                        stk(c.ho + i, word, keep);
-                        reinterpret_cast<int2 *>(stage + u)[0].y = (int)word;
-                        if (a.serving) a.serving[i] = (uint8_t)srv;
-                        if (a.serving_sinr) reinterpret_cast<float *>(a.serving_sinr)[i] = (float)srvS;
-                        if (a.obs_idx) a.obs_idx[(size_t)e * (nUE + nBS) + u] = lin;
-                        if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
-                    }
-                }
-            }
-        }
+        sum_sinr = (double)acc_fix * (1.0 / 4294967296.0);             // multiples of 2^-32 below 2^20: every later sum is exact
     } else {
     for (int u = tid; u < nUE; u += NT) {
         const size_t i = (size_t)e * nUE + u;
@@ -1238,8 +1166,8 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     if (bulk_ok && warp == WARP_TMA) bulk_wait_all();                  // the zeros have landed
     __syncthreads();                                                   // barrier 2
 
-    if constexpr (GUARD && NB <= 4) {
-        // ---- guard phase (FP32_GUARDED, thread-per-UE mapping): the UEs whose fp32 row was within guard_db of a decision
+    if constexpr (GUARD) {
+        // ---- guard phase (FP32_GUARDED): the UEs whose fp32 row was within guard_db of a decision
         // boundary are re-evaluated in float64 now that the UE loop's registers are dead (the call costs the hot loop
         // nothing), one warp per UE with lane = BS: a lone thread walking the row's float64 log10 / pow chains would hold
         // its CTA for tens of microseconds.  CTA-uniform branch, taken by about 2 % of the CTAs at the default guard.
@@ -1269,6 +1197,9 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                     if (a.serving_sinr) stk(reinterpret_cast<float *>(a.serving_sinr) + i, (float)srvS, keep);
                     if (a.obs_idx) stk(a.obs_idx + (size_t)e * (nUE + nBS) + u, ((1 + srv) * G + cell.x) * G + cell.y, keep);
                     if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
+                    if constexpr (NB > 4) {
+                        if (a.cells_off >= 0) reinterpret_cast<int32_t *>(dyn_smem + a.cells_off)[u] = ((1 + srv) * G + cell.x) * G + cell.y;
+                    }
                 }
             }
             __syncthreads();
@@ -1277,22 +1208,19 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     if (warp == WARP_GRP && group_tick) mob_group_finish(c, s, e, genv, tick - 1, inj, lane);
     {
         // the dense observation gets its non-zero cells (UEs on the plane of their post-handover serving BS, BSs on
-        // plane 0); thread = UE, (cell, serving) from the staging area when there is one
-        const int4 *stage = (!F64 && NB > 4 && a.cells_off >= 0) ? reinterpret_cast<const int4 *>(dyn_smem + a.cells_off) : nullptr;
+        // plane 0); thread = UE, flat indices from shared memory when the env's UEs fit
+        const int32_t *lin_arr = (!F64 && NB > 4 && a.cells_off >= 0) ? reinterpret_cast<const int32_t *>(dyn_smem + a.cells_off) : nullptr;
         if (full_obs) {
             for (int u = tid; u < nUE; u += NT) {
-                const size_t i = (size_t)e * nUE + u;
-                short2 cell;
-                int srv;
-                if (stage) {
-                    const int2 sv = *reinterpret_cast<const int2 *>(stage + u);
-                    cell = make_short2((short)(sv.x & 0xffff), (short)((uint32_t)sv.x >> 16));
-                    srv = sv.y & 31;
-                } else {
-                    cell = ldk_cell(c.ue_cell, i, keep);
-                    srv = ldk(c.ho + i, keep) & 31;
+                long long lin;
+                if (lin_arr) lin = lin_arr[u];
+                else {
+                    const size_t i = (size_t)e * nUE + u;
+                    const short2 cell = ldk_cell(c.ue_cell, i, keep);
+                    const int srv = ldk(c.ho + i, keep) & 31;
+                    lin = (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y);
                 }
-                obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
+                obs_add(obs_env, lin, 1.f, n_cells, c.err_flags);
             }
         }
         if (full_obs && tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);

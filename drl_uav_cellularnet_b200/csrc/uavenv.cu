@@ -105,10 +105,9 @@ int plan_kernel(uavenv_t *h) {
     CU(h, cudaFuncGetAttributes(&fa, (const void *)h->kernel));
     /* the TMA path needs whole float4s per env and 32-bit byte offsets */
     h->tiles_ok = h->cfg.obs_mode == UAVENV_OBS_F32 && (n_cells & 3) == 0 && n_cells * 4 < 0x7fffffffLL;
-    /* fp32 kernels with more than 4 BSs stage every UE's (cell, handover word, serving SINR) in shared memory between
-     * the movement pass (thread = UE) and the channel pass (lane = 4 BSs of a UE); if it does not fit, HBM is the
-     * staging area */
-    int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 16 + 127) & ~(int64_t)127) : 0;
+    /* fp32 kernels with more than 4 BSs keep every UE's flat observation index in shared memory for the count REDs
+     * that follow the zero stream (4 bytes per UE); if the env's UEs do not fit, the cells are re-read from HBM */
+    int64_t cells_bytes = (!f64 && h->d.nBS > 4) ? (((int64_t)h->d.nUE * 4 + 127) & ~(int64_t)127) : 0;
     if (cells_bytes > 49152) cells_bytes = 0;
     /* Shared-memory budget per CTA for three resident CTAs per SM (what the fp32 kernels are compiled for and what
      * measured best: NOTES.md); the zero tile takes what the staging area leaves, in equal copies of <= TILE_BYTES. */
