@@ -80,6 +80,10 @@ struct DevCfg {
     float f_Pdb;            // 10 log10(P)
     float f_db_k;           // 10 log10(2):             10 log10(x) = f_db_k * log2(x)
     float f_N, f_sh_mean, f_sh_sd;
+    // folded constants of the 4-BSs-per-lane mapping (ue_channel_quad): squared distance in cells
+    float f_d2_min;         // (pl_dis / grid_width)^2: path loss applies when d2 > f_d2_min
+    float f_c1;             // ant_gain - eq_loss - pl_a - f_loss_k log2(grid_width^2) + 10 log10(P)
+    float f_c0;             // ant_gain - eq_loss + 10 log10(P)                (no path loss)
     // FP32_GUARDED: a UE whose fp32 SINR row is within guard_db (dB) of a decision boundary -- top-2 gap (argmax),
     // best - current - ho_thr (handover), serving SINR - out_thr (outage) -- is re-evaluated in float64 with the
     // reference operation order, so every decision equals the FP64_PARITY kernel's.  0 = off (FP32_FAST).
@@ -121,7 +125,7 @@ struct CallArgs {
     uint8_t *bs_digits;          // [E,nBS]
     int32_t *obs_idx;            // [E,nUE+nBS] flat indices of the observation's non-zero cells
     int tile_bytes;              // bytes of the zeroed shared-memory tile the TMA warp streams from (0: no TMA path)
-    int cells_off;               // byte offset of the UE-cell staging area in dynamic shared memory (-1: use HBM)
+    int cells_off;               // byte offset of the per-UE observation indices in dynamic shared memory (-1: re-read HBM)
 };
 
 struct EnvShared {
@@ -207,6 +211,19 @@ __device__ __forceinline__ short2 ldk_cell(const int16_t *cells, size_t i, uint6
 __device__ __forceinline__ void stk_cell(int16_t *cells, size_t i, short2 c, uint64_t pol) {
     stk(reinterpret_cast<uint32_t *>(cells) + i, (uint32_t)(uint16_t)c.x | ((uint32_t)(uint16_t)c.y << 16), pol);
 }
+
+// cp.async (LDGSTS) with an L2 eviction-priority hint: one lane's piece of the NEXT chunk's state goes from HBM / L2 to
+// shared memory while the warp works on the current chunk (the fp32 mapping for more than 4 BSs, env_kernel)
+__device__ __forceinline__ void cp_async16(void *sdst, const void *gsrc, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)),
+                 "l"(__cvta_generic_to_global(gsrc)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *sdst, const void *gsrc, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sdst)),
+                 "l"(__cvta_generic_to_global(gsrc)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
 // One tick of the reference_point_group generator (ue_mobility.py:453-523), split in three so that the step
@@ -609,9 +626,9 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
             if (b < nBS) {
                 const int dx = cx - s.bsx[b], dy = cy - s.bsy[b];
                 const float q = c.f_q_scale * (float)(dx * dx + dy * dy);
-                const float loss = q > c.f_q_min ? fmaf(c.f_loss_k, __log2f(q), c.f_loss_a) : 0.f;
+                const float loss = q > c.f_q_min ? fmaf(c.f_loss_k, mufu_lg2(q), c.f_loss_a) : 0.f;
                 gdb[b] = c.f_g0 - loss - fade[b];
-                p[b] = exp2f(fmaf(gdb[b], c.f_exp_k, c.f_log2P));
+                p[b] = mufu_ex2(fmaf(gdb[b], c.f_exp_k, c.f_log2P));
             }
         }
         float pre[NB], suf[NB];
@@ -632,7 +649,7 @@ __device__ __forceinline__ typename Real<F64>::T ue_channel_pass(const DevCfg &c
 #pragma unroll
                 for (int j = 0; j < NB; j++) if (j != b) interf += p[j];
             }
-            S[b] = b < nBS ? (gdb[b] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + interf) : -3.0e38f;
+            S[b] = b < nBS ? (gdb[b] + c.f_Pdb) - c.f_db_k * mufu_lg2(c.f_N + interf) : -3.0e38f;
         }
     }
     if constexpr (DIAG) {
@@ -692,20 +709,23 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
 #pragma unroll
         for (int k = 0; k < 4; k++) if (FULL || b0 + k < nBS) fade[k] = (float)a.fading[pair0 + b0 + k];
     }
-    float gdb[4], p[4];
+    // log-domain form with the constants folded on the host (DevCfg): with d2 the squared distance in cells,
+    //   gP = 10 log10(P g) = f_c1 - f_loss_k log2(d2) - fade   (f_c0 - fade where the reference applies no path loss),
+    //   p  = P g = 2^(gP f_exp_k),   S = gP - f_db_k log2(N + interference)
+    float gP[4], p[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        gdb[k] = 0.f; p[k] = 0.f;
+        gP[k] = 0.f; p[k] = 0.f;
         const int b = b0 + k;
         if (FULL || b < nBS) {
             const int dx = cx - bx4[k], dy = cy - by4[k];
-            const float qd = c.f_q_scale * (float)(dx * dx + dy * dy);
-            const float loss = qd > c.f_q_min ? fmaf(c.f_loss_k, __log2f(qd), c.f_loss_a) : 0.f;
-            gdb[k] = c.f_g0 - loss - fade[k];
-            p[k] = exp2f(fmaf(gdb[k], c.f_exp_k, c.f_log2P));
+            const float d2 = (float)(dx * dx + dy * dy);
+            const float base = d2 > c.f_d2_min ? fmaf(-c.f_loss_k, mufu_lg2(d2), c.f_c1) : c.f_c0;
+            gP[k] = base - fade[k];
+            p[k] = mufu_ex2(gP[k] * c.f_exp_k);
         }
     }
-    const float quad = (p[0] + p[1]) + (p[2] + p[3]);
+    const float s01 = p[0] + p[1], s23 = p[2] + p[3], quad = s01 + s23;
     // quad sums of the OTHER lanes of the group: an exclusive butterfly (log2(LPU) shuffles) -- at every level a lane
     // adds its partner's partial sum to `others` and to its own partial sum; only sums of positive terms, never a difference
     float others = 0.f, part = quad;
@@ -716,10 +736,10 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
         part += t;
     }
     // exclude-self sums inside the quad: (others + the other three)
-    const float i0 = others + ((p[1] + p[2]) + p[3]), i1 = others + ((p[0] + p[2]) + p[3]);
-    const float i2 = others + ((p[0] + p[1]) + p[3]), i3 = others + ((p[0] + p[1]) + p[2]);
-    float S0 = (gdb[0] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i0), S1 = (gdb[1] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i1);
-    float S2 = (gdb[2] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i2), S3 = (gdb[3] + c.f_Pdb) - c.f_db_k * __log2f(c.f_N + i3);
+    const float i0 = others + (p[1] + s23), i1 = others + (p[0] + s23);
+    const float i2 = others + (s01 + p[3]), i3 = others + (s01 + p[2]);
+    float S0 = fmaf(-c.f_db_k, mufu_lg2(c.f_N + i0), gP[0]), S1 = fmaf(-c.f_db_k, mufu_lg2(c.f_N + i1), gP[1]);
+    float S2 = fmaf(-c.f_db_k, mufu_lg2(c.f_N + i2), gP[2]), S3 = fmaf(-c.f_db_k, mufu_lg2(c.f_N + i3), gP[3]);
     if (!FULL) {
         if (b0 + 0 >= nBS) S0 = -3.0e38f;
         if (b0 + 1 >= nBS) S1 = -3.0e38f;
@@ -735,33 +755,22 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
                 if (a.fading_used) a.fading_used[pair0 + b0 + k] = fade[k];
             }
     }
-    // first maximum inside the quad, then a butterfly argmax over the group: ties to the lower BS index
-    // (np.argmax, channel.py:141)
-    int best = b0;
-    float bestS = S0, second = -3.0e38f;
+    // best server = the FIRST maximum (np.argmax, channel.py:141): the group's maximum by an fmax butterfly, then the
+    // lowest BS index that attains it by a min butterfly (cheaper than carrying (value, index) pairs with tie tests)
+    float bestS = fmaxf(fmaxf(S0, S1), fmaxf(S2, S3));
+#pragma unroll
+    for (int o = 1; o < LPU; o <<= 1) bestS = fmaxf(bestS, __shfl_xor_sync(0xffffffffu, bestS, o));
+    int best = S0 == bestS ? b0 : (S1 == bestS ? b0 + 1 : (S2 == bestS ? b0 + 2 : (S3 == bestS ? b0 + 3 : 255)));
+#pragma unroll
+    for (int o = 1; o < LPU; o <<= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    float second = -3.0e38f;
     if constexpr (GUARD) {
-        // FP32_GUARDED: the runner-up travels with the maximum (the top-2 gap decides whether the argmax can be trusted)
-        if (S1 > bestS) { second = bestS; bestS = S1; best = b0 + 1; } else second = fmaxf(second, S1);
-        if (S2 > bestS) { second = bestS; bestS = S2; best = b0 + 2; } else second = fmaxf(second, S2);
-        if (S3 > bestS) { second = bestS; bestS = S3; best = b0 + 3; } else second = fmaxf(second, S3);
+        // FP32_GUARDED: the runner-up (largest SINR of any OTHER BS): its gap to the maximum says whether the argmax can
+        // be trusted
+        second = fmaxf(fmaxf(b0 == best ? -3.0e38f : S0, b0 + 1 == best ? -3.0e38f : S1),
+                       fmaxf(b0 + 2 == best ? -3.0e38f : S2, b0 + 3 == best ? -3.0e38f : S3));
 #pragma unroll
-        for (int o = 1; o < LPU; o <<= 1) {
-            const float oS = __shfl_xor_sync(0xffffffffu, bestS, o);
-            const float o2 = __shfl_xor_sync(0xffffffffu, second, o);
-            const int oB = __shfl_xor_sync(0xffffffffu, best, o);
-            if (oS > bestS || (oS == bestS && oB < best)) { second = fmaxf(bestS, o2); bestS = oS; best = oB; }
-            else second = fmaxf(second, oS);
-        }
-    } else {
-        if (S1 > bestS) { bestS = S1; best = b0 + 1; }
-        if (S2 > bestS) { bestS = S2; best = b0 + 2; }
-        if (S3 > bestS) { bestS = S3; best = b0 + 3; }
-#pragma unroll
-        for (int o = 1; o < LPU; o <<= 1) {
-            const float oS = __shfl_xor_sync(0xffffffffu, bestS, o);
-            const int oB = __shfl_xor_sync(0xffffffffu, best, o);
-            if (oS > bestS || (oS == bestS && oB < best)) { bestS = oS; best = oB; }
-        }
+        for (int o = 1; o < LPU; o <<= 1) second = fmaxf(second, __shfl_xor_sync(0xffffffffu, second, o));
     }
     // SINR of the UE's current (pre-handover) cell lives on lane cur/4 of the group
     const int cur = word & 31, ks = cur & 3;
@@ -861,6 +870,12 @@ constexpr int NT_SMALL = UAVENV_NT_SMALL;
 #endif
 constexpr int min_blocks(int nb, bool f64, int nt) { return f64 ? 1 : (nb > 8 ? UAVENV_MINB_WIDE : (nt == NT_SMALL ? UAVENV_MINB_SMALL : UAVENV_MINB)); }
 
+// fp32 mapping for more than 4 BSs: per warp, double-buffered landing area of the next chunk's state (cp.async)
+template <int NW> struct ChunkPrefetch {
+    double2 xy[NW][2][32];
+    uint32_t cell[NW][2][32], word[NW][2][32];
+};
+
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
 //   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
 template <int NB, bool F64, int NT, bool DIAG, bool GUARD>
@@ -959,7 +974,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             }
             if (lane == 0) s.blocked = blocked;
         }
-        if (lane == 0) { s.ok = ok; s.guard_n = 0; s.guard_sum = 0; s.next_chunk = 0; }
+        if (lane == 0) { s.ok = ok; s.guard_n = 0; s.guard_sum = 0; s.next_chunk = NW; }
     }
     if (warp == WARP_GRP && group_tick && lane < c.nG) mob_group_load(s, group_row_load(c, e, lane), lane);
     // the state of this thread's first UE is requested before the barrier: its HBM / L2 latency overlaps the BS warp's
@@ -968,7 +983,32 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     uint32_t word_0 = 0u;
     double2 p_0 = make_double2(0.0, 0.0);
     double thu_0 = 0.0;
-    if (tid < nUE && !(NB > 4 && !F64)) {
+    constexpr bool CHUNKED = NB > 4 && !F64;                           // the warp-pipelined mapping below
+    __shared__ __align__(16) unsigned char pf_raw[CHUNKED ? sizeof(ChunkPrefetch<NW>) : 16];
+    ChunkPrefetch<NW> &pf = *reinterpret_cast<ChunkPrefetch<NW> *>(pf_raw);
+    const bool need_word = mode == MODE_STEP || incremental;
+    const int n_chunks = (nUE + 31) >> 5;
+    auto prefetch = [&](int ch, int buf) {
+        if constexpr (CHUNKED) {
+            const int u = (ch << 5) + lane;
+            if (ch < n_chunks && u < nUE) {
+                const size_t i = (size_t)e * nUE + u;
+                cp_async4(&pf.cell[warp][buf][lane], reinterpret_cast<const uint32_t *>(c.ue_cell) + i, keep);
+                if (need_word) cp_async4(&pf.word[warp][buf][lane], c.ho + i, keep);
+                if (group_tick) cp_async16(&pf.xy[warp][buf][lane], c.xy + i, keep);
+            }
+            cp_async_commit();
+        }
+    };
+    if constexpr (CHUNKED) {
+        prefetch(warp, 0);                                             // chunk `warp` is this warp's first
+        if (bulk_ok) {                                                 // the zero tile, by everyone; barrier 1 publishes it
+            float4 *z4 = reinterpret_cast<float4 *>(zero_tile);
+            for (int i = tid; i < (int)(tile_bytes / 16); i += NT) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            fence_proxy_async_smem();          // generic-proxy writes of the tile -> visible to the async proxy
+        }
+    }
+    if (tid < nUE && !CHUNKED) {
         const size_t i0 = (size_t)e * nUE + tid;
         cell_0 = ldk_cell(c.ue_cell, i0, keep);
         word_0 = ldk(c.ho + i0, keep);
@@ -976,6 +1016,11 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
     }
     __syncthreads();                                                   // barrier 1
     if (!s.ok) {                                                       // the env's state is left untouched
+        if constexpr (CHUNKED) {
+            cp_async_wait<0>();
+            if (bulk_ok && warp == WARP_TMA)                           // (its observation is zeroed, like on the other path)
+                issue_zero_stream(obs_env, zero_tile, tile_bytes, (uint32_t)n_cells * 4u, lane, c.err_flags);
+        }
         if (bulk_ok && warp == WARP_TMA) bulk_wait_read_all();         // the tile must outlive the copies' reads
         return;
     }
@@ -1003,19 +1048,17 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         int4 *wst = wstage_all + warp * 32;
         // flat observation index of every UE for the count REDs after barrier 2 (if the env's UEs fit; else HBM is re-read)
         int32_t *lin_arr = a.cells_off >= 0 ? reinterpret_cast<int32_t *>(dyn_smem + a.cells_off) : nullptr;
-        if (bulk_ok && warp == WARP_TMA) {
-            // The zero stream is issued only now: with tens of bulk copies per env the ISSUE can block on the TMA queue for
-            // tens of microseconds (three CTAs per SM share it), and before barrier 1 the whole CTA would wait for it.
-            float4 *z4 = reinterpret_cast<float4 *>(zero_tile);
-            for (int i = lane; i < (int)(tile_bytes / 16); i += 32) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            fence_proxy_async_smem();
-            __syncwarp();
-            issue_zero_stream(obs_env, zero_tile, tile_bytes, (uint32_t)n_cells * 4u, lane, c.err_flags);
-        }
+        // The zero stream (the tile was zeroed by all threads before barrier 1) is issued by the TMA warp only now, after
+        // barrier 1: every bulk-copy instruction waits until the SM's TMA queue accepts it, and with tens of copies per env
+        // and three CTAs per SM that adds up to 40 % of the issuing warp's life (ncu: 5 % of all stall samples sit behind
+        // the UBLKCP loop) -- nobody may wait for it at a barrier.  Spreading the copies over all warps, a few per chunk
+        // drawn, was measured and is worse (343 vs 308 us: every warp then pays the issue latency inside its pipeline);
+        // starting the stream later in the CTA's life so that the count REDs find the zeros still in L2 is worse too
+        // (340 / 350 / 382 us for a start after 0 / 70 / 100 % of the chunks): profiles/r2/NOTES.md.
+        if (bulk_ok && warp == WARP_TMA) issue_zero_stream(obs_env, zero_tile, tile_bytes, (uint32_t)n_cells * 4u, lane, c.err_flags);
         constexpr int LPU = NB / 4, UPW = 32 / LPU;
         const int q = lane & (LPU - 1);
         const bool full_bs = nBS == NB;
-        const bool need_word = mode == MODE_STEP || incremental;
         // this lane's four BS cells stay in registers for the whole call
         int bx4[4], by4[4];
 #pragma unroll
@@ -1023,13 +1066,21 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             const int b = min(4 * q + k, nBS - 1);
             bx4[k] = s.bsx[b]; by4[k] = s.bsy[b];
         }
-        const int n_chunks = (nUE + 31) >> 5;
         long long acc_fix = 0;                                         // serving SINR, 2^-32 dB units
-        for (;;) {
+        // The state of the warp's NEXT chunk (float position, cell, handover word: 24 bytes per UE) is fetched with
+        // cp.async into a double-buffered 768-byte area per warp while the current chunk is processed: under the
+        // observation stream an HBM read takes microseconds, and a quarter of all warp cycles waited for these loads.
+        auto grab = [&]() {
             int ch = 0;
             if (lane == 0) ch = atomicAdd(&s.next_chunk, 1);
-            ch = __shfl_sync(0xffffffffu, ch, 0);
+            return __shfl_sync(0xffffffffu, ch, 0);
+        };
+        int ch = warp, buf = 0;                                        // first chunk: static, requested before barrier 1
+        for (;;) {
             if (ch >= n_chunks) break;
+            const int ch_next = grab();
+            prefetch(ch_next, buf ^ 1);
+            cp_async_wait<1>();                                        // this chunk's state has arrived (own copies only)
             const int u0 = ch << 5, uA = u0 + lane;
             const bool liveA = uA < nUE;
             const size_t iA = (size_t)e * nUE + (liveA ? uA : 0);
@@ -1038,12 +1089,13 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 short2 cell = make_short2(0, 0);
                 uint32_t word0 = 0u;
                 if (liveA) {
-                    cell = ldk_cell(c.ue_cell, iA, keep);
-                    if (need_word) word0 = ldk(c.ho + iA, keep);
+                    const uint32_t cw = pf.cell[warp][buf][lane];
+                    cell = make_short2((short)(cw & 0xffffu), (short)(cw >> 16));
+                    if (need_word) word0 = pf.word[warp][buf][lane];
                     if (incremental)       // the cell of the previous step leaves its association plane
                         obs_add(obs_env, (long long)(((size_t)(1 + (word0 & 31)) * G + cell.x) * G + cell.y), -1.f, n_cells, c.err_flags);
                     if (group_tick) {
-                        const double2 p = ldk(c.xy + iA, keep);
+                        const double2 p = pf.xy[warp][buf][lane];
                         const double thu = inj ? ldk(c.th_u + iA, keep) : 0.0;
                         cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, uA, p.x, p.y, thu, keep);
                     } else if (tr) {
@@ -1107,7 +1159,10 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 }
             }
             __syncwarp();                                              // the staging area is reused by the next chunk
+            ch = ch_next;
+            buf ^= 1;
         }
+        cp_async_wait<0>();
         sum_sinr = (double)acc_fix * (1.0 / 4294967296.0);             // multiples of 2^-32 below 2^20: every later sum is exact
     } else {
     for (int u = tid; u < nUE; u += NT) {
@@ -1163,7 +1218,9 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         cnt_ho += __shfl_down_sync(0xffffffffu, cnt_ho, o);
     }
     if (lane == 0) { s.red_sinr[warp] = sum_sinr; s.red_out[warp] = cnt_out; s.red_ho[warp] = cnt_ho; }
+#ifndef UAVENV_EXP_NO_WAIT
     if (bulk_ok && warp == WARP_TMA) bulk_wait_all();                  // the zeros have landed
+#endif
     __syncthreads();                                                   // barrier 2
 
     if constexpr (GUARD) {
@@ -1220,7 +1277,9 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                     const int srv = ldk(c.ho + i, keep) & 31;
                     lin = (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y);
                 }
+#ifndef UAVENV_EXP_NO_RED
                 obs_add(obs_env, lin, 1.f, n_cells, c.err_flags);
+#endif
             }
         }
         if (full_obs && tid < nBS) obs_add(obs_env, (long long)((size_t)s.bsx[tid] * G + s.bsy[tid]), 1.f, n_cells, c.err_flags);
@@ -1307,13 +1366,13 @@ __global__ void __launch_bounds__(CTA_THREADS) coverage_kernel(const __grid_cons
             if (b == srv) g_srv = gain; else p_interf = __dadd_rn(p_interf, __dmul_rn(c.P, gain));
         } else {
             const float qd = c.f_q_scale * (float)(dx * dx + dy * dy);
-            const float loss = qd > c.f_q_min ? fmaf(c.f_loss_k, __log2f(qd), c.f_loss_a) : 0.f;
-            gain = exp2f(((c.f_g0 - loss) - fade) * c.f_exp_k);
+            const float loss = qd > c.f_q_min ? fmaf(c.f_loss_k, mufu_lg2(qd), c.f_loss_a) : 0.f;
+            gain = mufu_ex2(((c.f_g0 - loss) - fade) * c.f_exp_k);
             if (b == srv) g_srv = gain; else p_interf = fmaf((float)c.P, gain, p_interf);
         }
     }
     if constexpr (F64) *o = __dmul_rn(10.0, log10(__dmul_rn(c.P, g_srv) / __dadd_rn(c.N, p_interf)));
-    else *o = c.f_db_k * (__log2f((float)c.P * g_srv) - __log2f(c.f_N + p_interf));
+    else *o = c.f_db_k * (mufu_lg2((float)c.P * g_srv) - mufu_lg2(c.f_N + p_interf));
 }
 
 }  // namespace uavk

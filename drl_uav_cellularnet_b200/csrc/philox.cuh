@@ -72,14 +72,22 @@ __device__ __forceinline__ void normal4_f64(const Philox4 &p, double z[4]) {
     }
 }
 
-// fp32 / MUFU version of the same draw (lg2, rsq, sin, cos).  Differs from normal4_f64 by ~1e-6 absolute.
+// The bare special-function unit: MUFU.LG2 / EX2 / SQRT without the denormal-range guards that __log2f / exp2f / sqrtf
+// wrap around them (3-8 instructions and a branch per call: a sixth of the dense channel pass, profiles/r2/NOTES.md).
+// Every argument on the fp32 paths is a normal float (squared distances >= 1, powers >= the noise floor 8e-16 W,
+// uniforms >= 2^-33), so the guards never fire.
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// fp32 / MUFU version of the same draw (lg2, sqrt, sin, cos).  Differs from normal4_f64 by ~1e-6 absolute.
 __device__ __forceinline__ void normal4_f32(const Philox4 &p, float z[4]) {
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         // (w + 0.5) * 2^-32; the fp32 rounding of w can reach 2^32, giving u1 = 1 -> r = 0 (harmless)
         const float u1 = fmaf((float)p.w[2 * k], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
         const float u2 = fmaf((float)p.w[2 * k + 1], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-        const float r = sqrtf(-1.3862943611198906f * __log2f(u1));  // -2 ln u1 = -2 ln2 * log2 u1
+        const float r = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u1));   // -2 ln u1 = -2 ln2 * log2 u1
         float s, c;
         __sincosf(6.2831853071795865f * (u2 - 0.5f), &s, &c);     // angle in (-pi, pi); the half-turn shift
         z[2 * k] = -r * c;                                         // is undone by the sign flips

@@ -114,7 +114,9 @@ int plan_kernel(uavenv_t *h) {
     int sm_smem = 0;
     CU(h, cudaDeviceGetAttribute(&sm_smem, cudaDevAttrMaxSharedMemoryPerMultiprocessor, h->device));
     const int64_t fixed = (int64_t)fa.sharedSizeBytes + 1024;               /* static + per-CTA reservation */
-    int64_t budget = f64 ? dev_smem - fixed : sm_smem / 3 - fixed;
+    /* resident CTAs per SM the kernel is compiled for (env_kernels.cuh: min_blocks) */
+    const int target_ctas = (!f64 && h->d.nBS > 8) ? UAVENV_MINB_WIDE : 3;
+    int64_t budget = f64 ? dev_smem - fixed : sm_smem / target_ctas - fixed;
     if (budget > dev_smem - fixed) budget = dev_smem - fixed;
     int64_t tile = TILE_BYTES;
     if (const char *ev = getenv("UAVENV_TILE_BYTES")) { const long v = atol(ev); if (v >= 128 && v % 128 == 0) tile = v; }
@@ -299,6 +301,12 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
     d.f_Pdb = (float)(10.0 * log10(d.P));
     d.f_db_k = (float)(10.0 * log10(2.0));
     d.f_N = (float)d.N; d.f_sh_mean = (float)cfg->shadow_mean; d.f_sh_sd = (float)cfg->shadow_sd;
+    {
+        const double q_scale = cfg->grid_width * cfg->grid_width, loss_k = cfg->pl_b * 0.5 * log10(2.0), pdb = 10.0 * log10(d.P);
+        d.f_d2_min = (float)(cfg->pl_dis * cfg->pl_dis / q_scale);
+        d.f_c1 = (float)(cfg->ant_gain - cfg->eq_loss - cfg->pl_a - loss_k * log2(q_scale) + pdb);
+        d.f_c0 = (float)(cfg->ant_gain - cfg->eq_loss + pdb);
+    }
     d.guard_db = cfg->precision == UAVENV_PREC_FP32_GUARDED ? (float)cfg->guard_db : 0.f;
 
     const int64_t nu = (int64_t)E * nUE;

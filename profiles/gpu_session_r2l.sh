@@ -1,0 +1,7 @@
+set -x
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_api.py -m gpu -x -q -k "not sweep and not full_size" 2>&1 | tail -8 > gpurun_out/r2l_tests.log
+tail -3 gpurun_out/r2l_tests.log
+for p in fp32 fp32_guarded; do python bench.py --workload dense --precision $p --steps 200 --no-cpu-baseline --no-extras > gpurun_out/r2l_dense_$p.json 2>/dev/null; done
+python bench.py --workload dense --precision fp32 --obs none --steps 200 --no-cpu-baseline --no-extras > gpurun_out/r2l_dense_noobs.json 2>/dev/null
+UAVENV_SO=$PWD/drl_uav_cellularnet_b200/variants/minb4.so python bench.py --workload dense --precision fp32 --steps 200 --no-cpu-baseline --no-extras > gpurun_out/r2l_dense_minb4.json 2>/dev/null
+UAVENV_SO=$PWD/drl_uav_cellularnet_b200/variants/minb4.so python bench.py --workload dense --precision fp32 --obs none --steps 200 --no-cpu-baseline --no-extras > gpurun_out/r2l_dense_minb4_noobs.json 2>/dev/null
