@@ -126,6 +126,7 @@ struct CallArgs {
     int32_t *obs_idx;            // [E,nUE+nBS] flat indices of the observation's non-zero cells
     int tile_bytes;              // bytes of the zeroed shared-memory tile the TMA warp streams from (0: no TMA path)
     int cells_off;               // byte offset of the per-UE observation indices in dynamic shared memory (-1: re-read HBM)
+    int copies_per_turn;         // fp32, more than 4 BSs: bulk copies of the zero stream the TMA warp issues per chunk it draws
 };
 
 struct EnvShared {
@@ -255,7 +256,7 @@ __device__ __forceinline__ void mob_group_load(EnvShared &s, const GroupRow &r, 
 // arrived groups theta[k], fl[k], v[k]); null = Philox.  Returns the UE's integer cell.
 // x, y (and thu, the injected direction uniform) are the UE's stored state, loaded by the caller.
 __device__ __forceinline__ short2 mob_ue_move(const DevCfg &c, EnvShared &s, int e, uint32_t genv, int tick,
-                                              bool aggregating, const double *inj, int u, double x, double y,
+                                              bool aggregating, const double *inj, int u, int g, double x, double y,
                                               double thu, uint64_t keep) {
     const size_t i = (size_t)e * c.nUE + u;
     // direction drawn at the end of the previous tick (:508-510) or at init (:437-439)
@@ -270,7 +271,6 @@ __device__ __forceinline__ short2 mob_ue_move(const DevCfg &c, EnvShared &s, int
     sincos(U_(0.0, TWO_PI, tu), &sn, &cs);
     x = __dadd_rn(x, cs);                                               // :455 (velocity 1.0, :436)
     y = __dadd_rn(y, sn);                                               // :456
-    const int g = c.ue_group[u];
     const double gvx = __dmul_rn(s.gv[g], s.gcos[g]), gvy = __dmul_rn(s.gv[g], s.gsin[g]);
     if (aggregating) {                                                  // :461-470
         double sc, cc;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(CTA_THREADS) mob_init_kernel(const __grid_cons
         for (int u = tid; u < c.nUE; u += blockDim.x) {
             const size_t i = (size_t)e * c.nUE + u;
             const double2 p = c.xy[i];
-            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u, p.x, p.y, 0.0, keep);
+            const short2 cell = mob_ue_move(c, s, e, genv, t, agg != 0, nullptr, u, c.ue_group[u], p.x, p.y, 0.0, keep);
             if (t == warmup) reinterpret_cast<short2 *>(c.ue_cell)[(size_t)e * c.nUE + u] = cell;
         }
         mob_phase_advance(c, agg, deagg);
@@ -874,6 +874,7 @@ constexpr int min_blocks(int nb, bool f64, int nt) { return f64 ? 1 : (nb > 8 ? 
 template <int NW> struct ChunkPrefetch {
     double2 xy[NW][2][32];
     uint32_t cell[NW][2][32], word[NW][2][32];
+    uint8_t grp[NW][2][32];      // the UEs' group ids (ue_group is padded to whole chunks): lanes 0-7 fetch 4 bytes each
 };
 
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
@@ -997,6 +998,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 if (need_word) cp_async4(&pf.word[warp][buf][lane], c.ho + i, keep);
                 if (group_tick) cp_async16(&pf.xy[warp][buf][lane], c.xy + i, keep);
             }
+            if (ch < n_chunks && group_tick && lane < 8) cp_async4(&pf.grp[warp][buf][4 * lane], c.ue_group + (ch << 5) + 4 * lane, keep);
             cp_async_commit();
         }
     };
@@ -1055,7 +1057,20 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // drawn, was measured and is worse (343 vs 308 us: every warp then pays the issue latency inside its pipeline);
         // starting the stream later in the CTA's life so that the count REDs find the zeros still in L2 is worse too
         // (340 / 350 / 382 us for a start after 0 / 70 / 100 % of the chunks): profiles/r2/NOTES.md.
-        if (bulk_ok && warp == WARP_TMA) issue_zero_stream(obs_env, zero_tile, tile_bytes, (uint32_t)n_cells * 4u, lane, c.err_flags);
+        // The TMA warp therefore drips the copies out, `copies_per_turn` each time it draws a chunk, sized so that the
+        // stream is complete one turn before the warp's expected last chunk: the queue is nearly empty whenever it issues.
+        const uint32_t obs_bytes = (uint32_t)n_cells * 4u;
+        const int n_copies = (bulk_ok && warp == WARP_TMA) ? (int)((obs_bytes + tile_bytes - 1) / tile_bytes) : 0;
+        int copies_done = 0;
+        auto issue_copies = [&](int n) {
+            const int k = copies_done + lane;
+            if (lane < n && k < n_copies) {
+                const uint32_t off = (uint32_t)k * tile_bytes;
+                bulk_store(reinterpret_cast<char *>(obs_env) + off, zero_tile, min(tile_bytes, obs_bytes - off));
+                bulk_commit();
+            }
+            copies_done += n;
+        };
         constexpr int LPU = NB / 4, UPW = 32 / LPU;
         const int q = lane & (LPU - 1);
         const bool full_bs = nBS == NB;
@@ -1077,10 +1092,12 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         };
         int ch = warp, buf = 0;                                        // first chunk: static, requested before barrier 1
         for (;;) {
+            if (copies_done < n_copies) issue_copies(a.copies_per_turn);
             if (ch >= n_chunks) break;
             const int ch_next = grab();
             prefetch(ch_next, buf ^ 1);
-            cp_async_wait<1>();                                        // this chunk's state has arrived (own copies only)
+            cp_async_wait<1>();                                        // this chunk's state has arrived (own copies) ...
+            __syncwarp();                                              // ... and the group ids, fetched by lanes 0-7
             const int u0 = ch << 5, uA = u0 + lane;
             const bool liveA = uA < nUE;
             const size_t iA = (size_t)e * nUE + (liveA ? uA : 0);
@@ -1097,7 +1114,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                     if (group_tick) {
                         const double2 p = pf.xy[warp][buf][lane];
                         const double thu = inj ? ldk(c.th_u + iA, keep) : 0.0;
-                        cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, uA, p.x, p.y, thu, keep);
+                        cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, uA, pf.grp[warp][buf][lane], p.x, p.y, thu, keep);
                     } else if (tr) {
                         const int2 xy = reinterpret_cast<const int2 *>(tr)[uA];
                         cell = make_short2((short)xy.x, (short)xy.y);
@@ -1163,6 +1180,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             buf ^= 1;
         }
         cp_async_wait<0>();
+        while (copies_done < n_copies) issue_copies(32);               // few chunks per warp: the rest of the stream
         sum_sinr = (double)acc_fix * (1.0 / 4294967296.0);             // multiples of 2^-32 below 2^20: every later sum is exact
     } else {
     for (int u = tid; u < nUE; u += NT) {
@@ -1177,7 +1195,7 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         if (group_tick) {
             const double2 p = first ? p_0 : ldk(c.xy + i, keep);
             const double thu = inj ? (first ? thu_0 : ldk(c.th_u + i, keep)) : 0.0;
-            cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, p.x, p.y, thu, keep);
+            cell = mob_ue_move(c, s, e, genv, tick, aggregating, inj, u, c.ue_group[u], p.x, p.y, thu, keep);
         } else if (tr) {
             const int2 xy = reinterpret_cast<const int2 *>(tr)[u];
             cell = make_short2((short)xy.x, (short)xy.y);

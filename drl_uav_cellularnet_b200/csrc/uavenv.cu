@@ -173,6 +173,18 @@ int run_env(uavenv_t *h, int mode, const uavenv_in *in, const uavenv_out *out, v
     /* the TMA warp streams the observation's zeros when the plan allows it and the buffer is float4-aligned */
     a.tile_bytes = (h->tiles_ok && a.obs && mode != MODE_CTOR && ((uintptr_t)a.obs & 15) == 0) ? h->tile_bytes : 0;
     a.cells_off = h->cells_off;
+    {   /* chunked mapping: the TMA warp issues this many bulk copies of the zero stream per chunk it draws, so that the
+         * stream is out one turn before its expected last chunk (UAVENV_STREAM_TURNS overrides the number of turns) */
+        static int turns_env = -1;
+        if (turns_env < 0) { const char *ev = getenv("UAVENV_STREAM_TURNS"); turns_env = ev ? atoi(ev) : 0; }
+        const int64_t n_chunks = (h->d.nUE + 31) / 32, per_warp = n_chunks / (h->threads / 32);
+        int64_t turns = turns_env > 0 ? turns_env : per_warp - 1;
+        if (turns < 1) turns = 1;
+        const int64_t total = (int64_t)(h->d.nBS + 1) * h->d.G * h->d.G * 4;
+        const int64_t n_copies = a.tile_bytes ? (total + a.tile_bytes - 1) / a.tile_bytes : 0;
+        const int64_t cpt = (n_copies + turns - 1) / turns;
+        a.copies_per_turn = (int)(cpt < 1 ? 1 : (cpt > 32 ? 32 : cpt));
+    }
     const env_kernel_fn k = (env_kernel_fn)((a.sinr_all || a.fading_used) ? h->kernel_diag : h->kernel);
     k<<<h->grid, h->threads, h->dyn_smem, (cudaStream_t)stream>>>(h->d, a);
     cudaError_t e = cudaGetLastError();
@@ -319,7 +331,8 @@ int uavenv_create(const uavenv_cfg *cfg, uavenv_t **out) {
         CU(h, cudaMemset(*f[i].dev, 0, (size_t)f[i].bytes));
     }
     CU(h, cudaMalloc(&h->init_bs, nBS * 4));
-    CU(h, cudaMalloc(&h->ue_group, nUE));
+    CU(h, cudaMalloc(&h->ue_group, (size_t)(nUE + 31) / 32 * 32));       /* whole chunks of 32: fetched 4 bytes per lane */
+    CU(h, cudaMemset(h->ue_group, 0, (size_t)(nUE + 31) / 32 * 32));
     CU(h, cudaMalloc(&h->err_flags, 16));                 /* [0] sticky flags, [8..16) FP32_GUARDED re-evaluation count */
     CU(h, cudaMemset(h->err_flags, 0, 16));
     CU(h, cudaMalloc(&h->h_action, (size_t)E * 8));
