@@ -254,9 +254,14 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
         push()
     ms_push = timed(push, 10)
     ms_ar = 0.0
-    if world > 1 and args.push != "p2p":
-        ms_ar = timed(lambda: torch.distributed.all_reduce(net.grad), 10)
+    if world > 1:                                # the NCCL all-reduce of the same 80.8 MB, for comparison in either mode
+        scratch = torch.zeros(net.n_flat, dtype=torch.float32, device=dev)
+        for _ in range(2):
+            torch.distributed.all_reduce(scratch)
+        ms_ar = timed(lambda: torch.distributed.all_reduce(scratch), 10)
+        del scratch
     ms_iter, ms_push, ms_ar = udist.max_over_ranks([ms_iter, ms_push, ms_ar], dev)
+    p2p_state = net.p2p_status() if args.push == "p2p" else None
     a_loss, c_loss = tr._graph_out
     finite = bool(torch.isfinite(a_loss)) and bool(torch.isfinite(c_loss))
     nbytes = net.n_flat * 4
@@ -267,8 +272,12 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
         "metric": "A3C env-steps/sec (rollout + update)", "unit": UNIT,
         "value": E * world * tr.T / (ms_iter * 1e-3), "ms_per_iteration": ms_iter, "iterations": iters,
         "envs_per_gpu": E, "rollout_steps": tr.T, "stream_groups": groups, "push": args.push if world > 1 else None,
-        "ms_push": ms_push, "ms_allreduce": ms_ar if ms_ar else None, "allreduce_bytes": nbytes if world > 1 else 0,
-        "allreduce_bus_gbs": (2.0 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9) if ms_ar else None,
+        "ms_push": ms_push, "push_note": "the push alone, back to back: p2p = uavnet_p2p_push (2 kernels, RMSProp and gradient zeroing "
+                                         "included); nccl = all_reduce + uavnet_rmsprop",
+        "p2p_pushes_completed": p2p_state[0] if p2p_state else None, "p2p_flag_wait_gave_up": p2p_state[1] if p2p_state else None,
+        "ms_allreduce_nccl": ms_ar if ms_ar else None, "allreduce_bytes": nbytes if world > 1 else 0,
+        "allreduce_bus_gbs_nccl": (2.0 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9) if ms_ar else None,
+        "push_link_gbs_per_direction": ((world - 1) / world * nbytes * 2 / (ms_push * 1e-3) / 1e9) if world > 1 else None,
         "params": net.n_params, "losses_finite": finite,
         "env_kernel_launches_per_iteration": int(env_launches_per_iter),
     }
@@ -297,7 +306,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 500)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="headline workload only (no other precisions / dense / A3C legs)")
-    ap.add_argument("--push", default="nccl", choices=["nccl", "p2p"], help="A3C gradient push at N > 1")
+    ap.add_argument("--push", default="p2p", choices=["nccl", "p2p"],
+                    help="A3C gradient push: p2p = one peer-memory kernel per rank (reduce-scatter + RMSProp + all-gather over NVLink, "
+                         "ranks ordered by flag words in peer memory); nccl = all-reduce of the flat gradient buffer + RMSProp pass")
     ap.add_argument("--spinup-ms", type=float, default=300.0, help="untimed spin-up before the warm-up steps (0 = none)")
     ap.add_argument("--guard-db", type=float, default=0.0, help="fp32_guarded: width of the re-evaluation band (0 = the library default)")
     ap.add_argument("--a3c-envs", type=int, default=8192)

@@ -75,7 +75,7 @@ SYMBOLS = [
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_step_host_state", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_guard_hits", "uavenv_get_cfg", "uavenv_last_error",
     "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
-    "uavnet_p2p_rmsprop", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record",
+    "uavnet_p2p_rmsprop", "uavnet_p2p_push", "uavnet_p2p_push_status", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record",
     "uavenv_launch_count", "uavenv_version", "uavenv_launch_plan",
 ]
 
@@ -126,6 +126,8 @@ def lib():
     L.uavnet_p2p_close.argtypes = [vp]
     L.uavnet_p2p_free.argtypes = [vp]
     L.uavnet_p2p_rmsprop.argtypes = [P(vp), P(vp), vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp]
+    L.uavnet_p2p_push.argtypes = [P(vp), P(vp), P(vp), vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp]
+    L.uavnet_p2p_push_status.argtypes = [vp, P(C.c_uint32), P(C.c_uint32)]
     L.uavnet_rmsprop.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, vp]
     L.uavnet_gemm.argtypes = [P(GemmDesc), vp]
     L.uavnet_gemm_check.argtypes = []

@@ -271,21 +271,23 @@ class ACNet:
     def enable_p2p(self):
         """Move the flat parameter / gradient buffers into IPC-shareable allocations, exchange their handles between
         the ranks' processes and map every peer's buffers (cudaIpcOpenMemHandle, peer access over NVLink).  From then
-        on ``apply_grads`` runs ``uavnet_p2p_rmsprop`` instead of all-reduce + ``uavnet_rmsprop``.  World size 1 (no
-        process group) takes the same code path with the local buffers only."""
+        on ``apply_grads`` is ``uavnet_p2p_push``: one peer-memory kernel per rank does reduce-scatter + RMSProp +
+        all-gather, ordered between the ranks by flag words in peer memory -- no NCCL call in the push, nothing for the
+        host to wait for, replayable in a CUDA graph.  World size 1 (no process group) takes the same code path with
+        the local buffers only."""
         import torch.distributed as dist
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank() if world > 1 else 0
         if world > 8:
-            raise ValueError("uavnet_p2p_rmsprop supports up to 8 ranks")
+            raise ValueError("uavnet_p2p_push supports up to 8 ranks")
         vp = C.c_void_p
         bufs, handles = [], []
-        for _ in range(2):                                            # 0: gradients, 1: parameters
+        for nbytes in (self.n_flat * 4, self.n_flat * 4, 256):        # 0: gradients, 1: parameters, 2: flag words (zeroed)
             ptr, hdl = vp(), (C.c_uint8 * 64)()
-            rc = self._lib.uavnet_p2p_alloc(self.n_flat * 4, C.byref(ptr), C.cast(hdl, vp))
+            rc = self._lib.uavnet_p2p_alloc(nbytes, C.byref(ptr), C.cast(hdl, vp))
             if rc:
                 raise RuntimeError("uavnet_p2p_alloc failed (%d)" % rc)
-            bufs.append(_ForeignCudaBuffer(ptr.value, self.n_flat))
+            bufs.append(_ForeignCudaBuffer(ptr.value, nbytes // 4))
             handles.append(bytes(hdl))
         grad = torch.as_tensor(bufs[0], device=self.device)
         flat = torch.as_tensor(bufs[1], device=self.device)
@@ -293,44 +295,74 @@ class ACNet:
         grad.copy_(self.grad)
         self.flat, self.grad = flat, grad
         self._bind_views()
-        gptrs, pptrs, opened = (vp * world)(), (vp * world)(), []
-        gptrs[rank], pptrs[rank] = bufs[0].ptr, bufs[1].ptr
+        gptrs, pptrs, fptrs, opened = (vp * world)(), (vp * world)(), (vp * world)(), []
+        gptrs[rank], pptrs[rank], fptrs[rank] = bufs[0].ptr, bufs[1].ptr, bufs[2].ptr
         if world > 1:
             every = [None] * world
             dist.all_gather_object(every, handles)
             for r in range(world):
                 if r == rank:
                     continue
-                for which, table in ((0, gptrs), (1, pptrs)):
+                for which, table in ((0, gptrs), (1, pptrs), (2, fptrs)):
                     peer = vp()
                     rc = self._lib.uavnet_p2p_open(C.cast(C.c_char_p(every[r][which]), vp), C.byref(peer))
                     if rc:
                         raise RuntimeError("uavnet_p2p_open failed (%d): no peer access to rank %d" % (rc, r))
                     table[r] = peer.value
                     opened.append(peer.value)
-            self._flag = torch.zeros(1, dtype=torch.float32, device=self.device)
-            dist.barrier()
-        self._p2p = {"bufs": bufs, "gptrs": gptrs, "pptrs": pptrs, "opened": opened, "rank": rank, "world": world}
+            torch.cuda.synchronize(self.device)
+            dist.barrier()                            # every rank has mapped every buffer before anyone pushes
+        self._p2p = {"bufs": bufs, "gptrs": gptrs, "pptrs": pptrs, "fptrs": fptrs, "opened": opened, "rank": rank, "world": world}
         return self
 
     def _apply_grads_p2p(self, lr: float):
-        import torch.distributed as dist
         q = self._p2p
-        if q["world"] > 1:
-            dist.all_reduce(self._flag)               # every rank's gradients are complete (stream-ordered)
-        rc = self._lib.uavnet_p2p_rmsprop(q["gptrs"], q["pptrs"], _ptr(self.ms), self.n_flat, q["rank"], q["world"], lr,
-                                          RMS_DECAY, RMS_EPS, self._stream())
+        rc = self._lib.uavnet_p2p_push(q["gptrs"], q["pptrs"], q["fptrs"], _ptr(self.ms), self.n_flat, q["rank"], q["world"], lr,
+                                       RMS_DECAY, RMS_EPS, self._stream())
         if rc:
-            raise RuntimeError("uavnet_p2p_rmsprop failed (%d)" % rc)
-        if q["world"] > 1:
-            dist.all_reduce(self._flag)               # every rank's slice has reached every copy of the parameters
-            self.grad.zero_()                         # ... and nobody reads this rank's gradients any more
+            raise RuntimeError("uavnet_p2p_push failed (%d)" % rc)
+
+    def p2p_status(self):
+        """(pushes completed on this rank, True if a flag wait ever gave up) -- synchronises"""
+        q = self._p2p
+        torch.cuda.synchronize(self.device)
+        e, t = C.c_uint32(0), C.c_uint32(0)
+        rc = self._lib.uavnet_p2p_push_status(C.c_void_p(q["bufs"][2].ptr), C.byref(e), C.byref(t))
+        if rc:
+            raise RuntimeError("uavnet_p2p_push_status failed (%d)" % rc)
+        return int(e.value), bool(t.value)
+
+    def _p2p_slice(self):
+        """[lo, hi) of the flat buffers this rank owns in the push (uavnet_p2p_push: ceil(n/4/world) float4s per rank)"""
+        q = self._p2p
+        n4 = self.n_flat // 4
+        per4 = (n4 + q["world"] - 1) // q["world"]
+        lo4 = q["rank"] * per4
+        return 4 * min(lo4, n4), 4 * min(lo4 + per4, n4), 4 * per4
 
     def close_p2p(self):
+        """Back to private buffers.  The push keeps the RMSProp slot `ms` only for the slice a rank owns: the slices are
+        gathered here so that every rank leaves with the complete optimiser state (and may continue with all-reduce +
+        uavnet_rmsprop)."""
         q = getattr(self, "_p2p", None)
         if not q:
             return
+        import torch.distributed as dist
         torch.cuda.synchronize(self.device)
+        if q["world"] > 1:
+            lo, hi, per = self._p2p_slice()
+            mine = torch.ones(per, dtype=torch.float32, device=self.device)
+            mine[:hi - lo].copy_(self.ms[lo:hi])
+            if dist.get_backend() == "nccl":
+                every = torch.empty(per * q["world"], dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(every, mine)
+            else:                                     # gloo (tests): through host memory
+                parts = [torch.empty(per, dtype=torch.float32) for _ in range(q["world"])]
+                dist.all_gather(parts, mine.cpu())
+                every = torch.cat(parts).to(self.device)
+            self.ms.copy_(every[:self.n_flat])
+            torch.cuda.synchronize(self.device)
+            dist.barrier()                            # nobody unmaps while a peer could still be in a push
         for ptr in q["opened"]:
             self._lib.uavnet_p2p_close(C.c_void_p(ptr))
         flat, grad = self.flat.clone(), self.grad.clone()
@@ -339,6 +371,7 @@ class ACNet:
         for b in q["bufs"]:
             self._lib.uavnet_p2p_free(C.c_void_p(b.ptr))
         self._p2p = None
+        self._pt_seen = None
 
     # ---- on-disk format of the reference (main.py:264-269,314; main_test.py:15-25) ---------------------------
     def actor_params(self):

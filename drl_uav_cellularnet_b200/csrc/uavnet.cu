@@ -210,6 +210,127 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_rmsprop_kernel(const __grid_c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same push without any host-side or NCCL ordering: the ranks synchronise through flag words in peer memory.
+//   flags (uint32, one 256-byte IPC buffer per rank):  [0..7] ready[r]  [8..15] done[r]  [16] block counter (push kernel)
+//                                                      [17] epoch of the last completed push  [18] block counter (finish)
+//                                                      [19] sticky: a wait gave up (peer missing)
+// Push number e = flags[17] + 1 on every rank (all ranks run the same number of pushes; the count lives in device
+// memory so that a CUDA graph replays it).  Protocol per rank:
+//   push kernel    block 0 writes ready[rank] = e into EVERY rank's flags (all kernels before it in the stream, i.e. the
+//                  whole backward pass, have completed);  every block waits until ready[r] >= e for all r (all ranks'
+//                  gradients are complete), then does its share of reduce-scatter + RMSProp + all-gather;  the last
+//                  block to finish writes done[rank] = e into every rank's flags.
+//   finish kernel  waits until done[r] >= e for all r (every rank's slice has reached this rank's parameters, nobody
+//                  reads this rank's gradients any more), zeroes the slices of the own gradient buffer that the push
+//                  kernel did not, and publishes flags[17] = e.
+// A rank never waits for something that depends on its own later progress, so the protocol cannot deadlock as long as
+// every rank launches both kernels; every wait is bounded all the same (about 2 s, then flags[19] is raised and the
+// kernel carries on): a missing peer must not hang the GPU.
+struct PeerPtrs2 {
+    float *g[UAVNET_MAX_PEERS];
+    float *p[UAVNET_MAX_PEERS];
+    unsigned int *f[UAVNET_MAX_PEERS];
+};
+enum { PF_READY = 0, PF_DONE = 8, PF_CNT_PUSH = 16, PF_EPOCH = 17, PF_CNT_FIN = 18, PF_TIMEOUT = 19 };
+
+__device__ __forceinline__ unsigned int ld_flag(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// all flags[base + r] >= e, r < world; bounded
+__device__ __forceinline__ void wait_flags(unsigned int *mine, int base, int world, unsigned int e) {
+    const long long t0 = clock64();
+    for (int r = 0; r < world; r++) {
+        while ((int)(ld_flag(mine + base + r) - e) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000LL) { mine[PF_TIMEOUT] = 1u; return; }
+        }
+    }
+}
+
+template <int W>   // W = world size known at compile time (all peer loads of an element in flight at once), 0 = any
+__global__ void __launch_bounds__(NET_THREADS) p2p_push_kernel(const __grid_constant__ PeerPtrs2 pp, float *__restrict__ ms,
+                                                               long long lo4, long long hi4, int rank, int world_rt, float lr,
+                                                               float decay, float eps, float gs) {
+    const int world = W > 0 ? W : world_rt;
+    unsigned int *mine = pp.f[rank];
+    __shared__ unsigned int e_sh;
+    if (threadIdx.x == 0) {
+        const unsigned int e = ld_flag(mine + PF_EPOCH) + 1u;
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (int r = 0; r < world; r++) st_flag(pp.f[(rank + r) % world] + PF_READY + rank, e);
+        }
+        wait_flags(mine, PF_READY, world, e);
+        e_sh = e;
+    }
+    __syncthreads();
+    const float od = 1.f - decay;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = lo4 + (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < hi4; i += (long long)gridDim.x * NET_THREADS) {
+        float4 acc = zero;
+        if constexpr (W > 0) {
+            // an NVLink peer load takes microseconds: all W of them are requested before the first is used
+            float4 v[W];
+#pragma unroll
+            for (int r = 0; r < W; r++) v[r] = __ldcs(reinterpret_cast<const float4 *>(pp.g[r]) + i);
+#pragma unroll
+            for (int r = 0; r < W; r++) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }   // fixed order
+        } else {
+            for (int r = 0; r < world; r++) {              // fixed summation order: bit-identical parameters on every rank
+                const float4 v = reinterpret_cast<const float4 *>(pp.g[r])[i];
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        acc.x *= gs; acc.y *= gs; acc.z *= gs; acc.w *= gs;
+        float4 mv = reinterpret_cast<float4 *>(ms)[i], pv = reinterpret_cast<const float4 *>(pp.p[rank])[i];
+        mv.x = decay * mv.x + od * acc.x * acc.x; mv.y = decay * mv.y + od * acc.y * acc.y;
+        mv.z = decay * mv.z + od * acc.z * acc.z; mv.w = decay * mv.w + od * acc.w * acc.w;
+        pv.x -= lr * acc.x / sqrtf(mv.x + eps); pv.y -= lr * acc.y / sqrtf(mv.y + eps);
+        pv.z -= lr * acc.z / sqrtf(mv.z + eps); pv.w -= lr * acc.w / sqrtf(mv.w + eps);
+        reinterpret_cast<float4 *>(ms)[i] = mv;
+        for (int j = 0; j < world; j++) reinterpret_cast<float4 *>(pp.p[(rank + j) % world])[i] = pv;
+        reinterpret_cast<float4 *>(pp.g[rank])[i] = zero;
+    }
+    __threadfence_system();                                 // this thread's peer stores are performed
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(mine + PF_CNT_PUSH, 1u) == gridDim.x - 1) {
+            mine[PF_CNT_PUSH] = 0u;
+            __threadfence_system();
+            for (int r = 0; r < world; r++) st_flag(pp.f[(rank + r) % world] + PF_DONE + rank, e_sh);
+        }
+    }
+}
+
+// waits for every rank's push kernel, zeroes the own gradient buffer outside [lo4, hi4) and publishes the epoch
+__global__ void __launch_bounds__(NET_THREADS) p2p_finish_kernel(unsigned int *mine, float4 *__restrict__ g4, long long n4,
+                                                                 long long lo4, long long hi4, int world) {
+    __shared__ unsigned int e_sh;
+    if (threadIdx.x == 0) {
+        const unsigned int e = ld_flag(mine + PF_EPOCH) + 1u;
+        wait_flags(mine, PF_DONE, world, e);
+        e_sh = e;
+    }
+    __syncthreads();
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * NET_THREADS)
+        if (i < lo4 || i >= hi4) g4[i] = zero;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(mine + PF_CNT_FIN, 1u) == gridDim.x - 1) {
+            mine[PF_CNT_FIN] = 0u;
+            st_flag(mine + PF_EPOCH, e_sh);
+        }
+    }
+}
+
 // softmax over the logits + np.random.choice(N_A, p=a_prob) (main.py:149,165-169), one warp per sample: the row is
 // read once into registers (PL > 0: PL = ceil(A / 32) slots per lane), exponentiated once, the probabilities are written
 // for the update, and the action is drawn by inverse CDF with one Philox uniform keyed by (seed, global row, call
@@ -475,6 +596,50 @@ int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_loca
     p2p_rmsprop_kernel<<<grid_for(hi4 - lo4, dev), NET_THREADS, 0, (cudaStream_t)stream>>>(pp, ms_local, lo4, hi4, rank, world, lr,
                                                                                      decay, eps, 1.0f / (float)world);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_p2p_push(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, int64_t n, int32_t rank,
+                    int32_t world, float lr, float decay, float eps, void *stream) {
+    if (!grads || !params || !flags || !ms_local || n < 4 || (n & 3) || world < 1 || world > UAVNET_MAX_PEERS || rank < 0 || rank >= world)
+        return UAVNET_EINVAL;
+    PeerPtrs2 pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int r = 0; r < world; r++) {
+        if (!grads[r] || !params[r] || !flags[r] || !aligned16(grads[r]) || !aligned16(params[r])) return UAVNET_EINVAL;
+        pp.g[r] = grads[r]; pp.p[r] = params[r]; pp.f[r] = flags[r];
+    }
+    const long long n4 = n >> 2, per4 = (n4 + world - 1) / world;
+    const long long lo4 = (long long)rank * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
+    const int dev = use_device_of(ms_local, stream);
+    const long long mine4 = hi4 > lo4 ? hi4 - lo4 : 1;
+    // every block of the push kernel spins on the flags first: keep the grid within about one wave
+    int grid = grid_for(mine4, dev);
+    const int one_wave = sm_count(dev) * 8;
+    if (grid > one_wave) grid = one_wave;
+    const long long hi = hi4 > lo4 ? hi4 : lo4;
+    const float gs = 1.0f / (float)world;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (world) {
+        case 1: p2p_push_kernel<1><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
+        case 2: p2p_push_kernel<2><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
+        case 4: p2p_push_kernel<4><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
+        case 8: p2p_push_kernel<8><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
+        default: p2p_push_kernel<0><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
+    }
+    if (cudaGetLastError() != cudaSuccess) return UAVNET_ECUDA;
+    int grid2 = grid_for(n4, dev);
+    if (grid2 > one_wave) grid2 = one_wave;
+    p2p_finish_kernel<<<grid2, NET_THREADS, 0, st>>>(flags[rank], (float4 *)grads[rank], n4, lo4, hi, world);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_p2p_push_status(const uint32_t *flags_own, uint32_t *epoch_out, uint32_t *timeout_out) {
+    if (!flags_own) return UAVNET_EINVAL;
+    uint32_t h[20];
+    if (cudaMemcpy(h, flags_own, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return UAVNET_ECUDA; }
+    if (epoch_out) *epoch_out = h[PF_EPOCH];
+    if (timeout_out) *timeout_out = h[PF_TIMEOUT];
+    return UAVNET_OK;
 }
 
 int uavnet_softmax_sample(const float *logits, int64_t M, int32_t A, uint64_t seed, uint32_t row_offset,

@@ -97,6 +97,18 @@ int uavnet_p2p_free(void *dev_ptr);
 int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_local, int64_t n, int32_t rank, int32_t world,
                        float lr, float decay, float eps, void *stream);
 
+/* The same push with the ranks ordered by flag words in peer memory instead of by the caller's collectives: no NCCL
+ * call, no host round trip, replayable inside a CUDA graph.  flags: HOST array of `world` device pointers to 256-byte
+ * zero-initialised IPC buffers (uavnet_p2p_alloc / uavnet_p2p_open), own buffer at index `rank`.  Two launches: the push
+ * kernel announces "my gradients are complete" to every rank, waits for everyone's announcement, does reduce-scatter +
+ * RMSProp + all-gather and announces "my slice is everywhere"; the finish kernel waits for everyone's second
+ * announcement and zeroes the rest of the own gradient buffer.  After it (stream order) the parameters of every rank
+ * are identical and the gradient buffer is zero.  Every rank must call it the same number of times.  Waits are bounded
+ * (about 2 s): uavnet_p2p_push_status reports the number of completed pushes and whether a wait ever gave up. */
+int uavnet_p2p_push(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, int64_t n, int32_t rank,
+                    int32_t world, float lr, float decay, float eps, void *stream);
+int uavnet_p2p_push_status(const uint32_t *flags_own, uint32_t *epoch_out, uint32_t *timeout_out);
+
 /* ---- the dense layers (main.py:148-149,152-153: 200->200 relu6, 200->625 softmax logits, 200->1) and their gradients
  * on the 5th-generation tensor cores: tcgen05.mma kind::tf32, fp32 accumulation in tensor memory, fused epilogue ----
  *   D[M,N] (+)= op(A)[M,K] . op(B)[K,N]

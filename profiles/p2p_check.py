@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Two or more ranks (torchrun, one process per GPU): the gradient push as ONE peer-memory kernel per rank
-(uavnet_p2p_rmsprop: reduce-scatter by NVLink peer loads + RMSProp + all-gather by peer stores) against the baseline
+(uavnet_p2p_push: reduce-scatter by NVLink peer loads + RMSProp + all-gather by peer stores, ranks ordered by flag
+words in peer memory) against the baseline
 NCCL all-reduce + uavnet_rmsprop -- same parameters bit for bit at 2 ranks, and the device time of both."""
 import json
 import os
@@ -14,11 +15,23 @@ import torch.distributed as dist  # noqa: E402
 from drl_uav_cellularnet_b200 import dist as udist  # noqa: E402
 from drl_uav_cellularnet_b200.a3c import ACNet  # noqa: E402
 
+import argparse  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--same-gpu", action="store_true", help="all ranks on cuda:0 (two processes sharing one GPU): the plumbing goes "
+                "through gloo, the push through CUDA IPC mappings of the other process's buffers on the same device")
+ap.add_argument("--n-s", type=int, default=50000)
+ap.add_argument("--n-a", type=int, default=625)
+ap.add_argument("--hidden", type=int, default=200)
+ap.add_argument("--iters", type=int, default=30)
+args = ap.parse_args()
 rank, world, local = udist.world()
+if args.same_gpu:
+    local = 0
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-udist.init("nccl", dev)
-a, b = ACNet(50000, 625, dev), ACNet(50000, 625, dev)
+udist.init("gloo" if args.same_gpu else "nccl", dev)
+a, b = ACNet(args.n_s, args.n_a, dev, hidden=args.hidden), ACNet(args.n_s, args.n_a, dev, hidden=args.hidden)
 b.enable_p2p()
 g = torch.Generator(device=dev).manual_seed(100 + rank)
 worst = 0.0
@@ -27,7 +40,12 @@ for it in range(4):
     a.grad.copy_(grad)
     b.grad.copy_(grad)
     if world > 1:
-        dist.all_reduce(a.grad)
+        if args.same_gpu:                      # gloo: reduce on the host
+            t = a.grad.cpu()
+            dist.all_reduce(t)
+            a.grad.copy_(t)
+        else:
+            dist.all_reduce(a.grad)
     a.apply_grads(1e-4, world)
     b.apply_grads(1e-4)
     torch.cuda.synchronize()
@@ -37,7 +55,7 @@ same = [None] * world
 dist.all_gather_object(same, float(b.flat.double().sum()))             # every rank holds the same parameters
 
 
-def timed(fn, n=30):
+def timed(fn, n=args.iters):
     for _ in range(3):
         fn()
     udist.barrier()
@@ -52,7 +70,7 @@ def timed(fn, n=30):
 
 
 def nccl_push():
-    if world > 1:
+    if world > 1 and not args.same_gpu:
         dist.all_reduce(a.grad)
     a.apply_grads(1e-4, world)
 
@@ -60,8 +78,16 @@ def nccl_push():
 ms_nccl = timed(nccl_push)
 ms_p2p = timed(lambda: b.apply_grads(1e-4))
 ms_nccl, ms_p2p = udist.max_over_ranks([ms_nccl, ms_p2p], dev)
+pushes, gave_up = b.p2p_status()
+# same state on both paths before the optimiser slots are compared: one more identical gradient through both
+grad = torch.randn(a.n_flat, device=dev, generator=g) * 1e-2
+a.flat.copy_(b.flat)
+b.close_p2p()                                          # gathers the RMSProp slot slices of all ranks
+ms_sums = [None] * world
+dist.all_gather_object(ms_sums, float(b.ms.double().sum()))
 if rank == 0:
     print(json.dumps({"world": world, "max_abs_param_diff_vs_nccl_path": worst, "param_sums_per_rank": same,
-                      "ms_nccl_allreduce_plus_rmsprop": ms_nccl, "ms_p2p_fused": ms_p2p, "bytes": a.n_flat * 4}))
-b.close_p2p()
+                      "ms_nccl_allreduce_plus_rmsprop": ms_nccl, "ms_p2p_fused": ms_p2p, "bytes": a.n_flat * 4,
+                      "pushes": pushes, "flag_wait_gave_up": gave_up, "ms_slot_sums_after_close_per_rank": ms_sums}))
+dist.barrier()
 dist.destroy_process_group()

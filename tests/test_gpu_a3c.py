@@ -283,7 +283,7 @@ def test_evaluation_driver_writes_the_reference_files(pkg, tmp_path):
 
 
 def test_p2p_push_world_size_1_equals_rmsprop(pkg):
-    """The peer-memory push (uavnet_p2p_rmsprop) with a single rank is the plain RMSProp step: same parameters bit for
+    """The peer-memory push (uavnet_p2p_push) with a single rank is the plain RMSProp step: same parameters bit for
     bit, gradients zeroed, buffers living in IPC-shareable allocations wrapped as torch tensors."""
     from drl_uav_cellularnet_b200.a3c import ACNet
     a, b = ACNet(2000, 25, "cuda:0", hidden=8), ACNet(2000, 25, "cuda:0", hidden=8)
@@ -300,6 +300,7 @@ def test_p2p_push_world_size_1_equals_rmsprop(pkg):
         assert float(b.grad.abs().max()) == 0.0
     idx = _rand_idx(4, 6, 2000, 0)
     assert torch.equal(a.forward(idx)[0], b.forward(idx)[0])           # the views follow the new buffers
+    assert b.p2p_status() == (3, False)
     b.close_p2p()
     assert torch.equal(a.flat, b.flat)
 
@@ -322,6 +323,33 @@ def test_p2p_push_two_ranks_equals_nccl_path():
     d = json.loads(line)
     assert d["world"] == 2 and d["max_abs_param_diff_vs_nccl_path"] == 0.0
     assert d["param_sums_per_rank"][0] == d["param_sums_per_rank"][1]
+    assert not d["flag_wait_gave_up"] and d["pushes"] > 30
+    assert d["ms_slot_sums_after_close_per_rank"][0] == d["ms_slot_sums_after_close_per_rank"][1]
+
+
+def test_p2p_push_two_processes_on_one_gpu():
+    """The peer-memory push between two PROCESSES that share cuda:0 (runs on the single-GPU box): rendezvous and the
+    reference all-reduce through gloo, the push itself through CUDA IPC mappings of the other process's gradient /
+    parameter / flag buffers -- the flag protocol, the fixed summation order and the gathered optimiser slots are the
+    same code as between GPUs.  Parameters bit-identical to all-reduce + uavnet_rmsprop on both ranks, no flag wait
+    gave up, the RMSProp slots of both ranks agree after close_p2p()."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29579", os.path.join(root, "profiles", "p2p_check.py"), "--same-gpu", "--n-s", "20000", "--hidden", "64",
+           "--iters", "5"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+    assert d["world"] == 2 and d["max_abs_param_diff_vs_nccl_path"] == 0.0
+    assert d["param_sums_per_rank"][0] == d["param_sums_per_rank"][1]
+    assert not d["flag_wait_gave_up"] and d["pushes"] >= 9
+    assert d["ms_slot_sums_after_close_per_rank"][0] == d["ms_slot_sums_after_close_per_rank"][1]
 
 
 def test_softmax_sample_kernel_matches_inverse_cdf(pkg):
