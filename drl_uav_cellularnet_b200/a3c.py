@@ -155,8 +155,8 @@ class ACNet:
         prob = v = None
         if want in ("both", "actor"):
             h2a = self.actor_hidden(h1, None if out is None else out["h2a"])
-            logits = self._gemm(h2a, self.pt["Wa3"], b_trans=True, bias=p["ba3"])
-            prob = torch.softmax(logits, dim=1, out=None if out is None else out["prob"])
+            # softmax through uavnet_softmax_sample (probabilities only): the same kernel the rollout uses
+            prob, _ = self.sample_head(h2a, 0, 0, None, 0, prob_out=None if out is None else out["prob"], want_action=False)
             cache.update(h2a=h2a, prob=prob)
         if want in ("both", "critic"):
             h2c, v = self.critic_head(h1)
@@ -181,7 +181,7 @@ class ACNet:
 
     def sample_head(self, h2a: torch.Tensor, seed: int, row_offset: int, counter_dev: Optional[torch.Tensor], counter_add: int,
                     prob_out: Optional[torch.Tensor] = None, action_out: Optional[torch.Tensor] = None,
-                    logits_out: Optional[torch.Tensor] = None):
+                    logits_out: Optional[torch.Tensor] = None, want_action: bool = True):
         """logits = h2a @ Wa3 + ba3, then softmax + np.random.choice(p=a_prob) in one kernel (uavnet_softmax_sample,
         Philox keyed by (seed, row_offset + row, *counter_dev + counter_add)) -> (prob [M, N_A], action int64 [M])"""
         M = h2a.shape[0]
@@ -189,17 +189,22 @@ class ACNet:
         logits = self._gemm(h2a, self.pt["Wa3"], logits_out if logits_out is not None else self._buf("logits", (M, self.n_a)),
                             b_trans=True, bias=self.p["ba3"])
         prob = prob_out if prob_out is not None else torch.empty_like(logits)
-        action = action_out if action_out is not None else torch.empty(M, dtype=torch.int64, device=self.device)
+        action = None
+        if want_action:
+            action = action_out if action_out is not None else torch.empty(M, dtype=torch.int64, device=self.device)
         rc = self._lib.uavnet_softmax_sample(_ptr(logits), M, self.n_a, int(seed), int(row_offset), _ptr(counter_dev),
                                              int(counter_add), _ptr(prob), _ptr(action), self._stream())
         if rc:
             raise RuntimeError("uavnet_softmax_sample failed (%d)" % rc)
         return prob, action
 
-    def choose_action(self, idx: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
-        """np.random.choice(N_A, p=a_prob) per env (main.py:165-169) -> int64 [M]"""
-        prob, _, _ = self.forward(idx, "actor")
-        return torch.multinomial(prob, 1, generator=generator).squeeze(1)
+    def choose_action(self, idx: torch.Tensor, seed: int = 0, row_offset: int = 0) -> torch.Tensor:
+        """np.random.choice(N_A, p=a_prob) per env (main.py:165-169) -> int64 [M]: softmax + inverse-CDF draw in one kernel
+        (uavnet_softmax_sample), one Philox uniform per row keyed by (seed, row_offset + row, number of this call)"""
+        self._sync_transposed()
+        h2a = self.actor_hidden(self.first_layer(idx))
+        self._choose_calls = getattr(self, "_choose_calls", 0) + 1
+        return self.sample_head(h2a, seed, row_offset, None, self._choose_calls)[1]
 
     def greedy_action(self, idx: torch.Tensor) -> torch.Tensor:
         """tf.argmax(a_prob, 1) of the evaluation driver (main_test.py:68)"""

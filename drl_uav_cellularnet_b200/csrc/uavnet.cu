@@ -256,7 +256,7 @@ __device__ __forceinline__ void wait_flags(unsigned int *mine, int base, int wor
 template <int W>   // W = world size known at compile time (all peer loads of an element in flight at once), 0 = any
 __global__ void __launch_bounds__(NET_THREADS) p2p_push_kernel(const __grid_constant__ PeerPtrs2 pp, float *__restrict__ ms,
                                                                long long lo4, long long hi4, int rank, int world_rt, float lr,
-                                                               float decay, float eps, float gs) {
+                                                               float decay, float eps, float gs, int dbg) {
     const int world = W > 0 ? W : world_rt;
     unsigned int *mine = pp.f[rank];
     __shared__ unsigned int e_sh;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_push_kernel(const __grid_cons
             // an NVLink peer load takes microseconds: all W of them are requested before the first is used
             float4 v[W];
 #pragma unroll
-            for (int r = 0; r < W; r++) v[r] = __ldcs(reinterpret_cast<const float4 *>(pp.g[r]) + i);
+            for (int r = 0; r < W; r++) v[r] = __ldcs(reinterpret_cast<const float4 *>(pp.g[(dbg & 2) ? rank : r]) + i);
 #pragma unroll
             for (int r = 0; r < W; r++) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }   // fixed order
         } else {
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_push_kernel(const __grid_cons
         pv.x -= lr * acc.x / sqrtf(mv.x + eps); pv.y -= lr * acc.y / sqrtf(mv.y + eps);
         pv.z -= lr * acc.z / sqrtf(mv.z + eps); pv.w -= lr * acc.w / sqrtf(mv.w + eps);
         reinterpret_cast<float4 *>(ms)[i] = mv;
-        for (int j = 0; j < world; j++) reinterpret_cast<float4 *>(pp.p[(rank + j) % world])[i] = pv;
+        for (int j = 0; j < world; j++) reinterpret_cast<float4 *>(pp.p[(dbg & 1) ? rank : (rank + j) % world])[i] = pv;
         reinterpret_cast<float4 *>(pp.g[rank])[i] = zero;
     }
     __threadfence_system();                                 // this thread's peer stores are performed
@@ -612,19 +612,25 @@ int uavnet_p2p_push(float *const *grads, float *const *params, uint32_t *const *
     const long long lo4 = (long long)rank * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
     const int dev = use_device_of(ms_local, stream);
     const long long mine4 = hi4 > lo4 ? hi4 - lo4 : 1;
-    // every block of the push kernel spins on the flags first: keep the grid within about one wave
+    // Two blocks per SM: measured on 8 B200s (80.8 MB, profiles/r2/NOTES.md) 64 / 148 / 296 / 592 / 1184 / 2368 blocks take
+    // 0.336 / 0.321 / 0.316 / 0.360 / 0.387 / 0.401 ms -- NVLink likes few fat streams of peer loads and stores better than
+    // many thin ones.  (Every block also spins on the flags first, so the grid has to stay within a wave anyway.)
     int grid = grid_for(mine4, dev);
     const int one_wave = sm_count(dev) * 8;
-    if (grid > one_wave) grid = one_wave;
+    if (grid > 2 * sm_count(dev)) grid = 2 * sm_count(dev);
     const long long hi = hi4 > lo4 ? hi4 : lo4;
     const float gs = 1.0f / (float)world;
     cudaStream_t st = (cudaStream_t)stream;
+    // timing experiments only (results are wrong when set): bit 0 = no peer stores, bit 1 = no peer loads
+    static int dbg = -1;
+    if (dbg < 0) { const char *ev = getenv("UAVNET_P2P_DBG"); dbg = ev ? atoi(ev) : 0; }
+    if (const char *ev = getenv("UAVNET_P2P_GRID")) { const int gmax = atoi(ev); if (gmax > 0) grid = gmax; }
     switch (world) {
-        case 1: p2p_push_kernel<1><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
-        case 2: p2p_push_kernel<2><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
-        case 4: p2p_push_kernel<4><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
-        case 8: p2p_push_kernel<8><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
-        default: p2p_push_kernel<0><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs); break;
+        case 1: p2p_push_kernel<1><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        case 2: p2p_push_kernel<2><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        case 4: p2p_push_kernel<4><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        case 8: p2p_push_kernel<8><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        default: p2p_push_kernel<0><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
     }
     if (cudaGetLastError() != cudaSuccess) return UAVNET_ECUDA;
     int grid2 = grid_for(n4, dev);

@@ -78,8 +78,14 @@ def test_forward_matches_dense_reference(pkg):
     assert float((prob.double() - rp.detach()).abs().max()) < 1e-5
     assert float((v.double() - rv.detach().squeeze(1)).abs().max()) < 1e-4
     assert torch.equal(net.greedy_action(idx), prob.argmax(1))
-    a = net.choose_action(idx, torch.Generator(device="cuda").manual_seed(0))
+    a = net.choose_action(idx, seed=7)
     assert a.shape == (64,) and int(a.min()) >= 0 and int(a.max()) < 625
+    a2 = net.choose_action(idx, seed=7)                       # the call counter is part of the key: fresh draws
+    assert not torch.equal(a, a2)
+    # the draws follow the probabilities: with one action's logit pushed up every row picks it
+    with torch.no_grad():
+        net.p["ba3"][17] += 50.0
+    assert bool((net.choose_action(idx, seed=1) == 17).all())
 
 
 def test_gradients_match_autograd_of_the_reference_losses(pkg):
