@@ -286,6 +286,31 @@ def test_evaluation_driver_writes_the_reference_files(pkg, tmp_path):
         assert float(r[0]) == out["reward"][t]
         assert np.array_equal(info["ue_xy"][0].cpu().numpy(), out["ue_location"][t]) and np.array_equal(out["ue_location"][t], trace[t])
         assert np.allclose(out["reward"][t], max(out["decomposed_reward"][t].sum(), -1.0), rtol=0, atol=1e-12)
+    # ... and what the ORACLE gives (config[0]: main_test.py's loop on the C restatement of the reference): the oracle env
+    # replays the same trace with the same Philox fading; at every step the greedy action is recomputed in float64 from the
+    # oracle's own dense state (argmax of the MLP of main.py:147-149, main_test.py:68) and must be the action the driver took
+    # (unless the top-2 probabilities are within fp32 reach of each other), and the driver's recorded reward / SINR /
+    # outage / locations / per-BS actions must be the oracle's.
+    P = {k: v.double().cpu().numpy() for k, v in (("W1", net.p["W1"][:, :net.h]), ("b1", net.p["b1"][:net.h]), ("W2", net.p["Wa2"]),
+                                                   ("b2", net.p["ba2"]), ("W3", net.p["Wa3"]), ("b3", net.p["ba3"]))}
+    oenv = orc.OracleEnv(cfg, mobility=orc.MOB_TRACE, fading=orc.FADE_PHILOX, seed=4, env_id=0, trace=trace)
+    state = oenv.reset()
+    for t in range(31):
+        x = state.reshape(-1)                                             # np.ravel(s), main_test.py:54,100: [plane, x, y] C order
+        nz = np.nonzero(x)[0]
+        h = np.clip(x[nz] @ P["W1"][nz] + P["b1"], 0, 6)
+        h = np.clip(h @ P["W2"] + P["b2"], 0, 6)
+        logits = h @ P["W3"] + P["b3"]
+        top = np.sort(logits)[-2:]
+        taken = int(out["action"][t] @ np.array([125, 25, 5, 1]))
+        if top[1] - top[0] > 1e-4:
+            assert int(np.argmax(logits)) == taken, t
+        state, r, d, oi = oenv.step(taken)
+        assert abs(out["reward"][t] - r) <= 1e-9 * max(1.0, abs(r)), t
+        assert np.array_equal(out["ue_location"][t], oenv.ue_xy) and np.array_equal(out["bs_location"][t][:, :2], oenv.bs_xy), t
+        assert np.max(np.abs(out["sinr"][t] - oenv.current_BS_sinr)) < 1e-9, t
+        assert abs(out["outage_fraction"][t] - oi["n_out"] / 40.0) < 1e-15, t
+        assert out["action"][t].tolist() == [float(v) for v in oi["digits"]], t
 
 
 def test_p2p_push_world_size_1_equals_rmsprop(pkg):

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle.make_golden import state_checksum
+from oracle.make_golden import load_trace_10k, state_checksum
 
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
@@ -387,13 +387,16 @@ def test_dense_channel_matches_reference_fixture(pkg, golden_dir):
 _SWEEP_ORACLE = {}
 
 
-def _sweep_oracle(orc, E, T, seed):
-    """the C oracle's side of the config[4] sweep, computed once per session and shared by the precisions"""
+def _sweep_oracle(orc, E, T, seed, golden_dir):
+    """the C oracle's side of the config[4] sweep, computed once per session and shared by the precisions.  The trace is
+    ue_trace_10k regenerated from the REFERENCE's own generator (tests/golden/ue_trace_10k.npz, oracle/make_golden.py
+    trace10k: seed + SHA-256 inside; its first 2100 rows are the trace of the reference fixture)."""
     from concurrent.futures import ThreadPoolExecutor
     key = (E, T, seed)
     if key not in _SWEEP_ORACLE:
         cfg = orc.default_cfg()
-        trace = orc.make_trace(cfg, seed, 0xFFFF, T + 1)
+        trace = load_trace_10k(golden_dir).astype(np.int32)
+        assert trace.shape[0] >= T + 1
         acts = np.stack([np.random.RandomState(1000 + e).randint(0, 625, size=T) for e in range(E)], axis=1)   # [T, E]
         with ThreadPoolExecutor(os.cpu_count() or 4) as ex:
             outs = list(ex.map(lambda e: orc.replay_run(cfg, trace, seed, e, acts[:, e]), range(E)))
@@ -403,9 +406,9 @@ def _sweep_oracle(orc, E, T, seed):
 
 @pytest.mark.timeout(900)
 @pytest.mark.parametrize("precision", ["fp32_guarded", "fp64", "fp32"])
-def test_trace_replay_equivalence_sweep_config5(pkg, orc, precision):
+def test_trace_replay_equivalence_sweep_config5(pkg, orc, golden_dir, precision):
     """BASELINE config[4] ("trace-replay equivalence sweep"): 1024 independent read_trace envs x 10 000 step_test
-    calls over one regenerated 10k trace, env e driven by its own fixed action stream RandomState(1000+e) and its
+    calls over ue_trace_10k regenerated from the reference's generator, env e driven by its own fixed action stream RandomState(1000+e) and its
     own Philox fading stream, against the C oracle (float64; pinned to the reference by tests/golden).  4.1e8 UE-steps;
     MAXSTEP/done is ignored like main_test.py:70-103 ignores it.
       fp64, fp32_guarded (the mode bench.py measures): new-outage counts, handover counts and a hash of every UE's serving
@@ -414,7 +417,7 @@ def test_trace_replay_equivalence_sweep_config5(pkg, orc, precision):
       fp32 (no guard): how many envs ever leave the oracle's trajectory, and after how many UE-steps, is REPORTED --
         the measured decision-flip rate of a plain fp32 pass (SURVEY H2 predicted about 4e-6 per UE-step)."""
     E, T, seed = 1024, 10000, 555
-    trace, acts, (o_out, o_ho, o_rew, o_hsh) = _sweep_oracle(orc, E, T, seed)
+    trace, acts, (o_out, o_ho, o_rew, o_hsh) = _sweep_oracle(orc, E, T, seed, golden_dir)
     env = pkg.BatchedMobiEnvironment(E, 4, 40, 100, "read_trace", trace=trace, fading="philox", precision=precision,
                                      obs="none", seed=seed)
     env.reset()
@@ -451,8 +454,12 @@ def test_trace_replay_equivalence_sweep_config5(pkg, orc, precision):
     assert np.array_equal(n_out, o_out)
     assert np.array_equal(n_ho, o_ho)
     if precision == "fp64":
-        rel = np.abs(rew - o_rew) / np.maximum(np.abs(o_rew), 1e-9)
-        assert rel.max() < 1e-9, rel.max()
+        # float64 against float64 (libm vs CUDA log10 / pow differ by ~1e-13 dB): 1e-9 relative, and absolute where the
+        # reward passes through zero (10 M samples: some land within 1e-7 of it)
+        err = np.abs(rew - o_rew)
+        assert float((err / np.maximum(np.abs(o_rew), 1.0)).max()) < 1e-9
+        rel = err / np.maximum(np.abs(o_rew), 1e-6)
+        assert rel.max() < 1e-8, rel.max()
     else:
         rep = _strict_reward_report(rew, o_rew, "sweep_config5_reward_fp32_guarded")
         assert rep["worst_rel_err_abs_reward_ge_0.1"] < REWARD_RTOL, rep

@@ -240,3 +240,15 @@ def test_free_running_statistics_match_reference(orc, golden_dir):
     for k, name in enumerate(g["columns"]):
         se = np.sqrt(ref[:, k].var(ddof=1) / len(ref) + got[:, k].var(ddof=1) / n_envs)
         assert abs(ref[:, k].mean() - got[:, k].mean()) < 4 * se, (str(name), ref[:, k].mean(), got[:, k].mean(), se)
+
+
+def test_ue_trace_10k_fixture_is_the_reference_generator_output(golden_dir):
+    """tests/golden/ue_trace_10k.npz (oracle/make_golden.py trace10k): 10 001 rows of the reference's group-reference
+    generator under the recorded seed; decodes to its SHA-256, stays on the grid, moves at most 3 cells per step, and its
+    first 2100 rows are the trace the reference fixture (ref_trace_replay.npz) was recorded on."""
+    from oracle.make_golden import load_trace_10k
+    tr = load_trace_10k(golden_dir)
+    assert tr.shape == (10001, 40, 2) and tr.min() >= 0 and tr.max() <= 99
+    assert np.abs(np.diff(tr, axis=0)).max() <= 3
+    g = np.load(os.path.join(golden_dir, "ref_trace_replay.npz"))
+    assert np.array_equal(tr[:g["trace"].shape[0]], g["trace"].astype(np.int64))
