@@ -75,7 +75,7 @@ SYMBOLS = [
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_step_host_state", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_guard_hits", "uavenv_get_cfg", "uavenv_last_error",
     "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
-    "uavnet_p2p_rmsprop", "uavnet_p2p_push", "uavnet_p2p_push_status", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record",
+    "uavnet_p2p_rmsprop", "uavnet_p2p_push", "uavnet_p2p_push_status", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record", "uavnet_critic_td", "uavnet_mean_rows",
     "uavenv_launch_count", "uavenv_version", "uavenv_launch_plan",
 ]
 
@@ -133,6 +133,8 @@ def lib():
     L.uavnet_gemm_check.argtypes = []
     L.uavnet_rank1_mask.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp, vp]
     L.uavnet_rollout_record.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp]
+    L.uavnet_critic_td.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp]
+    L.uavnet_mean_rows.argtypes = [vp, C.c_int64, vp, vp]
     L.uavnet_nstep_targets.argtypes = [vp, vp, vp, C.c_int32, C.c_int64, C.c_float, vp, vp]
     _lib = L
     return L

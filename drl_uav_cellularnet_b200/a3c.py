@@ -229,11 +229,15 @@ class ACNet:
             h1, h2a = c["h1"], c["h2a"]
         gemm = self._gemm
         h2c, v = self.critic_head(h1, self._buf("h2c", (M, H)), self._buf("v", (M,)))
-        td = (v_target - v).contiguous()
+        # td = v_target - v, dv = -2 td / M and c_loss = mean(td^2) in one launch (uavnet_critic_td)
+        td, dv1, loss2 = self._buf("td", (M,)), self._buf("dv", (M,)), self._buf("loss2", (2,))
+        vt = v_target.contiguous()
+        rc = self._lib.uavnet_critic_td(_ptr(vt), _ptr(v), M, _ptr(td), _ptr(dv1), _ptr(loss2), self._stream())
+        if rc:
+            raise RuntimeError("uavnet_critic_td failed (%d)" % rc)
+        dv = dv1.unsqueeze(1)                                              # [M, 1]
         # -- critic: every weight gradient is x^T @ dy accumulated into the flat gradient buffer, its bias gradient the
         # -- column sums of dy from the same pass; every data gradient is (dy @ W^T) * relu6'(layer output) --
-        c_loss = (td * td).mean()
-        dv = ((-2.0 / M) * td).unsqueeze(1)                                # [M, 1]
         gemm(h2c, dv, g["Wc3"], a_trans=True, accumulate=True, colsum=g["bc3"])
         dpre2c = self._buf("dpre2c", (M, H))                               # (dv (x) wc3) * relu6'(h2c)
         rc = self._lib.uavnet_rank1_mask(_ptr(dv), _ptr(p["Wc3"]), _ptr(h2c), M, H, _ptr(dpre2c), self._stream())
@@ -249,7 +253,9 @@ class ACNet:
                                              _ptr(loss_row), self._stream())
         if rc:
             raise RuntimeError("uavnet_actor_head_bwd failed (%d)" % rc)
-        a_loss = loss_row.mean()
+        rc = self._lib.uavnet_mean_rows(_ptr(loss_row), M, _ptr(loss2), self._stream())       # a_loss = mean of the rows
+        if rc:
+            raise RuntimeError("uavnet_mean_rows failed (%d)" % rc)
         gemm(h2a, dz, g["Wa3"], a_trans=True, accumulate=True, colsum=g["ba3"])
         dpre2a = gemm(dz, p["Wa3"], self._buf("dpre2a", (M, H)), b_trans=True, mask_src=h2a)
         gemm(h1[:, :H], dpre2a, g["Wa2"], a_trans=True, accumulate=True, colsum=g["ba2"])
@@ -258,7 +264,7 @@ class ACNet:
                                          self._stream())
         if rc:
             raise RuntimeError("uavnet_sparse_bwd failed (%d)" % rc)
-        return a_loss, c_loss
+        return loss2[0], loss2[1]                                          # (a_loss, c_loss): views of a persistent buffer
 
     # ---- the "push" (main.py:85-86,159-160): all-reduce + both RMSProp optimisers in one pass ---------------
     def apply_grads(self, lr: float = LR_A, world_size: int = 1):

@@ -420,6 +420,49 @@ __global__ void __launch_bounds__(NET_THREADS) rank1_mask_kernel(const float *__
     }
 }
 
+// Critic loss pieces of one update in one launch (main.py:64-66,80): td = v_target - v, dv = d(mean td^2)/dv = -2 td / M,
+// and the two loss scalars as sums of per-block partial sums: loss[0] += sum(a_loss_row) / M (rows from
+// actor_head_bwd_kernel of the PREVIOUS call are not used: a_rows may be null), loss[1] += sum(td^2) / M.  `loss` is
+// zeroed by the caller (2 floats).
+__global__ void __launch_bounds__(NET_THREADS) critic_td_kernel(const float *__restrict__ v_target, const float *__restrict__ v,
+                                                                long long M, float inv_m, float *__restrict__ td,
+                                                                float *__restrict__ dv, float *__restrict__ loss) {
+    __shared__ float part[NET_THREADS / 32];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < M; i += (long long)gridDim.x * NET_THREADS) {
+        const float t = v_target[i] - v[i];
+        td[i] = t;
+        dv[i] = -2.f * inv_m * t;
+        acc += t * t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < NET_THREADS / 32; w++) tot += part[w];
+        atomicAdd(loss + 1, tot * inv_m);
+    }
+}
+
+// loss[0] += sum(rows) / M  (the actor loss from the per-sample terms uavnet_actor_head_bwd wrote)
+__global__ void __launch_bounds__(NET_THREADS) mean_rows_kernel(const float *__restrict__ rows, long long M, float inv_m,
+                                                                float *__restrict__ out) {
+    __shared__ float part[NET_THREADS / 32];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < M; i += (long long)gridDim.x * NET_THREADS) acc += rows[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < NET_THREADS / 32; w++) tot += part[w];
+        atomicAdd(out, tot * inv_m);
+    }
+}
+
 // one rollout step's bookkeeping (main.py:199-211: ep_r += r; buffer_r.append(r)) in one launch
 __global__ void __launch_bounds__(NET_THREADS) rollout_record_kernel(const double *__restrict__ r, const uint8_t *__restrict__ done,
                                                                      long long E, float *__restrict__ r_out,
@@ -667,6 +710,26 @@ int uavnet_rank1_mask(const float *dv, const float *w, const float *h, int64_t M
     const int dev = use_device_of(dv, stream);
     rank1_mask_kernel<<<grid_for(M * (H / 4), dev), NET_THREADS, 0, (cudaStream_t)stream>>>(dv, (const float4 *)w, (const float4 *)h, M,
                                                                                      H / 4, (float4 *)out);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_critic_td(const float *v_target, const float *v, int64_t M, float *td, float *dv, float *loss2, void *stream) {
+    if (!v_target || !v || !td || !dv || !loss2 || M < 1) return UAVNET_EINVAL;
+    const int dev = use_device_of(v, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(loss2, 0, 2 * sizeof(float), st) != cudaSuccess) { cudaGetLastError(); return UAVNET_ECUDA; }
+    int grid = grid_for(M, dev);
+    if (grid > 2 * sm_count(dev)) grid = 2 * sm_count(dev);
+    critic_td_kernel<<<grid, NET_THREADS, 0, st>>>(v_target, v, M, 1.0f / (float)M, td, dv, loss2);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_mean_rows(const float *rows, int64_t M, float *out_accum, void *stream) {
+    if (!rows || !out_accum || M < 1) return UAVNET_EINVAL;
+    const int dev = use_device_of(rows, stream);
+    int grid = grid_for(M, dev);
+    if (grid > 2 * sm_count(dev)) grid = 2 * sm_count(dev);
+    mean_rows_kernel<<<grid, NET_THREADS, 0, (cudaStream_t)stream>>>(rows, M, 1.0f / (float)M, out_accum);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 

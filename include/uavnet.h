@@ -58,6 +58,12 @@ int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *
  * float32 [M,H] contiguous, H a multiple of 4. */
 int uavnet_rank1_mask(const float *dv, const float *w, const float *h, int64_t M, int32_t H, float *out, void *stream);
 
+/* The critic's side of the losses in one launch (main.py:64-66): td[i] = v_target[i] - v[i] (the TD error both losses use),
+ * dv[i] = d(mean td^2)/dv[i] = -2 td[i] / M, loss2[1] = mean(td^2) = c_loss; loss2[0] is zeroed for uavnet_mean_rows.  loss2: 2 floats. */
+int uavnet_critic_td(const float *v_target, const float *v, int64_t M, float *td, float *dv, float *loss2, void *stream);
+/* *out_accum += mean(rows[0..M)): a_loss from the per-sample terms uavnet_actor_head_bwd writes (main.py:76) */
+int uavnet_mean_rows(const float *rows, int64_t M, float *out_accum, void *stream);
+
 /* Bookkeeping of one rollout step (main.py:199-211: ep_r += r, buffer_r.append(r)) for E envs in one launch:
  * reward_out[e] = (float) reward[e] (the env kernel's float64 reward), done_out[e] = done[e], ep_return[e] += reward[e];
  * where done[e], the finished episode's return goes to ep_finished[e] and ep_return[e] restarts at 0 (ep_r of

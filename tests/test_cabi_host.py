@@ -75,6 +75,8 @@ def test_entry_points_reject_bad_arguments_without_a_gpu(native):
     assert L.uavnet_rank1_mask(None, None, None, 1, 4, None, None) == -1
     assert L.uavnet_nstep_targets(None, None, None, 1, 1, 0.9, None, None) == -1
     assert L.uavnet_rollout_record(None, None, 1, None, None, None, None, None) == -1
+    assert L.uavnet_critic_td(None, None, 1, None, None, None, None) == -1
+    assert L.uavnet_mean_rows(None, 1, None, None) == -1
     d = native.GemmDesc()
     assert L.uavnet_gemm(C.byref(d), None) == -1                 # no operands
     assert L.uavnet_gemm_check() == 0                            # nothing launched: no device access
