@@ -68,6 +68,11 @@ class ACNet:
         if precision not in dense.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(dense.PRECISIONS))
         self.precision = precision
+        # first-layer weight gradient: "gather" (counting sort + per-row sums) or "scatter" (float REDs); measured in
+        # profiles/r2/NOTES.md section 5
+        import os
+        self.sparse_bwd = os.environ.get("UAVNET_SPARSE_BWD", "gather")
+        self.sparse_bwd_passes = int(os.environ.get("UAVNET_BWD_PASSES", "2"))
         self.ld_a = (self.n_a + 3) // 4 * 4          # rows of Wa3 / dz padded to 16 bytes (625 -> 628): vector staging
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -260,8 +265,16 @@ class ACNet:
         dpre2a = gemm(dz, p["Wa3"], self._buf("dpre2a", (M, H)), b_trans=True, mask_src=h2a)
         gemm(h1[:, :H], dpre2a, g["Wa2"], a_trans=True, accumulate=True, colsum=g["ba2"])
         gemm(dpre2a, p["Wa2"], dpre1[:, :H], b_trans=True, mask_src=h1[:, :H], out_colsum=g["b1"][:H])   # + first-layer bias gradient
-        rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
-                                         self._stream())
+        if self.sparse_bwd == "gather":
+            # rows bucketed by a counting sort, then one plain sum per row and column half (no float atomics)
+            nb = int(self._lib.uavnet_sparse_bwd_gather_workspace(M, idx.shape[1], self.n_s))
+            ws = self._buf("bwd_ws", (nb // 4,), torch.int32)
+            rc = self._lib.uavnet_sparse_bwd_gather(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]), _ptr(ws),
+                                                    self.sparse_bwd_passes if (2 * H // 4) % self.sparse_bwd_passes == 0 else 1,
+                                                    self._stream())
+        else:
+            rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
+                                             self._stream())
         if rc:
             raise RuntimeError("uavnet_sparse_bwd failed (%d)" % rc)
         return loss2[0], loss2[1]                                          # (a_loss, c_loss): views of a persistent buffer

@@ -70,6 +70,129 @@ __global__ void __launch_bounds__(NET_THREADS) sparse_bwd_kernel(const int32_t *
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// First-layer weight gradient, gather side: dW[r, :] += sum over the (sample, slot) pairs with idx[m, k] = r of dpre[m, :].
+// The scatter version above sends 360 M 16-byte REDs through the L2 atomic units (0.9 ms for a rollout batch of 81 920 x 44).
+// Here the pairs are first bucketed by row (a counting sort of the 3.6 M row indices: histogram, exclusive scan, scatter of
+// the sample numbers), then every row sums its samples' gradient vectors with plain loads -- the same access pattern as
+// sparse_fwd_kernel with the roles of weights and activations swapped -- and is written once.  The caller runs the sum per
+// column half so that the gathered operand (dpre[:, half], 65 MB for the rollout batch) stays L2-resident.
+__global__ void __launch_bounds__(NET_THREADS) row_hist_kernel(const int32_t *__restrict__ idx, long long n, int n_rows,
+                                                               int32_t *__restrict__ count) {
+    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * NET_THREADS) {
+        const int r = __ldg(idx + i);
+        if ((unsigned)r < (unsigned)n_rows) atomicAdd(count + r, 1);
+    }
+}
+
+// exclusive scan of count[0..n_rows) into cursor[0..n_rows) (the fill kernel's write positions); one CTA of 1024 threads walks
+// the array in tiles of 4096 (one coalesced int4 per thread): thread-local scan, warp scan by shuffles, the 32 warp totals
+// through shared memory, a running carry between tiles.  n_rows is padded to a multiple of 4 by the workspace layout.
+__global__ void __launch_bounds__(1024) row_scan_kernel(const int32_t *__restrict__ count, int n_rows, int32_t *__restrict__ cursor) {
+    __shared__ int32_t wtot[32];
+    __shared__ int32_t carry_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_sh = 0;
+    __syncthreads();
+    const int n4 = (n_rows + 3) >> 2;
+    for (int base = 0; base < n4; base += 1024) {
+        const int i4 = base + tid;
+        int4 c = make_int4(0, 0, 0, 0);
+        if (i4 < n4) c = reinterpret_cast<const int4 *>(count)[i4];
+        if (4 * i4 + 1 >= n_rows) c.y = 0;
+        if (4 * i4 + 2 >= n_rows) c.z = 0;
+        if (4 * i4 + 3 >= n_rows) c.w = 0;
+        if (4 * i4 >= n_rows) c.x = 0;
+        const int32_t mine = c.x + c.y + c.z + c.w;
+        int32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int32_t w = wtot[lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t up = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += up;
+            }
+            wtot[lane] = winc - w;                          // exclusive warp offsets
+        }
+        __syncthreads();
+        const int32_t carry = carry_sh;
+        int32_t ex = carry + wtot[warp] + inc - mine;       // exclusive prefix of this thread's first element
+        if (i4 < n4) {
+            int4 o;
+            o.x = ex; o.y = ex + c.x; o.z = o.y + c.y; o.w = o.z + c.z;
+            reinterpret_cast<int4 *>(cursor)[i4] = o;
+        }
+        __syncthreads();
+        if (tid == 1023) carry_sh = ex + mine;
+        __syncthreads();
+    }
+}
+
+// bucket fill: position = cursor[row]++; the sorted arrays hold the sample number and the row of every (sample, slot) pair
+__global__ void __launch_bounds__(NET_THREADS) row_fill_kernel(const int32_t *__restrict__ idx, long long n, int K, int n_rows,
+                                                               int32_t *__restrict__ cursor, int32_t *__restrict__ sample_of,
+                                                               int32_t *__restrict__ row_of) {
+    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < n; i += (long long)gridDim.x * NET_THREADS) {
+        const int r = __ldg(idx + i);
+        if ((unsigned)r < (unsigned)n_rows) {
+            const int pos = atomicAdd(cursor + r, 1);
+            sample_of[pos] = (int32_t)(i / K);
+            row_of[pos] = r;
+        }
+    }
+}
+
+// Work item = (slice of SLICE consecutive entries of the row-sorted pair list, float4 column of [c0_4, c0_4 + nc4)): the
+// thread adds up the gradient vectors of its entries and flushes the sum with one 16-byte RED whenever the row changes and at
+// the end of the slice.  Fixed-size slices keep the load balanced whatever the row histogram looks like -- in the aggregation
+// phases of the mobility model a few hundred cells hold most UEs, and a thread-per-row sum then serialises on them (measured:
+// 0.58 ms with spread-out UEs, 2.2 ms right after an aggregation phase) -- and there are ~60x fewer REDs than in the scatter.
+constexpr int BWD_SLICE = 64;
+__global__ void __launch_bounds__(NET_THREADS) sparse_bwd_gather_kernel(const int32_t *__restrict__ sample_of,
+                                                                        const int32_t *__restrict__ row_of, const int32_t *total_dev,
+                                                                        const float4 *__restrict__ dpre4, int H4, int c0_4, int nc4,
+                                                                        float4 *dW4) {
+    const int total = *total_dev;                           // pairs that landed in a bucket (= cursor of the last row after the fill)
+    const long long n_slices = (total + BWD_SLICE - 1) / BWD_SLICE, items = n_slices * nc4;
+    for (long long w = (long long)blockIdx.x * NET_THREADS + threadIdx.x; w < items; w += (long long)gridDim.x * NET_THREADS) {
+        const long long sl = w / nc4;
+        const int c4 = c0_4 + (int)(w - sl * nc4);
+        const int lo = (int)(sl * BWD_SLICE), hi = min(lo + BWD_SLICE, total);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int cur = __ldg(row_of + lo);
+        for (int j = lo; j < hi; j += 8) {
+            int r[8], m[8];
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int jj = min(j + q, hi - 1);
+                r[q] = __ldg(row_of + jj); m[q] = __ldg(sample_of + jj);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = __ldg(dpre4 + (size_t)m[q] * H4 + c4);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (j + q < hi) {
+                    if (r[q] != cur) {
+                        atomicAdd(dW4 + (size_t)cur * H4 + c4, acc);
+                        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        cur = r[q];
+                    }
+                    acc.x += v[q].x; acc.y += v[q].y; acc.z += v[q].z; acc.w += v[q].w;
+                }
+            }
+        }
+        atomicAdd(dW4 + (size_t)cur * H4 + c4, acc);
+    }
+}
+
 __global__ void __launch_bounds__(NET_THREADS) rmsprop_kernel(float *__restrict__ p, float *__restrict__ g, float *__restrict__ ms,
                                                               long long n, float lr, float decay, float eps, float gs, int zero_grad) {
     const long long n4 = n >> 2;
@@ -569,6 +692,36 @@ int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
     const int dev = use_device_of(idx, stream);
     sparse_bwd_kernel<<<grid_for(M * (H / 4), dev), NET_THREADS, 0, (cudaStream_t)stream>>>(idx, M, K, (const float4 *)dpre,
                                                                                     H / 4, (float4 *)dW);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int64_t uavnet_sparse_bwd_gather_workspace(int64_t M, int32_t K, int64_t n_rows) {
+    if (M < 1 || K < 1 || n_rows < 1) return 0;
+    // count[n_rows] | cursor[n_rows] | sample_of[M * K] | row_of[M * K], int32 each, 16-byte aligned pieces
+    auto pad = [](int64_t n) { return (n + 3) / 4 * 4; };
+    return 4 * (2 * pad(n_rows) + 2 * pad(M * K));
+}
+
+int uavnet_sparse_bwd_gather(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
+                             void *workspace, int32_t col_passes, void *stream) {
+    if (!idx || !dpre || !dW || !workspace || M < 1 || K < 1 || n_rows < 1 || n_rows > 0x7fffffffLL || M * K > 0x7fffffffLL || H < 4 ||
+        (H & 3) || !aligned16(dpre) || !aligned16(dW) || !aligned16(workspace) || col_passes < 1 || (H / 4) % col_passes != 0)
+        return UAVNET_EINVAL;
+    const int dev = use_device_of(idx, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto pad = [](int64_t n) { return (n + 3) / 4 * 4; };
+    int32_t *count = (int32_t *)workspace, *cursor = count + pad(n_rows), *sample_of = cursor + pad(n_rows), *row_of = sample_of + pad(M * K);
+    if (cudaMemsetAsync(count, 0, (size_t)pad(n_rows) * 4, st) != cudaSuccess) { cudaGetLastError(); return UAVNET_ECUDA; }
+    const long long n = M * K;
+    row_hist_kernel<<<grid_for(n, dev), NET_THREADS, 0, st>>>(idx, n, (int)n_rows, count);
+    row_scan_kernel<<<1, 1024, 0, st>>>(count, (int)n_rows, cursor);
+    row_fill_kernel<<<grid_for(n, dev), NET_THREADS, 0, st>>>(idx, n, K, (int)n_rows, cursor, sample_of, row_of);
+    // after the fill cursor[r] = end of row r's bucket: the last row's cursor is the number of bucketed pairs
+    const int H4 = H / 4, nc4 = H4 / col_passes;
+    const long long items = ((n + BWD_SLICE - 1) / BWD_SLICE) * nc4;
+    for (int p = 0; p < col_passes; p++)
+        sparse_bwd_gather_kernel<<<grid_for(items, dev), NET_THREADS, 0, st>>>(sample_of, row_of, cursor + (n_rows - 1), (const float4 *)dpre,
+                                                                          H4, p * nc4, nc4, (float4 *)dW);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 

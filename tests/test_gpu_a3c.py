@@ -383,6 +383,39 @@ def test_p2p_push_two_processes_on_one_gpu():
     assert d["ms_slot_sums_after_close_per_rank"][0] == d["ms_slot_sums_after_close_per_rank"][1]
 
 
+@pytest.mark.parametrize("M,K,R,H,passes", [(300, 44, 5000, 400, 2), (64, 7, 50, 16, 1), (2048, 44, 50000, 400, 4), (10, 3, 4, 8, 2)])
+def test_sparse_bwd_gather_equals_scatter_and_float64(pkg, M, K, R, H, passes):
+    """First-layer weight gradient, gather side (counting sort of the row indices + one plain sum per row) against the
+    scatter side (float REDs) and a float64 index_add: same result up to fp32 summation order, duplicates inside a sample
+    counted twice, rows nobody touches left alone (the buffer accumulates)."""
+    import ctypes as C
+    from drl_uav_cellularnet_b200 import _native as N
+    L = N.lib()
+    g = torch.Generator().manual_seed(M + K)
+    idx = torch.randint(0, R, (M, K), generator=g, dtype=torch.int32)
+    idx[:, 1] = idx[:, 0]                                                     # a duplicate in every sample
+    idx = idx.cuda()
+    dpre = torch.randn(M, H, generator=g).cuda()
+    dpre[dpre.abs() < 0.5] = 0.0                                              # relu6' zeros
+    base = torch.randn(R, H, generator=g).cuda()
+    ref = base.double()
+    ref.index_add_(0, idx.reshape(-1).long(), dpre.double().repeat_interleave(K, dim=0))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a, b = base.clone(), base.clone()
+    assert L.uavnet_sparse_bwd(C.c_void_p(idx.data_ptr()), M, K, R, C.c_void_p(dpre.data_ptr()), H, C.c_void_p(a.data_ptr()), st) == 0
+    nb = L.uavnet_sparse_bwd_gather_workspace(M, K, R)
+    ws = torch.empty(nb // 4, dtype=torch.int32, device="cuda")
+    assert L.uavnet_sparse_bwd_gather(C.c_void_p(idx.data_ptr()), M, K, R, C.c_void_p(dpre.data_ptr()), H, C.c_void_p(b.data_ptr()),
+                                      C.c_void_p(ws.data_ptr()), passes, st) == 0
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert float((a.double() - ref).abs().max()) < 1e-5 * scale
+    assert float((b.double() - ref).abs().max()) < 1e-5 * scale
+    untouched = torch.ones(R, dtype=torch.bool, device="cuda")
+    untouched[idx.reshape(-1).long()] = False
+    assert torch.equal(b[untouched], base[untouched])
+
+
 def test_softmax_sample_kernel_matches_inverse_cdf(pkg):
     """uavnet_softmax_sample: probabilities = torch.softmax (1e-6), and the action is exactly the inverse-CDF pick for the
     Philox uniform of (seed, row, counter) -- recomputed on the host with the oracle's Philox -- and the empirical
