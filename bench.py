@@ -281,7 +281,7 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
         "params": net.n_params, "losses_finite": finite,
         "env_kernel_launches_per_iteration": int(env_launches_per_iter),
     }
-    tr._graph = None                              # the captured NCCL work must be gone before the process group is
+    tr._graph = tr._graph_lean = None             # the captured NCCL work must be gone before the process group is
     del tr
     if args.push == "p2p":
         net.close_p2p()

@@ -490,6 +490,10 @@ class A3CTrainer:
         for e, sl in zip(self.envs, self.slices):
             e.bind_obs_idx(self.buf_idx[0][sl])
             e.reset()
+        # host-side lower bound on the steps until an env of handle g can be done (all envs were just reset)
+        self._until = [int(e.cfg.max_step) for e in self.envs]
+        self._stale = [False] * len(self.envs)
+        self._resets = None
         self.updates = 0
 
     def _rollout_step(self, g: int, t: int):
@@ -506,10 +510,27 @@ class A3CTrainer:
                                             net._stream())
         if rc:
             raise RuntimeError("uavnet_rollout_record failed (%d)" % rc)
-        env.reset(env_mask=env.done_u8)                                  # finished episodes restart (main.py:188-190)
+        # finished episodes restart (main.py:188-190).  The masked reset is a launch of E CTAs that all exit unless some env
+        # is done; the host knows a lower bound on the steps until that can happen (`_until`), so the launch is only made
+        # when an episode CAN end at this step -- 1 rollout in 200 at the reference's MAXSTEP = 2000, T = 10.
+        self._until[g] -= 1
+        if self._resets is True or (self._resets is None and self._until[g] <= 0):
+            env.reset(env_mask=env.done_u8)
+            self._stale[g] = True
 
-    def rollout(self):
+    def _resync_until(self):
+        """after a rollout that may have reset some envs: steps until the earliest possible `done` per handle (one small
+        device read per episode end)"""
+        for g, e in enumerate(self.envs):
+            if self._stale[g]:
+                self._until[g] = int((int(e.cfg.max_step) - e.step_n).min())
+                self._stale[g] = False
+
+    def rollout(self, resets=None):
+        """resets: None = the masked reset is launched only at steps where an episode can end (host-side bound); True /
+        False = always / never (what `capture` records into its two graphs)"""
         net = self.net
+        self._resets = resets
         net._sync_transposed()                                               # before the streams fork
         if len(self.envs) == 1:
             for t in range(self.T):
@@ -530,6 +551,8 @@ class A3CTrainer:
         self.buf_idx[0].copy_(self.buf_idx[self.T])                          # the next rollout starts where this one ended
         for e, sl in zip(self.envs, self.slices):
             e.bind_obs_idx(self.buf_idx[0][sl])
+        if resets is None and any(self._stale):
+            self._resync_until()
         return vt
 
     def update(self, v_target: torch.Tensor):
@@ -545,8 +568,8 @@ class A3CTrainer:
         self.updates += 1
         return a_loss, c_loss
 
-    def train_iteration(self):
-        return self.update(self.rollout())
+    def train_iteration(self, resets=None):
+        return self.update(self.rollout(resets))
 
     # ---- one CUDA graph per iteration: ~100 launches (env step, reset, dense products, softmax + sampling, ...) replayed
     # ---- without Python or launch latency between them
@@ -564,12 +587,27 @@ class A3CTrainer:
                 self.train_iteration()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # two graphs: the iteration with the masked resets after every step and the one without; the host picks per replay
+        # from its bound on the steps until an episode can end
+        until = list(self._until)
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
-            self._graph_out = self.train_iteration()
+            self._graph_out = self.train_iteration(resets=True)
+        self._graph_lean = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph_lean):
+            self._graph_out_lean = self.train_iteration(resets=False)
+        self._until = until                       # capturing runs nothing: the counters go back to where they were
+        self._stale = [False] * len(self.envs)
+        self._resets = None
         return self
 
     def train_iteration_graph(self):
         """Replay the captured iteration; returns the (a_loss, c_loss) tensors of the replay (static buffers)."""
+        if min(self._until) > self.T:             # no episode can end inside this rollout: the graph without reset launches
+            self._until = [u - self.T for u in self._until]
+            self._graph_lean.replay()
+            return self._graph_out_lean
         self._graph.replay()
+        self._stale = [True] * len(self.envs)
+        self._resync_until()
         return self._graph_out

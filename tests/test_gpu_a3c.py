@@ -313,6 +313,49 @@ def test_evaluation_driver_writes_the_reference_files(pkg, tmp_path):
         assert out["action"][t].tolist() == [float(v) for v in oi["digits"]], t
 
 
+def test_reset_launches_are_skipped_only_when_no_episode_can_end(pkg):
+    """The trainer launches the masked reset only at steps where an episode can end (host-side bound on step_n) -- eagerly and
+    through its two CUDA graphs -- and the envs still restart exactly when they are done: with MAXSTEP = 25 and rollouts of
+    10 steps, episodes end inside every third rollout; step counters, rewards and finished-episode returns equal those of a
+    trainer that launches the reset after every step."""
+    from drl_uav_cellularnet_b200.a3c import A3CTrainer, ACNet
+
+    def run(mode):
+        env = pkg.BatchedMobiEnvironment(32, 4, 40, 100, "group", seed=9, obs="none", max_step=25)
+        net = ACNet(env.observation_space_dim, env.action_space_dim, "cuda:0", hidden=16, precision="fp32")
+        tr = A3CTrainer(env, net, seed=3)
+        if mode == "graph":
+            tr.capture(warmup=1)
+        rows, launches0 = [], env.launch_count
+        for it in range(9):
+            if mode == "always":
+                tr.train_iteration(resets=True)
+            elif mode == "graph":
+                tr.train_iteration_graph()
+            else:
+                tr.train_iteration()
+            torch.cuda.synchronize()
+            rows.append((env.step_n.clone(), tr.buf_r.clone(), tr.buf_done.clone(), tr.ep_finished.clone(), net.flat.clone()))
+        return rows, env.launch_count - launches0
+
+    ref, n_ref = run("always")
+    for mode in ("auto", "graph"):
+        got, n = run(mode)
+        skip = 1 if mode == "graph" else 0                              # the graph run made one eager warm-up iteration first
+        for it in range(9 - skip):
+            a, b = got[it], ref[it + skip]
+            assert torch.equal(a[0], b[0]), (mode, it)                    # step counters: resets happened when due
+            assert torch.equal(a[2], b[2]), (mode, it)                    # ... and the done flags of the rollout
+            assert torch.equal(torch.isnan(a[3]), torch.isnan(b[3])), (mode, it)      # which envs have finished an episode
+            if it == 0 and skip == 0:
+                # same rollout and same update (the gradient sums are ordered by atomics: equal up to fp32 rounding; later
+                # iterations may sample different actions from parameters that differ in the last bit)
+                assert torch.equal(a[1], b[1]), mode
+                assert torch.allclose(a[4], b[4], rtol=0, atol=1e-6), mode
+        if mode == "auto":
+            assert n < n_ref                                             # and fewer launches were made
+
+
 def test_p2p_push_world_size_1_equals_rmsprop(pkg):
     """The peer-memory push (uavnet_p2p_push) with a single rank is the plain RMSProp step: same parameters bit for
     bit, gradients zeroed, buffers living in IPC-shareable allocations wrapped as torch tensors."""
