@@ -18,6 +18,9 @@ namespace uavk {
 
 constexpr int NET_THREADS = 256;
 
+// (-DUAVNET_BOUNDS_CHECK builds test every index against n_rows and raise bit 1 of the device error word that
+// uavnet_gemm_check reads; the production build trusts the env kernel's obs_idx.  The gather-side backward and its counting
+// sort ignore out-of-range indices in every build.)
 // One thread per (sample m, float4 column c4): consecutive threads read consecutive 16-byte pieces of the same weight
 // row (coalesced, rows come from L2 -- the 80 MB first-layer matrix is L2-resident on B200), the row indices are
 // warp-broadcast loads.  K is unrolled by 8 so that 8 independent row reads are in flight per thread.  (A warp-per-sample
@@ -25,7 +28,8 @@ constexpr int NET_THREADS = 256;
 // flight: 39.9 us against 35.4 us for 8192 x 44 rows x 1.6 kB -- the kernel wants the parallelism.)
 __global__ void __launch_bounds__(NET_THREADS) sparse_fwd_kernel(const int32_t *__restrict__ idx, long long M, int K,
                                                                       const float4 *__restrict__ W4, const float4 *__restrict__ b4,
-                                                                      int H4, float4 *__restrict__ out4, int relu6) {
+                                                                      int H4, float4 *__restrict__ out4, int relu6, int n_rows,
+                                                                      unsigned int *err) {
     const long long total = M * H4;
     for (long long w = (long long)blockIdx.x * NET_THREADS + threadIdx.x; w < total; w += (long long)gridDim.x * NET_THREADS) {
         const long long m = w / H4;
@@ -37,6 +41,10 @@ __global__ void __launch_bounds__(NET_THREADS) sparse_fwd_kernel(const int32_t *
             int r[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) r[j] = __ldg(row + k + j);
+#ifdef UAVNET_BOUNDS_CHECK
+#pragma unroll
+            for (int j = 0; j < 8; j++) if ((unsigned)r[j] >= (unsigned)n_rows) { if (err) atomicOr(err, 2u); r[j] = 0; }
+#endif
             float4 v[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) v[j] = __ldg(W4 + (size_t)r[j] * H4 + c4);
@@ -44,7 +52,11 @@ __global__ void __launch_bounds__(NET_THREADS) sparse_fwd_kernel(const int32_t *
             for (int j = 0; j < 8; j++) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
         }
         for (; k < K; k++) {
-            const float4 v = __ldg(W4 + (size_t)__ldg(row + k) * H4 + c4);
+            int rk = __ldg(row + k);
+#ifdef UAVNET_BOUNDS_CHECK
+            if ((unsigned)rk >= (unsigned)n_rows) { if (err) atomicOr(err, 2u); rk = 0; }
+#endif
+            const float4 v = __ldg(W4 + (size_t)rk * H4 + c4);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         if (relu6) {
@@ -660,6 +672,16 @@ int sm_count(int dev) {
     return d.n_sm;
 }
 
+// the device error word (bit 0: a uavnet_gemm CTA gave up on a barrier; bit 1: bounds-check build, index outside the table)
+unsigned int *ensure_err_word(int dev) {
+    DeviceState &d = g_dev[dev];
+    if (!d.gemm_err) {
+        if (cudaMalloc(&d.gemm_err, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); d.gemm_err = nullptr; return nullptr; }
+        cudaMemset(d.gemm_err, 0, sizeof(unsigned int));
+    }
+    return d.gemm_err;
+}
+
 int grid_for(long long items, int dev) {
     long long g = (items + NET_THREADS - 1) / NET_THREADS;
     const long long cap = (long long)sm_count(dev) * 8 * 4;   // a few waves of 8 CTAs per SM; the kernels are grid-stride
@@ -681,7 +703,13 @@ int uavnet_sparse_fwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
         return UAVNET_EINVAL;
     const int dev = use_device_of(idx, stream);
     sparse_fwd_kernel<<<grid_for(M * (H / 4), dev), NET_THREADS, 0, (cudaStream_t)stream>>>(
-        idx, M, K, (const float4 *)W, (const float4 *)b, H / 4, (float4 *)out, relu6);
+        idx, M, K, (const float4 *)W, (const float4 *)b, H / 4, (float4 *)out, relu6, (int)n_rows,
+#ifdef UAVNET_BOUNDS_CHECK
+        ensure_err_word(dev)
+#else
+        nullptr
+#endif
+    );
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
@@ -956,10 +984,17 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     g.D = d->D; g.ldd = d->ldd; g.M = d->M; g.N = d->N; g.K = d->K;
     g.bias = d->bias; g.relu6 = d->relu6; g.mask_src = d->mask_src; g.ld_mask = d->ld_mask; g.accumulate = d->accumulate;
     g.colsum = d->colsum; g.out_colsum = d->out_colsum; g.dot_w = d->dot_w; g.dot_b = d->dot_b; g.dot_out = d->dot_out;
-    // N tile: as few tiles as possible, each a multiple of 16 columns, at most 256
-    const int bn_max = 256;
+    static int bn_max_env = -1;                                              // tuning experiments only
+    if (bn_max_env < 0) { const char *e = getenv("UAVNET_GEMM_BN_MAX"); bn_max_env = e ? atoi(e) : 0; }
     const long long rows = d->M + (d->colsum ? 1 : 0);
     const long long tiles_m = (rows + tc::BM - 1) / tc::BM;
+    // N tile: up to 256 columns (one tile for N = 200, three of 208 for N = 625) -- except for products with many row tiles
+    // (the update's 81 920-row data gradients): there 112-column tiles measured 15 % faster on the 625-deep product (121 vs
+    // 142 us: three pipeline stages instead of two inside the same shared-memory budget, twice the CTAs to overlap
+    // epilogues with main loops).  The value-head epilogue needs the whole row in one tile.
+    int bn_max = 256;
+    if (tiles_m >= 2 * sm_count(dev) && !d->dot_out && !d->accumulate && d->N <= 256) bn_max = 112;
+    if (bn_max_env >= 16 && bn_max_env <= 256) bn_max = bn_max_env / 16 * 16;
     int tiles_n = (d->N + bn_max - 1) / bn_max;
     g.tiles_n = tiles_n;
     g.BN = (((d->N + tiles_n - 1) / tiles_n) + 15) / 16 * 16;
@@ -993,11 +1028,8 @@ int uavnet_gemm(const uavnet_gemm_desc *d, void *stream) {
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("UAVNET_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
     g.dbg = dbg;
-    if (!ds.gemm_err) {
-        if (cudaMalloc(&ds.gemm_err, sizeof(unsigned int)) != cudaSuccess) { cudaGetLastError(); ds.gemm_err = nullptr; return UAVNET_ECUDA; }
-        cudaMemset(ds.gemm_err, 0, sizeof(unsigned int));
-    }
-    g.err = ds.gemm_err;
+    g.err = ensure_err_word(dev);
+    if (!g.err) return UAVNET_ECUDA;
     // staging mode per operand: TMA boxes for row-major, 16-byte aligned operands (one MMA per k-step only: the hi/lo
     // split of 3xTF32 needs the data in registers), threads otherwise
     static int no_tma = -1;
