@@ -25,6 +25,8 @@ struct Field {
 
 }  // namespace
 
+#define UAVENV_ALIAS_CACHE 32
+
 struct uavenv {
     uavenv_cfg cfg;
     DevCfg d;
@@ -35,6 +37,10 @@ struct uavenv {
     void *xy, *th_u, *grp, *ctr, *bs_xy, *ue_cell, *ho, *init_bs, *ue_group, *trace, *err_flags;
     // step_host staging (device)
     void *h_action, *h_reward, *h_mean, *h_nout, *h_done, *h_idx;
+    /* step_host: host buffer -> device alias (NULL = pageable) */
+    const void *alias_host[UAVENV_ALIAS_CACHE];
+    void *alias_dev[UAVENV_ALIAS_CACHE];
+    int n_alias;
     Field fields[F_COUNT];
     bool ctor_done;
     // launch plan of the persistent step kernel
@@ -434,12 +440,22 @@ int uavenv_step(uavenv_t *h, const uavenv_in *in, const uavenv_out *out, void *s
     return run_env(h, MODE_STEP, in, out, stream);
 }
 
-/* device alias of a pinned (page-locked, mapped) host buffer, or NULL for pageable memory */
-static void *pinned_alias(const void *p) {
+/* device alias of a pinned (page-locked, mapped) host buffer, or NULL for pageable memory.  The answer is cached per
+ * handle (a hot loop passes the same few buffers every step and cudaPointerGetAttributes costs about a microsecond);
+ * a caller that unregisters or frees a pinned buffer and reuses its address as pageable memory must make a new handle. */
+static void *pinned_alias(uavenv_t *h, const void *p) {
     if (!p) return nullptr;
+    for (int i = 0; i < h->n_alias; i++)
+        if (h->alias_host[i] == p) return h->alias_dev[i];
     cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+    void *dev = nullptr;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) cudaGetLastError();
+    else if (at.type == cudaMemoryTypeHost) dev = at.devicePointer;
+    if (h->n_alias < UAVENV_ALIAS_CACHE) {
+        h->alias_host[h->n_alias] = p;
+        h->alias_dev[h->n_alias++] = dev;
+    }
+    return dev;
 }
 
 static int step_host_impl(uavenv_t *h, const int64_t *action_host, void *obs_dev, double *reward_host, uint8_t *done_host,
@@ -455,7 +471,7 @@ static int step_host_impl(uavenv_t *h, const int64_t *action_host, void *obs_dev
      * Pageable buffers go through device staging and cudaMemcpyAsync.  UAVENV_HOST_ACTION_COPY=1 forces the staged
      * copy for the actions (tuning). */
     static const bool force_copy = getenv("UAVENV_HOST_ACTION_COPY") != nullptr;
-    const void *act = force_copy ? nullptr : pinned_alias(action_host);
+    const void *act = force_copy ? nullptr : pinned_alias(h, action_host);
     if (!act) {
         CU(h, cudaMemcpyAsync(h->h_action, action_host, E * 8, cudaMemcpyHostToDevice, st));
         act = h->h_action;
@@ -463,8 +479,8 @@ static int step_host_impl(uavenv_t *h, const int64_t *action_host, void *obs_dev
     uavenv_in in;
     memset(&in, 0, sizeof(in));
     in.action = (const int64_t *)act;
-    void *rw = pinned_alias(reward_host), *dn = pinned_alias(done_host), *ms = pinned_alias(mean_sinr_host),
-         *no = pinned_alias(n_out_host);
+    void *rw = pinned_alias(h, reward_host), *dn = pinned_alias(h, done_host), *ms = pinned_alias(h, mean_sinr_host),
+         *no = pinned_alias(h, n_out_host);
     uavenv_out out;
     memset(&out, 0, sizeof(out));
     out.obs = obs_dev;

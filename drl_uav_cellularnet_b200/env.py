@@ -287,24 +287,28 @@ class BatchedMobiEnvironment:
         """uavenv_step_host: int64 [E] actions in (pinned) HOST memory in, reward/done/... in HOST memory out;
         the copies and the stream synchronisation are inside the call.  The dense observation stays on the device;
         obs_idx_host (int32 [E, nUE + nBS], uavenv_step_host_state) also returns the state to the host in sparse form."""
-        for t in (action_host, reward_host, done_host, mean_sinr_host, n_out_host):
-            if t is not None and (t.is_cuda or not t.is_contiguous() or t.numel() != self.n_envs):
-                raise ValueError("step_host takes contiguous host tensors of n_envs elements")
-        if obs_idx_host is not None and (obs_idx_host.is_cuda or not obs_idx_host.is_contiguous() or obs_idx_host.dtype != torch.int32
-                                         or obs_idx_host.numel() != self.n_envs * (self.nUE + self.nBS)):
-            raise ValueError("obs_idx_host must be a contiguous int32 host tensor of n_envs * (nUE + nBS) elements")
-        key = tuple(0 if t is None else t.data_ptr() for t in (action_host, reward_host, done_host, mean_sinr_host,
-                                                               n_out_host, obs_idx_host))
-        args = self._host_args.get(key)
-        if args is None:                      # ctypes argument objects are cached per buffer set (hot loop)
+        bufs = (action_host, reward_host, done_host, mean_sinr_host, n_out_host, obs_idx_host)
+        key = tuple(map(id, bufs))            # the entry keeps the tensors alive, so an id cannot be reused while it is cached
+        ent = self._host_args.get(key)
+        if ent is None:                       # validation and the ctypes argument objects: once per buffer set (hot loop)
+            for t in bufs[:5]:
+                if t is not None and (t.is_cuda or not t.is_contiguous() or t.numel() != self.n_envs):
+                    raise ValueError("step_host takes contiguous host tensors of n_envs elements")
+            if obs_idx_host is not None and (obs_idx_host.is_cuda or not obs_idx_host.is_contiguous() or obs_idx_host.dtype != torch.int32
+                                             or obs_idx_host.numel() != self.n_envs * (self.nUE + self.nBS)):
+                raise ValueError("obs_idx_host must be a contiguous int32 host tensor of n_envs * (nUE + nBS) elements")
             if len(self._host_args) > 64:
                 self._host_args.clear()
-            args = self._host_args[key] = (_ptr(action_host), _ptr(self.obs), _ptr(reward_host), _ptr(done_host),
-                                           _ptr(mean_sinr_host), _ptr(n_out_host), _ptr(obs_idx_host))
-        if obs_idx_host is None:
-            rc = self._lib.uavenv_step_host(self._h, *args[:6], self._stream())
-        else:
-            rc = self._lib.uavenv_step_host_state(self._h, *args, self._stream())
+            args = (_ptr(action_host), _ptr(self.obs), _ptr(reward_host), _ptr(done_host), _ptr(mean_sinr_host), _ptr(n_out_host))
+            fn = self._lib.uavenv_step_host if obs_idx_host is None else self._lib.uavenv_step_host_state
+            if obs_idx_host is not None:
+                args = args + (_ptr(obs_idx_host),)
+            ent = self._host_args[key] = (fn, args, bufs, tuple(None if t is None else t.data_ptr() for t in bufs))
+        fn, args, _, ptrs = ent
+        if action_host.data_ptr() != ptrs[0]:     # a cached tensor object was resized / re-pointed: start over
+            del self._host_args[key]
+            return self.step_host(action_host, reward_host, done_host, mean_sinr_host, n_out_host, obs_idx_host)
+        rc = fn(self._h, *args, self._stream())
         if rc:
             self._raise(rc, "step_host")
         return self.obs
