@@ -884,7 +884,9 @@ __global__ void __launch_bounds__(NT, min_blocks(NB, F64, NT))
 env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a) {
     using T = typename Real<F64>::T;
     constexpr int NW = NT / 32;
-    constexpr int WARP_TMA = NW - 1, WARP_GRP = NW >= 2 ? NW - 2 : 0, WARP_BS = NW >= 3 ? NW - 3 : 0;
+    // two-warp CTAs (no observation stream to issue): the group state is loaded by warp 1 while warp 0 decodes the action
+    // and moves the BSs
+    constexpr int WARP_TMA = NW - 1, WARP_GRP = NW == 2 ? 1 : (NW >= 2 ? NW - 2 : 0), WARP_BS = NW >= 3 ? NW - 3 : 0;
     static_assert(NW >= 1 && NW <= CTA_THREADS / 32, "CTA size");
     __shared__ EnvShared s;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -929,12 +931,25 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 if (cur < 0) { ok = 0; cur = 0; }
                 // lane b takes digit b = (action / n_act^(nBS-1-b)) mod n_act; more digits than BSs is an error
                 // (the reference fails at ue_mobility.py:334)
-                long long rem = cur;
                 int mine = 0;
-                for (int pos = nBS - 1; pos >= 0; pos--) {
-                    const int d = (int)(rem % c.n_act);
-                    rem /= c.n_act;
-                    if (pos == lane) mine = d;
+                long long rem = cur;
+                if (cur <= 0x7fffffffLL) {
+                    // the usual case (5^nBS fits 31 bits up to 13 BSs): 32-bit divisions -- the 64-bit ones are ~70-instruction
+                    // subroutines, and this serial decode sits in front of barrier 1 (a fifth of the small kernel's lifetime)
+                    unsigned int r32 = (unsigned int)cur;
+                    const unsigned int n_act = (unsigned int)c.n_act;
+                    for (int pos = nBS - 1; pos >= 0; pos--) {
+                        const unsigned int q = r32 / n_act;
+                        if (pos == lane) mine = (int)(r32 - q * n_act);
+                        r32 = q;
+                    }
+                    rem = r32;
+                } else {
+                    for (int pos = nBS - 1; pos >= 0; pos--) {
+                        const int d = (int)(rem % c.n_act);
+                        rem /= c.n_act;
+                        if (pos == lane) mine = d;
+                    }
                 }
                 if (rem != 0) ok = 0;
                 if (lane < nBS) digit = mine;
