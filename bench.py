@@ -222,7 +222,8 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
     envs = [BatchedMobiEnvironment(eg, 4, 40, GRID, "group", seed=2026, obs="none", env_offset=rank * E + g * eg,
                                    device=local_rank) for g in range(groups)]
     net = ACNet(envs[0].observation_space_dim, envs[0].action_space_dim, dev, precision=args.a3c_precision)
-    if args.push == "p2p":
+    use_p2p = args.push == "p2p" and world > 1      # one GPU: nothing to push, the plain RMSProp pass
+    if use_p2p:
         net.enable_p2p()
     tr = A3CTrainer(envs if groups > 1 else envs[0], net, seed=100 + rank)
 
@@ -247,7 +248,7 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
     ms_iter = timed(tr.train_iteration_graph, iters)
     # the push alone (eager): all-reduce of the flat gradient buffer + RMSProp, or the peer-memory kernel
     def push():
-        if world > 1 and args.push != "p2p":
+        if world > 1 and not use_p2p:
             torch.distributed.all_reduce(net.grad)
         net.apply_grads(1e-30, world)           # a step too small to move the parameters: the timing loop leaves the net alone
     for _ in range(2):
@@ -261,7 +262,7 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
         ms_ar = timed(lambda: torch.distributed.all_reduce(scratch), 10)
         del scratch
     ms_iter, ms_push, ms_ar = udist.max_over_ranks([ms_iter, ms_push, ms_ar], dev)
-    p2p_state = net.p2p_status() if args.push == "p2p" else None
+    p2p_state = net.p2p_status() if use_p2p else None
     a_loss, c_loss = tr._graph_out
     finite = bool(torch.isfinite(a_loss)) and bool(torch.isfinite(c_loss))
     nbytes = net.n_flat * 4
@@ -283,7 +284,7 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
     }
     tr._graph = tr._graph_lean = None             # the captured NCCL work must be gone before the process group is
     del tr
-    if args.push == "p2p":
+    if use_p2p:
         net.close_p2p()
     return out
 

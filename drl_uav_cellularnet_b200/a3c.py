@@ -18,6 +18,7 @@ What changes against the reference
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -70,7 +71,6 @@ class ACNet:
         self.precision = precision
         # first-layer weight gradient: "gather" (counting sort + per-row sums) or "scatter" (float REDs); measured in
         # profiles/r2/NOTES.md section 5
-        import os
         self.sparse_bwd = os.environ.get("UAVNET_SPARSE_BWD", "gather")
         self.sparse_bwd_passes = int(os.environ.get("UAVNET_BWD_PASSES", "2"))
         self.ld_a = (self.n_a + 3) // 4 * 4          # rows of Wa3 / dz padded to 16 bytes (625 -> 628): vector staging
