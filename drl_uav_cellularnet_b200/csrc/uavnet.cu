@@ -512,27 +512,63 @@ __global__ void __launch_bounds__(NET_THREADS) softmax_sample_kernel(const float
         double ua, ub;
         philox_uniform2(k0, k1, row0 + (uint32_t)m, 0u, seq, DOM_SAMPLE, ua, ub);
         const float target = (float)ua;                   // in [0, 1)
-        // chunks of 32 consecutive actions: warp-inclusive scan, first crossing wins
-        float carry = 0.f;
         int pick = -1;
-        auto chunk = [&](int base, float p) {
-            const int j = base + lane;
-            if (j < A && prob) prob[m * A + j] = p;
-            float inc = p;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float up = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += up;
-            }
-            const unsigned hit = __ballot_sync(0xffffffffu, j < A && carry + inc > target);
-            if (pick < 0 && hit) pick = base + __ffs(hit) - 1;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        };
         if constexpr (PL > 0) {
+            // probabilities out (coalesced), then a two-level inverse-CDF search over chunks of 32 consecutive actions: the
+            // chunk totals of all PL chunks by one butterfly (every lane ends up with all of them), a serial walk over the
+            // totals to the chunk the uniform falls into, and ONE warp-inclusive scan inside that chunk -- instead of a
+            // scan + ballot per chunk (the kernel was bound by those: 520 -> ~300 instructions per row)
 #pragma unroll
-            for (int k = 0; k < PL; k++) chunk(32 * k, zv[k] * inv);
+            for (int k = 0; k < PL; k++) {
+                const int j = lane + 32 * k;
+                if (j < A && prob) prob[m * A + j] = zv[k] * inv;
+            }
+            float T[PL];
+#pragma unroll
+            for (int k = 0; k < PL; k++) T[k] = zv[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < PL; k++) T[k] += __shfl_xor_sync(0xffffffffu, T[k], o);
+            }
+            const float thr = target * sum;                // compare unnormalised sums with u * sum
+            float carry = 0.f, carry_at = 0.f, val = 0.f;
+            int kst = -1;
+#pragma unroll
+            for (int k = 0; k < PL; k++) {
+                if (kst < 0 && carry + T[k] > thr) { kst = k; carry_at = carry; val = zv[k]; }
+                carry += T[k];
+            }
+            if (kst >= 0) {
+                float inc = val;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += up;
+                }
+                const int j = 32 * kst + lane;
+                const unsigned hit = __ballot_sync(0xffffffffu, j < A && carry_at + inc > thr);
+                // (the chunk total and the scan add the same 32 numbers in different orders: if rounding left no lane
+                // above the threshold, the chunk's last action is the pick)
+                pick = hit ? 32 * kst + __ffs(hit) - 1 : min(32 * kst + 31, A - 1);
+            }
         } else {
-            for (int base = 0; base < A; base += 32) chunk(base, base + lane < A ? expf(z[base + lane] - mx) * inv : 0.f);
+            // any A: chunks of 32 consecutive actions, a warp-inclusive scan per chunk, first crossing wins
+            float carry = 0.f;
+            for (int base = 0; base < A; base += 32) {
+                const int j = base + lane;
+                const float p = j < A ? expf(z[j] - mx) * inv : 0.f;
+                if (j < A && prob) prob[m * A + j] = p;
+                float inc = p;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float up = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += up;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, j < A && carry + inc > target);
+                if (pick < 0 && hit) pick = base + __ffs(hit) - 1;
+                carry += __shfl_sync(0xffffffffu, inc, 31);
+            }
         }
         if (pick < 0) pick = A - 1;                       // rounding: the cumulative sum ended just below u
         if (lane == 0 && action) action[m] = pick;
