@@ -74,7 +74,7 @@ SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_step_host_state", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_guard_hits", "uavenv_get_cfg", "uavenv_last_error",
-    "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_sparse_bwd_gather", "uavnet_sparse_bwd_gather_workspace", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
+    "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_sparse_bwd_gather", "uavnet_sparse_bwd_gather_workspace", "uavnet_sparse_bwd_gather_prepare", "uavnet_sparse_bwd_gather_apply", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
     "uavnet_p2p_rmsprop", "uavnet_p2p_push", "uavnet_p2p_push_status", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record", "uavnet_critic_td", "uavnet_mean_rows",
     "uavenv_launch_count", "uavenv_version", "uavenv_launch_plan",
 ]
@@ -120,6 +120,8 @@ def lib():
     L.uavnet_sparse_fwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp, C.c_int32, vp, C.c_int32, vp]
     L.uavnet_sparse_bwd.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp]
     L.uavnet_sparse_bwd_gather.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp]
+    L.uavnet_sparse_bwd_gather_prepare.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp]
+    L.uavnet_sparse_bwd_gather_apply.argtypes = [C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp]
     L.uavnet_sparse_bwd_gather_workspace.argtypes = [C.c_int64, C.c_int32, C.c_int64]
     L.uavnet_sparse_bwd_gather_workspace.restype = C.c_int64
     L.uavnet_softmax_sample.argtypes = [vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, vp, vp]

@@ -131,6 +131,11 @@ class ACNet:
             t = self._scratch[key] = torch.empty(shape, dtype=dtype, device=self.device)
         return t
 
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _gemm(self, A, B, out=None, **kw):
         return dense.gemm(A, B, out, precision=self.precision, **kw)
 
@@ -233,6 +238,19 @@ class ACNet:
             prob, _, c = self.forward(idx, "actor")
             h1, h2a = c["h1"], c["h2a"]
         gemm = self._gemm
+        side = ws = None
+        if self.sparse_bwd == "gather":
+            # the bucketing of the first layer's (sample, slot) pairs needs the indices only: it runs on a side stream under
+            # the dense layers' backward products and is joined right before the sums
+            nb = int(self._lib.uavnet_sparse_bwd_gather_workspace(M, idx.shape[1], self.n_s))
+            ws = self._buf("bwd_ws", (nb // 4,), torch.int32)
+            cur = torch.cuda.current_stream(self.device)
+            side = self._side_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                rc = self._lib.uavnet_sparse_bwd_gather_prepare(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(ws), self._stream())
+            if rc:
+                raise RuntimeError("uavnet_sparse_bwd_gather_prepare failed (%d)" % rc)
         h2c, v = self.critic_head(h1, self._buf("h2c", (M, H)), self._buf("v", (M,)))
         # td = v_target - v, dv = -2 td / M and c_loss = mean(td^2) in one launch (uavnet_critic_td)
         td, dv1, loss2 = self._buf("td", (M,)), self._buf("dv", (M,)), self._buf("loss2", (2,))
@@ -267,11 +285,10 @@ class ACNet:
         gemm(dpre2a, p["Wa2"], dpre1[:, :H], b_trans=True, mask_src=h1[:, :H], out_colsum=g["b1"][:H])   # + first-layer bias gradient
         if self.sparse_bwd == "gather":
             # rows bucketed by a counting sort, then one plain sum per row and column half (no float atomics)
-            nb = int(self._lib.uavnet_sparse_bwd_gather_workspace(M, idx.shape[1], self.n_s))
-            ws = self._buf("bwd_ws", (nb // 4,), torch.int32)
-            rc = self._lib.uavnet_sparse_bwd_gather(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]), _ptr(ws),
-                                                    self.sparse_bwd_passes if (2 * H // 4) % self.sparse_bwd_passes == 0 else 1,
-                                                    self._stream())
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            rc = self._lib.uavnet_sparse_bwd_gather_apply(M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]), _ptr(ws),
+                                                          self.sparse_bwd_passes if (2 * H // 4) % self.sparse_bwd_passes == 0 else 1,
+                                                          self._stream())
         else:
             rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
                                              self._stream())

@@ -766,10 +766,10 @@ int64_t uavnet_sparse_bwd_gather_workspace(int64_t M, int32_t K, int64_t n_rows)
     return 4 * (2 * pad(n_rows) + 2 * pad(M * K));
 }
 
-int uavnet_sparse_bwd_gather(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
-                             void *workspace, int32_t col_passes, void *stream) {
-    if (!idx || !dpre || !dW || !workspace || M < 1 || K < 1 || n_rows < 1 || n_rows > 0x7fffffffLL || M * K > 0x7fffffffLL || H < 4 ||
-        (H & 3) || !aligned16(dpre) || !aligned16(dW) || !aligned16(workspace) || col_passes < 1 || (H / 4) % col_passes != 0)
+// step 1 of the gather-side gradient: bucket the (sample, slot) pairs by row.  Depends on the indices only, so a caller can
+// run it on a side stream as soon as the rollout's indices exist, under the backward products of the dense layers.
+int uavnet_sparse_bwd_gather_prepare(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, void *workspace, void *stream) {
+    if (!idx || !workspace || M < 1 || K < 1 || n_rows < 1 || n_rows > 0x7fffffffLL || M * K > 0x7fffffffLL || !aligned16(workspace))
         return UAVNET_EINVAL;
     const int dev = use_device_of(idx, stream);
     cudaStream_t st = (cudaStream_t)stream;
@@ -780,13 +780,34 @@ int uavnet_sparse_bwd_gather(const int32_t *idx, int64_t M, int32_t K, int64_t n
     row_hist_kernel<<<grid_for(n, dev), NET_THREADS, 0, st>>>(idx, n, (int)n_rows, count);
     row_scan_kernel<<<1, 1024, 0, st>>>(count, (int)n_rows, cursor);
     row_fill_kernel<<<grid_for(n, dev), NET_THREADS, 0, st>>>(idx, n, K, (int)n_rows, cursor, sample_of, row_of);
-    // after the fill cursor[r] = end of row r's bucket: the last row's cursor is the number of bucketed pairs
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+// step 2: the slice-wise sums over the sorted list (after the fill cursor[r] = end of row r's bucket: the last row's cursor
+// is the number of bucketed pairs)
+int uavnet_sparse_bwd_gather_apply(int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW, void *workspace,
+                                   int32_t col_passes, void *stream) {
+    if (!dpre || !dW || !workspace || M < 1 || K < 1 || n_rows < 1 || n_rows > 0x7fffffffLL || M * K > 0x7fffffffLL || H < 4 || (H & 3) ||
+        !aligned16(dpre) || !aligned16(dW) || !aligned16(workspace) || col_passes < 1 || (H / 4) % col_passes != 0)
+        return UAVNET_EINVAL;
+    const int dev = use_device_of(dpre, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto pad = [](int64_t n) { return (n + 3) / 4 * 4; };
+    int32_t *count = (int32_t *)workspace, *cursor = count + pad(n_rows), *sample_of = cursor + pad(n_rows), *row_of = sample_of + pad(M * K);
+    const long long n = M * K;
     const int H4 = H / 4, nc4 = H4 / col_passes;
     const long long items = ((n + BWD_SLICE - 1) / BWD_SLICE) * nc4;
     for (int p = 0; p < col_passes; p++)
         sparse_bwd_gather_kernel<<<grid_for(items, dev), NET_THREADS, 0, st>>>(sample_of, row_of, cursor + (n_rows - 1), (const float4 *)dpre,
                                                                           H4, p * nc4, nc4, (float4 *)dW);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_sparse_bwd_gather(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
+                             void *workspace, int32_t col_passes, void *stream) {
+    if (!idx || !dpre || !dW || !workspace || H < 4 || (H & 3) || col_passes < 1 || (H / 4) % col_passes != 0) return UAVNET_EINVAL;
+    const int rc = uavnet_sparse_bwd_gather_prepare(idx, M, K, n_rows, workspace, stream);
+    return rc ? rc : uavnet_sparse_bwd_gather_apply(M, K, n_rows, dpre, H, dW, workspace, col_passes, stream);
 }
 
 int uavnet_actor_head_bwd(const float *prob, const int64_t *a_his, const float *td, int64_t M, int32_t A, float beta,

@@ -47,6 +47,11 @@ int uavnet_sparse_bwd(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, 
 int64_t uavnet_sparse_bwd_gather_workspace(int64_t M, int32_t K, int64_t n_rows);
 int uavnet_sparse_bwd_gather(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
                              void *workspace, int32_t col_passes, void *stream);
+/* The two halves of it: _prepare buckets the pairs (needs the indices only -- a caller can run it on a side stream as soon
+ * as the rollout's indices exist, under the dense layers' backward products), _apply does the sums. */
+int uavnet_sparse_bwd_gather_prepare(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, void *workspace, void *stream);
+int uavnet_sparse_bwd_gather_apply(int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW, void *workspace,
+                                   int32_t col_passes, void *stream);
 
 /* Actor head of the rollout (main.py:149,165-169): prob = softmax(logits) and action ~ np.random.choice(A, p=prob) by
  * inverse CDF with one Philox4x32-10 uniform per sample, keyed by (seed, row_offset + row, counter) -- the first action
