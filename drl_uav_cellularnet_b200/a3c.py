@@ -71,6 +71,7 @@ class ACNet:
         self.precision = precision
         # first-layer weight gradient: "gather" (counting sort + per-row sums) or "scatter" (float REDs); measured in
         # profiles/r2/NOTES.md section 5
+        self.overlap_chains = os.environ.get("UAVNET_OVERLAP_CHAINS", "1") != "0"
         self.sparse_bwd = os.environ.get("UAVNET_SPARSE_BWD", "gather")
         self.sparse_bwd_passes = int(os.environ.get("UAVNET_BWD_PASSES", "2"))
         self.ld_a = (self.n_a + 3) // 4 * 4          # rows of Wa3 / dz padded to 16 bytes (625 -> 628): vector staging
@@ -131,10 +132,12 @@ class ACNet:
             t = self._scratch[key] = torch.empty(shape, dtype=dtype, device=self.device)
         return t
 
-    def _side_stream(self):
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
-        return self._side
+    def _side_stream(self, i: int = 0):
+        if getattr(self, "_sides", None) is None:
+            self._sides = {}
+        if i not in self._sides:
+            self._sides[i] = torch.cuda.Stream(device=self.device)
+        return self._sides[i]
 
     def _gemm(self, A, B, out=None, **kw):
         return dense.gemm(A, B, out, precision=self.precision, **kw)
@@ -259,16 +262,22 @@ class ACNet:
         if rc:
             raise RuntimeError("uavnet_critic_td failed (%d)" % rc)
         dv = dv1.unsqueeze(1)                                              # [M, 1]
-        # -- critic: every weight gradient is x^T @ dy accumulated into the flat gradient buffer, its bias gradient the
-        # -- column sums of dy from the same pass; every data gradient is (dy @ W^T) * relu6'(layer output) --
-        gemm(h2c, dv, g["Wc3"], a_trans=True, accumulate=True, colsum=g["bc3"])
-        dpre2c = self._buf("dpre2c", (M, H))                               # (dv (x) wc3) * relu6'(h2c)
-        rc = self._lib.uavnet_rank1_mask(_ptr(dv), _ptr(p["Wc3"]), _ptr(h2c), M, H, _ptr(dpre2c), self._stream())
-        if rc:
-            raise RuntimeError("uavnet_rank1_mask failed (%d)" % rc)
-        gemm(h1[:, H:], dpre2c, g["Wc2"], a_trans=True, accumulate=True, colsum=g["bc2"])
         dpre1 = self._buf("dpre1", (M, 2 * H))
-        gemm(dpre2c, p["Wc2"], dpre1[:, H:], b_trans=True, mask_src=h1[:, H:], out_colsum=g["b1"][H:])
+        # -- critic: every weight gradient is x^T @ dy accumulated into the flat gradient buffer, its bias gradient the
+        # -- column sums of dy from the same pass; every data gradient is (dy @ W^T) * relu6'(layer output).  The critic's
+        # -- backward chain and the actor's touch disjoint buffers once td exists: the critic's runs on a second stream --
+        main = torch.cuda.current_stream(self.device)
+        cstream = self._side_stream(1) if self.overlap_chains else main
+        if cstream is not main:
+            cstream.wait_stream(main)
+        with torch.cuda.stream(cstream):
+            gemm(h2c, dv, g["Wc3"], a_trans=True, accumulate=True, colsum=g["bc3"])
+            dpre2c = self._buf("dpre2c", (M, H))                           # (dv (x) wc3) * relu6'(h2c)
+            rc = self._lib.uavnet_rank1_mask(_ptr(dv), _ptr(p["Wc3"]), _ptr(h2c), M, H, _ptr(dpre2c), self._stream())
+            if rc:
+                raise RuntimeError("uavnet_rank1_mask failed (%d)" % rc)
+            gemm(h1[:, H:], dpre2c, g["Wc2"], a_trans=True, accumulate=True, colsum=g["bc2"])
+            gemm(dpre2c, p["Wc2"], dpre1[:, H:], b_trans=True, mask_src=h1[:, H:], out_colsum=g["b1"][H:])
         # -- actor: d(a_loss)/d(logits) in one fused pass over the softmax output --
         dz = self._buf("dz", (M, self.ld_a))[:, :self.n_a]
         loss_row = self._buf("loss_row", (M,))
@@ -283,6 +292,8 @@ class ACNet:
         dpre2a = gemm(dz, p["Wa3"], self._buf("dpre2a", (M, H)), b_trans=True, mask_src=h2a)
         gemm(h1[:, :H], dpre2a, g["Wa2"], a_trans=True, accumulate=True, colsum=g["ba2"])
         gemm(dpre2a, p["Wa2"], dpre1[:, :H], b_trans=True, mask_src=h1[:, :H], out_colsum=g["b1"][:H])   # + first-layer bias gradient
+        if cstream is not main:
+            main.wait_stream(cstream)
         if self.sparse_bwd == "gather":
             # rows bucketed by a counting sort, then one plain sum per row and column half (no float atomics)
             torch.cuda.current_stream(self.device).wait_stream(side)
