@@ -224,7 +224,7 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
     net = ACNet(envs[0].observation_space_dim, envs[0].action_space_dim, dev, precision=args.a3c_precision)
     use_p2p = args.push == "p2p" and world > 1      # one GPU: nothing to push, the plain RMSProp pass
     if use_p2p:
-        net.enable_p2p()
+        net.enable_p2p(split=args.split_push)
     tr = A3CTrainer(envs if groups > 1 else envs[0], net, seed=100 + rank)
 
     def timed(fn, n):
@@ -272,7 +272,7 @@ def bench_a3c(args, rank, world, local_rank, dev, udist):
                     % (E, world, tr.T, args.a3c_precision, args.push if world > 1 else "none (1 GPU)"),
         "metric": "A3C env-steps/sec (rollout + update)", "unit": UNIT,
         "value": E * world * tr.T / (ms_iter * 1e-3), "ms_per_iteration": ms_iter, "iterations": iters,
-        "envs_per_gpu": E, "rollout_steps": tr.T, "stream_groups": groups, "push": args.push if world > 1 else None,
+        "envs_per_gpu": E, "rollout_steps": tr.T, "stream_groups": groups, "push": args.push if world > 1 else None, "push_split": bool(use_p2p and args.split_push),
         "ms_push": ms_push, "push_note": "the push alone, back to back: p2p = uavnet_p2p_push (2 kernels, RMSProp and gradient zeroing "
                                          "included); nccl = all_reduce + uavnet_rmsprop",
         "p2p_pushes_completed": p2p_state[0] if p2p_state else None, "p2p_flag_wait_gave_up": p2p_state[1] if p2p_state else None,
@@ -312,6 +312,8 @@ def main():
                          "ranks ordered by flag words in peer memory); nccl = all-reduce of the flat gradient buffer + RMSProp pass")
     ap.add_argument("--spinup-ms", type=float, default=300.0, help="untimed spin-up before the warm-up steps (0 = none)")
     ap.add_argument("--guard-db", type=float, default=0.0, help="fp32_guarded: width of the re-evaluation band (0 = the library default)")
+    ap.add_argument("--split-push", action="store_true", help="p2p push in two parts: the actor half of the first layer's gradient early, "
+                    "under the critic half's gather pass, the rest at the end of the update (default: one piece; measured equal at 8 GPUs)")
     ap.add_argument("--a3c-envs", type=int, default=8192)
     ap.add_argument("--a3c-groups", type=int, default=4)
     ap.add_argument("--a3c-precision", default="tf32", choices=["tf32", "fp32"])

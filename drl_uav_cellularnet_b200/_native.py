@@ -67,6 +67,11 @@ class GemmDesc(C.Structure):
                 ("precision", C.c_int32)]
 
 
+class PushPart(C.Structure):
+    """uavnet_push_part (include/uavnet.h): a column range of a row-major matrix inside the flat buffers, in float32 elements"""
+    _fields_ = [("offset", C.c_int64), ("rows", C.c_int64), ("row_width", C.c_int32), ("col0", C.c_int32), ("n_cols", C.c_int32)]
+
+
 GEMM_TF32, GEMM_3XTF32 = 0, 1
 
 # every symbol include/uavenv.h and include/uavnet.h declare
@@ -74,8 +79,8 @@ SYMBOLS = [
     "uavenv_cfg_default", "uavenv_create", "uavenv_destroy", "uavenv_set_trace", "uavenv_ctor_pass",
     "uavenv_reset", "uavenv_step", "uavenv_step_host", "uavenv_step_host_state", "uavenv_coverage_map", "uavenv_state_bytes", "uavenv_state_field",
     "uavenv_get_state", "uavenv_set_state", "uavenv_check", "uavenv_guard_hits", "uavenv_get_cfg", "uavenv_last_error",
-    "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_sparse_bwd_gather", "uavnet_sparse_bwd_gather_workspace", "uavnet_sparse_bwd_gather_prepare", "uavnet_sparse_bwd_gather_apply", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
-    "uavnet_p2p_rmsprop", "uavnet_p2p_push", "uavnet_p2p_push_status", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record", "uavnet_critic_td", "uavnet_mean_rows",
+    "uavnet_sparse_fwd", "uavnet_sparse_bwd", "uavnet_sparse_bwd_gather", "uavnet_sparse_bwd_gather_workspace", "uavnet_sparse_bwd_gather_prepare", "uavnet_sparse_bwd_gather_apply", "uavnet_sparse_bwd_gather_apply_cols", "uavnet_rmsprop", "uavnet_actor_head_bwd", "uavnet_softmax_sample", "uavnet_p2p_alloc", "uavnet_p2p_open", "uavnet_p2p_close", "uavnet_p2p_free",
+    "uavnet_p2p_rmsprop", "uavnet_p2p_push", "uavnet_p2p_push_status", "uavnet_p2p_push_part", "uavnet_gemm", "uavnet_gemm_check", "uavnet_nstep_targets", "uavnet_rank1_mask", "uavnet_rollout_record", "uavnet_critic_td", "uavnet_mean_rows",
     "uavenv_launch_count", "uavenv_version", "uavenv_launch_plan",
 ]
 
@@ -122,6 +127,7 @@ def lib():
     L.uavnet_sparse_bwd_gather.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp]
     L.uavnet_sparse_bwd_gather_prepare.argtypes = [vp, C.c_int64, C.c_int32, C.c_int64, vp, vp]
     L.uavnet_sparse_bwd_gather_apply.argtypes = [C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, vp, vp, C.c_int32, vp]
+    L.uavnet_sparse_bwd_gather_apply_cols.argtypes = [C.c_int64, C.c_int32, C.c_int64, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp]
     L.uavnet_sparse_bwd_gather_workspace.argtypes = [C.c_int64, C.c_int32, C.c_int64]
     L.uavnet_sparse_bwd_gather_workspace.restype = C.c_int64
     L.uavnet_softmax_sample.argtypes = [vp, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, vp, C.c_uint32, vp, vp, vp]
@@ -133,6 +139,7 @@ def lib():
     L.uavnet_p2p_rmsprop.argtypes = [P(vp), P(vp), vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp]
     L.uavnet_p2p_push.argtypes = [P(vp), P(vp), P(vp), vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp]
     L.uavnet_p2p_push_status.argtypes = [vp, P(C.c_uint32), P(C.c_uint32)]
+    L.uavnet_p2p_push_part.argtypes = [P(vp), P(vp), P(vp), vp, P(PushPart), P(PushPart), C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float, vp]
     L.uavnet_rmsprop.argtypes = [vp, vp, vp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, vp]
     L.uavnet_gemm.argtypes = [P(GemmDesc), vp]
     L.uavnet_gemm_check.argtypes = []

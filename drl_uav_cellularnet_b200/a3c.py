@@ -228,11 +228,13 @@ class ACNet:
         return self.forward(idx, "critic")[1]
 
     # ---- losses + gradients (main.py:64-78), accumulated into self.grad -------------------------------------
-    def accumulate_grads(self, idx: torch.Tensor, a_his: torch.Tensor, v_target: torch.Tensor, saved: Optional[dict] = None):
+    def accumulate_grads(self, idx: torch.Tensor, a_his: torch.Tensor, v_target: torch.Tensor, saved: Optional[dict] = None,
+                         early_push=None):
         """Adds d(a_loss)/d(actor params) and d(c_loss)/d(critic params) for the batch to ``self.grad``;
         returns (a_loss, c_loss) as 0-d tensors.  a_loss = mean(-(log(pi(a)+1e-5) * sg(td) + beta * H)),
         c_loss = mean(td^2), td = v_target - v.  `saved`: activations kept from the rollout (h1, h2a, prob -- the
-        parameters do not change between the rollout and its update), else they are recomputed from idx."""
+        parameters do not change between the rollout and its update), else they are recomputed from idx.  early_push: called
+        once the actor half of the first layer's gradient is complete (split peer-memory push)."""
         H, p, g = self.h, self.p, self.g
         M = idx.shape[0]
         if saved is not None:
@@ -297,9 +299,19 @@ class ACNet:
         if self.sparse_bwd == "gather":
             # rows bucketed by a counting sort, then one plain sum per row and column half (no float atomics)
             torch.cuda.current_stream(self.device).wait_stream(side)
-            rc = self._lib.uavnet_sparse_bwd_gather_apply(M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]), _ptr(ws),
-                                                          self.sparse_bwd_passes if (2 * H // 4) % self.sparse_bwd_passes == 0 else 1,
-                                                          self._stream())
+            if early_push is not None and H % 4 == 0:
+                # the actor half first; its push (early_push: a callable, e.g. ACNet.push_early) goes out under the critic half
+                rc = self._lib.uavnet_sparse_bwd_gather_apply_cols(M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, 0, H, _ptr(g["W1"]),
+                                                                   _ptr(ws), self._stream())
+                if rc:
+                    raise RuntimeError("uavnet_sparse_bwd_gather_apply_cols failed (%d)" % rc)
+                early_push()
+                rc = self._lib.uavnet_sparse_bwd_gather_apply_cols(M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, H, H, _ptr(g["W1"]),
+                                                                   _ptr(ws), self._stream())
+            else:
+                rc = self._lib.uavnet_sparse_bwd_gather_apply(M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]), _ptr(ws),
+                                                              self.sparse_bwd_passes if (2 * H // 4) % self.sparse_bwd_passes == 0 else 1,
+                                                              self._stream())
         else:
             rc = self._lib.uavnet_sparse_bwd(_ptr(idx), M, idx.shape[1], self.n_s, _ptr(dpre1), 2 * H, _ptr(g["W1"]),
                                              self._stream())
@@ -320,7 +332,7 @@ class ACNet:
             raise RuntimeError("uavnet_rmsprop failed (%d)" % rc)
 
     # ---- the push over NVLink peer memory: reduce-scatter + RMSProp + all-gather in ONE kernel per rank ----------
-    def enable_p2p(self):
+    def enable_p2p(self, split: bool = False):
         """Move the flat parameter / gradient buffers into IPC-shareable allocations, exchange their handles between
         the ranks' processes and map every peer's buffers (cudaIpcOpenMemHandle, peer access over NVLink).  From then
         on ``apply_grads`` is ``uavnet_p2p_push``: one peer-memory kernel per rank does reduce-scatter + RMSProp +
@@ -364,11 +376,53 @@ class ACNet:
                     opened.append(peer.value)
             torch.cuda.synchronize(self.device)
             dist.barrier()                            # every rank has mapped every buffer before anyone pushes
-        self._p2p = {"bufs": bufs, "gptrs": gptrs, "pptrs": pptrs, "fptrs": fptrs, "opened": opened, "rank": rank, "world": world}
+        # split: the push of an update comes in two parts -- the actor half of the first layer's gradient as soon as its gather
+        # pass is done (push_early, on a side stream under the critic half's pass), everything else in apply_grads.  The two
+        # modes give different ranks ownership of an element (its RMSProp slot lives on the owner), so the mode is fixed here.
+        self._p2p = {"bufs": bufs, "gptrs": gptrs, "pptrs": pptrs, "fptrs": fptrs, "opened": opened, "rank": rank, "world": world,
+                     "split": bool(split), "early_done": False}
         return self
+
+    def _push_parts(self):
+        """the two pushes of the split mode as lists of (offset, rows, row_width, col0, n_cols) in float32 elements"""
+        o, n, stored, _ = self.segments["W1"]
+        H2 = stored[1]
+        early = [(o, stored[0], H2, 0, H2 // 2)]
+        tail0 = o + (n + 3) // 4 * 4
+        late = [(o, stored[0], H2, H2 // 2, H2 // 2), (tail0, 1, self.n_flat - tail0, 0, self.n_flat - tail0)]
+        return early, late
+
+    def _push_part(self, parts, lr: float):
+        q = self._p2p
+        a = N.PushPart(*parts[0])
+        b = N.PushPart(*parts[1]) if len(parts) > 1 else None
+        rc = self._lib.uavnet_p2p_push_part(q["gptrs"], q["pptrs"], q["fptrs"], _ptr(self.ms), C.byref(a), C.byref(b) if b is not None else None,
+                                            q["rank"], q["world"], lr, RMS_DECAY, RMS_EPS, self._stream())
+        if rc:
+            raise RuntimeError("uavnet_p2p_push_part failed (%d)" % rc)
+
+    def push_early(self, lr: float = LR_A):
+        """split mode: push the actor half of the first layer's gradient now, on a side stream that waits for everything
+        enqueued so far on the current one; apply_grads pushes the rest and joins"""
+        q = self._p2p
+        main = torch.cuda.current_stream(self.device)
+        ps = self._side_stream(2)
+        ps.wait_stream(main)
+        with torch.cuda.stream(ps):
+            self._push_part(self._push_parts()[0], lr)
+        q["early_done"] = True
 
     def _apply_grads_p2p(self, lr: float):
         q = self._p2p
+        if q["split"]:
+            early, late = self._push_parts()
+            if q["early_done"]:
+                torch.cuda.current_stream(self.device).wait_stream(self._side_stream(2))    # pushes are ordered by their epochs
+            else:
+                self._push_part(early, lr)            # nobody pushed the first part ahead of time: both parts here
+            self._push_part(late, lr)
+            q["early_done"] = False
+            return
         rc = self._lib.uavnet_p2p_push(q["gptrs"], q["pptrs"], q["fptrs"], _ptr(self.ms), self.n_flat, q["rank"], q["world"], lr,
                                        RMS_DECAY, RMS_EPS, self._stream())
         if rc:
@@ -384,13 +438,26 @@ class ACNet:
             raise RuntimeError("uavnet_p2p_push_status failed (%d)" % rc)
         return int(e.value), bool(t.value)
 
-    def _p2p_slice(self):
-        """[lo, hi) of the flat buffers this rank owns in the push (uavnet_p2p_push: ceil(n/4/world) float4s per rank)"""
+    def _p2p_owned_mask(self) -> torch.Tensor:
+        """bool [n_flat]: the elements whose RMSProp slot this rank maintains (its slices of the pushes' element numberings,
+        uavnet_p2p_push / uavnet_p2p_push_part)"""
         q = self._p2p
-        n4 = self.n_flat // 4
-        per4 = (n4 + q["world"] - 1) // q["world"]
-        lo4 = q["rank"] * per4
-        return 4 * min(lo4, n4), 4 * min(lo4 + per4, n4), 4 * per4
+        world, rank = q["world"], q["rank"]
+        pushes = list(self._push_parts()) if q["split"] else [[(0, 1, self.n_flat, 0, self.n_flat)]]
+        mask4 = torch.zeros(self.n_flat // 4, dtype=torch.bool, device=self.device)
+        for parts in pushes:
+            sizes = [rows * (ncols // 4) for (_, rows, _, _, ncols) in parts]
+            n4 = sum(sizes)
+            per4 = (n4 + world - 1) // world
+            lo, hi = min(rank * per4, n4), min(rank * per4 + per4, n4)
+            j = torch.arange(lo, hi, device=self.device, dtype=torch.int64)
+            start = 0
+            for (off, rows, row_w, col0, ncols), sz in zip(parts, sizes):
+                jj = j[(j >= start) & (j < start + sz)] - start
+                sub = ncols // 4
+                mask4[off // 4 + (jj // sub) * (row_w // 4) + col0 // 4 + jj % sub] = True
+                start += sz
+        return mask4.repeat_interleave(4)
 
     def close_p2p(self):
         """Back to private buffers.  The push keeps the RMSProp slot `ms` only for the slice a rank owns: the slices are
@@ -402,17 +469,14 @@ class ACNet:
         import torch.distributed as dist
         torch.cuda.synchronize(self.device)
         if q["world"] > 1:
-            lo, hi, per = self._p2p_slice()
-            mine = torch.ones(per, dtype=torch.float32, device=self.device)
-            mine[:hi - lo].copy_(self.ms[lo:hi])
+            mine = torch.where(self._p2p_owned_mask(), self.ms, torch.zeros_like(self.ms))     # every element has one owner
             if dist.get_backend() == "nccl":
-                every = torch.empty(per * q["world"], dtype=torch.float32, device=self.device)
-                dist.all_gather_into_tensor(every, mine)
+                dist.all_reduce(mine)
             else:                                     # gloo (tests): through host memory
-                parts = [torch.empty(per, dtype=torch.float32) for _ in range(q["world"])]
-                dist.all_gather(parts, mine.cpu())
-                every = torch.cat(parts).to(self.device)
-            self.ms.copy_(every[:self.n_flat])
+                host = mine.cpu()
+                dist.all_reduce(host)
+                mine = host.to(self.device)
+            self.ms.copy_(mine)
             torch.cuda.synchronize(self.device)
             dist.barrier()                            # nobody unmaps while a peer could still be in a push
         for ptr in q["opened"]:
@@ -586,7 +650,10 @@ class A3CTrainer:
     def update(self, v_target: torch.Tensor):
         net, M = self.net, self.T * self.E
         saved = {"h1": self.buf_h1.view(M, -1), "h2a": self.buf_h2a.view(M, -1), "prob": self.buf_prob.view(M, -1)}
-        a_loss, c_loss = net.accumulate_grads(self.buf_idx[:self.T].view(M, self.K), self.buf_a.view(M), v_target.reshape(M), saved)
+        q = getattr(net, "_p2p", None)
+        early = net.push_early if (q and q["split"] and q["world"] > 1 and net.sparse_bwd == "gather") else None
+        a_loss, c_loss = net.accumulate_grads(self.buf_idx[:self.T].view(M, self.K), self.buf_a.view(M), v_target.reshape(M), saved,
+                                              early_push=early)
         world = 1
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             world = torch.distributed.get_world_size()

@@ -388,10 +388,26 @@ __device__ __forceinline__ void wait_flags(unsigned int *mine, int base, int wor
     }
 }
 
+// What a push covers: up to two regions of the flat buffers, each a sub-matrix (all rows, a column range) of a row-major
+// matrix or a plain range -- in float4 units.  The elements are numbered region a first, then region b; rank r owns the
+// r-th of `world` equal slices of that numbering.  (The learner pushes the actor half of the first layer's gradient as soon
+// as it is complete, and the critic half together with all the small layers at the end.)
+struct PushRegion { long long base4, n4; int row_w4, col0_4, sub_w4; };
+struct PushRegions { PushRegion a, b; };
+__device__ __forceinline__ long long push_flat4(const PushRegions &R, long long j) {
+    const bool in_a = j < R.a.n4;
+    const PushRegion &r = in_a ? R.a : R.b;
+    const long long jj = in_a ? j : j - R.a.n4;
+    if (r.sub_w4 == r.row_w4) return r.base4 + jj;
+    const long long row = jj / r.sub_w4;
+    return r.base4 + row * r.row_w4 + r.col0_4 + (jj - row * r.sub_w4);
+}
+
 template <int W>   // W = world size known at compile time (all peer loads of an element in flight at once), 0 = any
 __global__ void __launch_bounds__(NET_THREADS) p2p_push_kernel(const __grid_constant__ PeerPtrs2 pp, float *__restrict__ ms,
-                                                               long long lo4, long long hi4, int rank, int world_rt, float lr,
-                                                               float decay, float eps, float gs, int dbg) {
+                                                               const __grid_constant__ PushRegions R, long long lo4,
+                                                               long long hi4, int rank, int world_rt, float lr, float decay,
+                                                               float eps, float gs, int dbg) {
     const int world = W > 0 ? W : world_rt;
     unsigned int *mine = pp.f[rank];
     __shared__ unsigned int e_sh;
@@ -407,7 +423,8 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_push_kernel(const __grid_cons
     __syncthreads();
     const float od = 1.f - decay;
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long i = lo4 + (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < hi4; i += (long long)gridDim.x * NET_THREADS) {
+    for (long long jn = lo4 + (long long)blockIdx.x * NET_THREADS + threadIdx.x; jn < hi4; jn += (long long)gridDim.x * NET_THREADS) {
+        const long long i = push_flat4(R, jn);
         float4 acc = zero;
         if constexpr (W > 0) {
             // an NVLink peer load takes microseconds: all W of them are requested before the first is used
@@ -443,9 +460,11 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_push_kernel(const __grid_cons
     }
 }
 
-// waits for every rank's push kernel, zeroes the own gradient buffer outside [lo4, hi4) and publishes the epoch
-__global__ void __launch_bounds__(NET_THREADS) p2p_finish_kernel(unsigned int *mine, float4 *__restrict__ g4, long long n4,
-                                                                 long long lo4, long long hi4, int world) {
+// waits for every rank's push kernel, zeroes the pushed elements of the own gradient buffer outside the own slice [lo4, hi4)
+// (the push kernel zeroed that one) and publishes the epoch
+__global__ void __launch_bounds__(NET_THREADS) p2p_finish_kernel(unsigned int *mine, float4 *__restrict__ g4,
+                                                                 const __grid_constant__ PushRegions R, long long lo4, long long hi4,
+                                                                 int world) {
     __shared__ unsigned int e_sh;
     if (threadIdx.x == 0) {
         const unsigned int e = ld_flag(mine + PF_EPOCH) + 1u;
@@ -454,8 +473,9 @@ __global__ void __launch_bounds__(NET_THREADS) p2p_finish_kernel(unsigned int *m
     }
     __syncthreads();
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long i = (long long)blockIdx.x * NET_THREADS + threadIdx.x; i < n4; i += (long long)gridDim.x * NET_THREADS)
-        if (i < lo4 || i >= hi4) g4[i] = zero;
+    const long long n = R.a.n4 + R.b.n4;
+    for (long long j = (long long)blockIdx.x * NET_THREADS + threadIdx.x; j < n; j += (long long)gridDim.x * NET_THREADS)
+        if (j < lo4 || j >= hi4) g4[push_flat4(R, j)] = zero;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -803,6 +823,23 @@ int uavnet_sparse_bwd_gather_apply(int64_t M, int32_t K, int64_t n_rows, const f
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
+// the sums for the columns [col0, col0 + n_cols) only (a caller that wants to do something between the column passes)
+int uavnet_sparse_bwd_gather_apply_cols(int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, int32_t col0, int32_t n_cols,
+                                        float *dW, void *workspace, void *stream) {
+    if (!dpre || !dW || !workspace || M < 1 || K < 1 || n_rows < 1 || n_rows > 0x7fffffffLL || M * K > 0x7fffffffLL || H < 4 || (H & 3) ||
+        !aligned16(dpre) || !aligned16(dW) || !aligned16(workspace) || col0 < 0 || (col0 & 3) || n_cols < 4 || (n_cols & 3) || col0 + n_cols > H)
+        return UAVNET_EINVAL;
+    const int dev = use_device_of(dpre, stream);
+    auto pad = [](int64_t n) { return (n + 3) / 4 * 4; };
+    int32_t *count = (int32_t *)workspace, *cursor = count + pad(n_rows), *sample_of = cursor + pad(n_rows), *row_of = sample_of + pad(M * K);
+    const long long n = M * K;
+    const int nc4 = n_cols / 4;
+    const long long items = ((n + BWD_SLICE - 1) / BWD_SLICE) * nc4;
+    sparse_bwd_gather_kernel<<<grid_for(items, dev), NET_THREADS, 0, (cudaStream_t)stream>>>(sample_of, row_of, cursor + (n_rows - 1),
+                                                                                        (const float4 *)dpre, H / 4, col0 / 4, nc4, (float4 *)dW);
+    return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
 int uavnet_sparse_bwd_gather(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW,
                              void *workspace, int32_t col_passes, void *stream) {
     if (!idx || !dpre || !dW || !workspace || H < 4 || (H & 3) || col_passes < 1 || (H / 4) % col_passes != 0) return UAVNET_EINVAL;
@@ -879,27 +916,24 @@ int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_loca
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
 }
 
-int uavnet_p2p_push(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, int64_t n, int32_t rank,
-                    int32_t world, float lr, float decay, float eps, void *stream) {
-    if (!grads || !params || !flags || !ms_local || n < 4 || (n & 3) || world < 1 || world > UAVNET_MAX_PEERS || rank < 0 || rank >= world)
-        return UAVNET_EINVAL;
+static int p2p_push_regions(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, const PushRegions &R,
+                            int32_t rank, int32_t world, float lr, float decay, float eps, void *stream) {
     PeerPtrs2 pp;
     memset(&pp, 0, sizeof(pp));
     for (int r = 0; r < world; r++) {
         if (!grads[r] || !params[r] || !flags[r] || !aligned16(grads[r]) || !aligned16(params[r])) return UAVNET_EINVAL;
         pp.g[r] = grads[r]; pp.p[r] = params[r]; pp.f[r] = flags[r];
     }
-    const long long n4 = n >> 2, per4 = (n4 + world - 1) / world;
-    const long long lo4 = (long long)rank * per4, hi4 = lo4 + per4 < n4 ? lo4 + per4 : n4;
+    const long long n4 = R.a.n4 + R.b.n4, per4 = (n4 + world - 1) / world;
+    const long long lo4 = (long long)rank * per4 < n4 ? (long long)rank * per4 : n4, hi = lo4 + per4 < n4 ? lo4 + per4 : n4;
     const int dev = use_device_of(ms_local, stream);
-    const long long mine4 = hi4 > lo4 ? hi4 - lo4 : 1;
+    const long long mine4 = hi > lo4 ? hi - lo4 : 1;
     // Two blocks per SM: measured on 8 B200s (80.8 MB, profiles/r2/NOTES.md) 64 / 148 / 296 / 592 / 1184 / 2368 blocks take
     // 0.336 / 0.321 / 0.316 / 0.360 / 0.387 / 0.401 ms -- NVLink likes few fat streams of peer loads and stores better than
     // many thin ones.  (Every block also spins on the flags first, so the grid has to stay within a wave anyway.)
     int grid = grid_for(mine4, dev);
     const int one_wave = sm_count(dev) * 8;
     if (grid > 2 * sm_count(dev)) grid = 2 * sm_count(dev);
-    const long long hi = hi4 > lo4 ? hi4 : lo4;
     const float gs = 1.0f / (float)world;
     cudaStream_t st = (cudaStream_t)stream;
     // timing experiments only (results are wrong when set): bit 0 = no peer stores, bit 1 = no peer loads
@@ -907,17 +941,48 @@ int uavnet_p2p_push(float *const *grads, float *const *params, uint32_t *const *
     if (dbg < 0) { const char *ev = getenv("UAVNET_P2P_DBG"); dbg = ev ? atoi(ev) : 0; }
     if (const char *ev = getenv("UAVNET_P2P_GRID")) { const int gmax = atoi(ev); if (gmax > 0) grid = gmax; }
     switch (world) {
-        case 1: p2p_push_kernel<1><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
-        case 2: p2p_push_kernel<2><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
-        case 4: p2p_push_kernel<4><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
-        case 8: p2p_push_kernel<8><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
-        default: p2p_push_kernel<0><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        case 1: p2p_push_kernel<1><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, R, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        case 2: p2p_push_kernel<2><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, R, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        case 4: p2p_push_kernel<4><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, R, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        case 8: p2p_push_kernel<8><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, R, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
+        default: p2p_push_kernel<0><<<grid, NET_THREADS, 0, st>>>(pp, ms_local, R, lo4, hi, rank, world, lr, decay, eps, gs, dbg); break;
     }
     if (cudaGetLastError() != cudaSuccess) return UAVNET_ECUDA;
     int grid2 = grid_for(n4, dev);
     if (grid2 > one_wave) grid2 = one_wave;
-    p2p_finish_kernel<<<grid2, NET_THREADS, 0, st>>>(flags[rank], (float4 *)grads[rank], n4, lo4, hi, world);
+    p2p_finish_kernel<<<grid2, NET_THREADS, 0, st>>>(flags[rank], (float4 *)grads[rank], R, lo4, hi, world);
     return cudaGetLastError() == cudaSuccess ? UAVNET_OK : UAVNET_ECUDA;
+}
+
+int uavnet_p2p_push(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, int64_t n, int32_t rank,
+                    int32_t world, float lr, float decay, float eps, void *stream) {
+    if (!grads || !params || !flags || !ms_local || n < 4 || (n & 3) || world < 1 || world > UAVNET_MAX_PEERS || rank < 0 || rank >= world)
+        return UAVNET_EINVAL;
+    PushRegions R;
+    memset(&R, 0, sizeof(R));
+    R.a.base4 = 0; R.a.n4 = n >> 2; R.a.row_w4 = R.a.sub_w4 = 1;
+    R.b.row_w4 = R.b.sub_w4 = 1;
+    return p2p_push_regions(grads, params, flags, ms_local, R, rank, world, lr, decay, eps, stream);
+}
+
+int uavnet_p2p_push_part(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, const uavnet_push_part *a,
+                         const uavnet_push_part *b, int32_t rank, int32_t world, float lr, float decay, float eps, void *stream) {
+    if (!grads || !params || !flags || !ms_local || !a || world < 1 || world > UAVNET_MAX_PEERS || rank < 0 || rank >= world) return UAVNET_EINVAL;
+    PushRegions R;
+    memset(&R, 0, sizeof(R));
+    const uavnet_push_part *src[2] = {a, b};
+    PushRegion *dst[2] = {&R.a, &R.b};
+    for (int k = 0; k < 2; k++) {
+        dst[k]->row_w4 = dst[k]->sub_w4 = 1;
+        const uavnet_push_part *q = src[k];
+        if (!q) continue;
+        if (q->offset < 0 || (q->offset & 3) || q->rows < 1 || q->row_width < 4 || (q->row_width & 3) || q->col0 < 0 || (q->col0 & 3) ||
+            q->n_cols < 4 || (q->n_cols & 3) || q->col0 + q->n_cols > q->row_width)
+            return UAVNET_EINVAL;
+        dst[k]->base4 = q->offset >> 2; dst[k]->row_w4 = q->row_width >> 2; dst[k]->col0_4 = q->col0 >> 2; dst[k]->sub_w4 = q->n_cols >> 2;
+        dst[k]->n4 = (long long)q->rows * (q->n_cols >> 2);
+    }
+    return p2p_push_regions(grads, params, flags, ms_local, R, rank, world, lr, decay, eps, stream);
 }
 
 int uavnet_p2p_push_status(const uint32_t *flags_own, uint32_t *epoch_out, uint32_t *timeout_out) {

@@ -52,6 +52,8 @@ int uavnet_sparse_bwd_gather(const int32_t *idx, int64_t M, int32_t K, int64_t n
 int uavnet_sparse_bwd_gather_prepare(const int32_t *idx, int64_t M, int32_t K, int64_t n_rows, void *workspace, void *stream);
 int uavnet_sparse_bwd_gather_apply(int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, float *dW, void *workspace,
                                    int32_t col_passes, void *stream);
+int uavnet_sparse_bwd_gather_apply_cols(int64_t M, int32_t K, int64_t n_rows, const float *dpre, int32_t H, int32_t col0, int32_t n_cols,
+                                        float *dW, void *workspace, void *stream);
 
 /* Actor head of the rollout (main.py:149,165-169): prob = softmax(logits) and action ~ np.random.choice(A, p=prob) by
  * inverse CDF with one Philox4x32-10 uniform per sample, keyed by (seed, row_offset + row, counter) -- the first action
@@ -130,6 +132,15 @@ int uavnet_p2p_rmsprop(float *const *grads, float *const *params, float *ms_loca
 int uavnet_p2p_push(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, int64_t n, int32_t rank,
                     int32_t world, float lr, float decay, float eps, void *stream);
 int uavnet_p2p_push_status(const uint32_t *flags_own, uint32_t *epoch_out, uint32_t *timeout_out);
+/* The same push for PART of the flat buffers: up to two parts, each a column range of a row-major matrix inside the buffers
+ * (offset / row_width / col0 / n_cols in float32 elements, multiples of 4; a plain range is one row).  b may be NULL.  The
+ * elements of a, then of b, are numbered consecutively and rank r owns the r-th of `world` equal slices of that numbering.
+ * What the learner uses it for: the actor half of the first layer's gradient (columns 0..199 of [50000, 400]) is pushed as
+ * soon as it is complete, on a side stream under the critic half's gather pass; the rest follows at the end.  Every element
+ * must be covered by exactly one push per update, the same way on every rank. */
+typedef struct uavnet_push_part { int64_t offset; int64_t rows; int32_t row_width; int32_t col0; int32_t n_cols; } uavnet_push_part;
+int uavnet_p2p_push_part(float *const *grads, float *const *params, uint32_t *const *flags, float *ms_local, const uavnet_push_part *a,
+                         const uavnet_push_part *b, int32_t rank, int32_t world, float lr, float decay, float eps, void *stream);
 
 /* ---- the dense layers (main.py:148-149,152-153: 200->200 relu6, 200->625 softmax logits, 200->1) and their gradients
  * on the 5th-generation tensor cores: tcgen05.mma kind::tf32, fp32 accumulation in tensor memory, fused epilogue ----

@@ -20,6 +20,8 @@ import argparse  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--same-gpu", action="store_true", help="all ranks on cuda:0 (two processes sharing one GPU): the plumbing goes "
                 "through gloo, the push through CUDA IPC mappings of the other process's buffers on the same device")
+ap.add_argument("--split", action="store_true", help="push in two parts (ACNet.enable_p2p(split=True)): the actor half of the "
+                "first layer early on a side stream, the rest in apply_grads")
 ap.add_argument("--n-s", type=int, default=50000)
 ap.add_argument("--n-a", type=int, default=625)
 ap.add_argument("--hidden", type=int, default=200)
@@ -32,7 +34,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 udist.init("gloo" if args.same_gpu else "nccl", dev)
 a, b = ACNet(args.n_s, args.n_a, dev, hidden=args.hidden), ACNet(args.n_s, args.n_a, dev, hidden=args.hidden)
-b.enable_p2p()
+b.enable_p2p(split=args.split)
 g = torch.Generator(device=dev).manual_seed(100 + rank)
 worst = 0.0
 for it in range(4):
@@ -47,6 +49,8 @@ for it in range(4):
         else:
             dist.all_reduce(a.grad)
     a.apply_grads(1e-4, world)
+    if args.split and it % 2 == 0:
+        b.push_early(1e-4)                     # every other iteration the first part goes ahead on its side stream
     b.apply_grads(1e-4)
     torch.cuda.synchronize()
     worst = max(worst, float((a.flat - b.flat).abs().max()))
@@ -85,9 +89,11 @@ a.flat.copy_(b.flat)
 b.close_p2p()                                          # gathers the RMSProp slot slices of all ranks
 ms_sums = [None] * world
 dist.all_gather_object(ms_sums, float(b.ms.double().sum()))
+ms_diff = float((a.ms - b.ms).abs().max())     # same gradient history on both paths: the gathered slots must agree
 if rank == 0:
     print(json.dumps({"world": world, "max_abs_param_diff_vs_nccl_path": worst, "param_sums_per_rank": same,
                       "ms_nccl_allreduce_plus_rmsprop": ms_nccl, "ms_p2p_fused": ms_p2p, "bytes": a.n_flat * 4,
-                      "pushes": pushes, "flag_wait_gave_up": gave_up, "ms_slot_sums_after_close_per_rank": ms_sums}))
+                      "pushes": pushes, "flag_wait_gave_up": gave_up, "ms_slot_sums_after_close_per_rank": ms_sums,
+                      "ms_slot_max_abs_diff_vs_nccl_path": ms_diff, "split": bool(args.split)}))
 dist.barrier()
 dist.destroy_process_group()

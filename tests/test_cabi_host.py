@@ -72,6 +72,8 @@ def test_entry_points_reject_bad_arguments_without_a_gpu(native):
     assert L.uavnet_sparse_bwd_gather(None, 1, 1, 1, None, 4, None, None, 1, None) == -1
     assert L.uavnet_sparse_bwd_gather_prepare(None, 1, 1, 1, None, None) == -1
     assert L.uavnet_sparse_bwd_gather_apply(1, 1, 1, None, 4, None, None, 1, None) == -1
+    assert L.uavnet_sparse_bwd_gather_apply_cols(1, 1, 1, None, 4, 0, 4, None, None, None) == -1
+    assert L.uavnet_p2p_push_part(None, None, None, None, None, None, 0, 1, 1e-4, 0.9, 1e-10, None) == -1
     assert L.uavnet_sparse_bwd_gather_workspace(81920, 44, 50000) >= 4 * (2 * 81920 * 44 + 2 * 50000)
     assert L.uavnet_rmsprop(None, None, None, 4, 1e-4, 0.9, 1e-10, 1.0, 1, None) == -1
     assert L.uavnet_actor_head_bwd(None, None, None, 1, 625, 0.001, None, 625, None, None) == -1

@@ -414,16 +414,18 @@ def test_p2p_push_two_processes_on_one_gpu():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29579", os.path.join(root, "profiles", "p2p_check.py"), "--same-gpu", "--n-s", "20000", "--hidden", "64",
-           "--iters", "5"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert res.returncode == 0, res.stderr[-2000:]
-    d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
-    assert d["world"] == 2 and d["max_abs_param_diff_vs_nccl_path"] == 0.0
-    assert d["param_sums_per_rank"][0] == d["param_sums_per_rank"][1]
-    assert not d["flag_wait_gave_up"] and d["pushes"] >= 9
-    assert d["ms_slot_sums_after_close_per_rank"][0] == d["ms_slot_sums_after_close_per_rank"][1]
+    for split in (False, True):                       # one push per update / the two-part push of the trainer
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29579", os.path.join(root, "profiles", "p2p_check.py"), "--same-gpu", "--n-s", "20000", "--hidden", "64",
+               "--iters", "5"] + (["--split"] if split else [])
+        res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        d = json.loads([ln for ln in res.stdout.splitlines() if ln.startswith("{")][-1])
+        assert d["world"] == 2 and d["max_abs_param_diff_vs_nccl_path"] == 0.0 and d["split"] == split
+        assert d["param_sums_per_rank"][0] == d["param_sums_per_rank"][1]
+        assert not d["flag_wait_gave_up"] and d["pushes"] >= 9
+        assert d["ms_slot_sums_after_close_per_rank"][0] == d["ms_slot_sums_after_close_per_rank"][1]
+        assert d["ms_slot_max_abs_diff_vs_nccl_path"] == 0.0          # every element's RMSProp slot came back from its owner
 
 
 @pytest.mark.parametrize("M,K,R,H,passes", [(300, 44, 5000, 400, 2), (64, 7, 50, 16, 1), (2048, 44, 50000, 400, 4), (10, 3, 4, 8, 2)])
