@@ -877,6 +877,46 @@ template <int NW> struct ChunkPrefetch {
     uint8_t grp[NW][2][32];      // the UEs' group ids (ue_group is padded to whole chunks): lanes 0-7 fetch 4 bytes each
 };
 
+// The guard phase of FP32_GUARDED (see env_kernel): kept out of line so that its live ranges and the float64 call inside it
+// stay off the step kernel's register budget -- the kernel runs at the 80-register cap of 3 CTAs per SM, and with the phase
+// inlined two values were spilled for the whole kernel.  All threads of the CTA call; warp w takes entries w, w + NW, ...
+template <int NB, int NT>
+__device__ __noinline__ void guard_phase(const DevCfg &c, const CallArgs &a, EnvShared &s, int e, uint32_t genv, uint32_t epoch, int mode,
+                                         bool incremental, float *obs_env, int n_cells, int32_t *lin_arr) {
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nUE = c.nUE, nBS = c.nBS, G = c.G;
+    const uint64_t keep = l2_policy_evict_last();
+    const int n_g = s.guard_n;
+    const bool listed = n_g <= GUARD_LIST;                               // else: every warp scans its share for the marks
+    for (int k = warp; k < (listed ? n_g : nUE); k += NW) {
+        const int u = listed ? s.guard_ue[k] : k;
+        const size_t i = (size_t)e * nUE + u;
+        uint32_t word = ldk(c.ho + i, keep);
+        if (!(word & HO_PENDING)) continue;
+        word &= ~HO_PENDING;
+        const short2 cell = ldk_cell(c.ue_cell, i, keep);
+        double bS, cS;
+        int bb, new_out, did_ho;
+        ue_row_f64_warp(c, c.fading == FADE_INJECTED ? a.fading + i * nBS : nullptr, s.bsx, s.bsy, genv, u, cell.x, cell.y, epoch,
+                        (int)(word & 31), &bb, &bS, &cS);
+        const double srvS = ho_decide<double>(c, mode, bb, bS, cS, word, new_out, did_ho);
+        if (lane == 0) {
+            stk(c.ho + i, word, keep);
+            // order-independent accumulation: the list order is not deterministic, the results must be
+            atomicAdd(reinterpret_cast<unsigned long long *>(&s.guard_sum), (unsigned long long)__double2ll_rn(srvS * 4294967296.0));
+            if (new_out) atomicAdd(&s.red_out[0], 1);
+            if (did_ho) atomicAdd(&s.red_ho[0], 1);
+            const int srv = word & 31;
+            const int lin = ((1 + srv) * G + cell.x) * G + cell.y;
+            if (a.serving) stk(a.serving + i, (uint8_t)srv, keep);
+            if (a.serving_sinr) stk(reinterpret_cast<float *>(a.serving_sinr) + i, (float)srvS, keep);
+            if (a.obs_idx) stk(a.obs_idx + (size_t)e * (nUE + nBS) + u, lin, keep);
+            if (incremental) obs_add(obs_env, (long long)lin, 1.f, n_cells, c.err_flags);
+            if (lin_arr) lin_arr[u] = lin;
+        }
+    }
+}
+
 // One CTA per environment.  Warp roles (every warp also takes part in the per-UE loop):
 //   last warp: bulk copies of the zero tile;  last-1: group state load / finish;  last-2: action + BS_move
 template <int NB, bool F64, int NT, bool DIAG, bool GUARD>
@@ -1261,37 +1301,9 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // boundary are re-evaluated in float64 now that the UE loop's registers are dead (the call costs the hot loop
         // nothing), one warp per UE with lane = BS: a lone thread walking the row's float64 log10 / pow chains would hold
         // its CTA for tens of microseconds.  CTA-uniform branch, taken by about 2 % of the CTAs at the default guard.
-        const int n_g = s.guard_n;
-        if (n_g > 0) {
-            const bool listed = n_g <= GUARD_LIST;                       // else: every warp scans its share for the marks
-            for (int k = warp; k < (listed ? n_g : nUE); k += NW) {
-                const int u = listed ? s.guard_ue[k] : k;
-                const size_t i = (size_t)e * nUE + u;
-                uint32_t word = ldk(c.ho + i, keep);
-                if (!(word & HO_PENDING)) continue;
-                word &= ~HO_PENDING;
-                const short2 cell = ldk_cell(c.ue_cell, i, keep);
-                double bS, cS;
-                int bb, new_out, did_ho;
-                ue_row_f64_warp(c, c.fading == FADE_INJECTED ? a.fading + i * nBS : nullptr, s.bsx, s.bsy, genv, u, cell.x,
-                                cell.y, (uint32_t)epoch, (int)(word & 31), &bb, &bS, &cS);
-                const double srvS = ho_decide<double>(c, mode, bb, bS, cS, word, new_out, did_ho);
-                if (lane == 0) {
-                    stk(c.ho + i, word, keep);
-                    // order-independent accumulation: the list order is not deterministic, the results must be
-                    atomicAdd(reinterpret_cast<unsigned long long *>(&s.guard_sum), (unsigned long long)__double2ll_rn(srvS * 4294967296.0));
-                    if (new_out) atomicAdd(&s.red_out[0], 1);
-                    if (did_ho) atomicAdd(&s.red_ho[0], 1);
-                    const int srv = word & 31;
-                    if (a.serving) stk(a.serving + i, (uint8_t)srv, keep);
-                    if (a.serving_sinr) stk(reinterpret_cast<float *>(a.serving_sinr) + i, (float)srvS, keep);
-                    if (a.obs_idx) stk(a.obs_idx + (size_t)e * (nUE + nBS) + u, ((1 + srv) * G + cell.x) * G + cell.y, keep);
-                    if (incremental) obs_add(obs_env, (long long)(((size_t)(1 + srv) * G + cell.x) * G + cell.y), 1.f, n_cells, c.err_flags);
-                    if constexpr (NB > 4) {
-                        if (a.cells_off >= 0) reinterpret_cast<int32_t *>(dyn_smem + a.cells_off)[u] = ((1 + srv) * G + cell.x) * G + cell.y;
-                    }
-                }
-            }
+        if (s.guard_n > 0) {
+            guard_phase<NB, NT>(c, a, s, e, genv, (uint32_t)epoch, mode, incremental, obs_env, n_cells,
+                                (NB > 4 && a.cells_off >= 0) ? reinterpret_cast<int32_t *>(dyn_smem + a.cells_off) : nullptr);
             __syncthreads();
         }
     }
