@@ -475,6 +475,17 @@ def main():
                                         "frac": ach_d / measured_peak_gbs()[0], "algorithmic_bytes_per_env_step": b_d,
                                         "kernel": _kernel_name(dw["n_bs"], args.precision)},
                            "device_error_flags": denv.check()}
+        if args.precision != "fp32":
+            # the plain fp32 kernels on the same workload (no float64 re-evaluation of near-tie UEs)
+            denv.close()
+            denv = BatchedMobiEnvironment(dw["envs"], dw["n_bs"], dw["n_ue"], GRID, "group", precision="fp32", seed=2026,
+                                          env_offset=rank * dw["envs"], device=local_rank)
+            denv.reset()
+            ms_p, l_p, _, _ = time_env_steps(denv, dpool, n_d, 3, barrier)
+            ms_p = udist.max_over_ranks([ms_p], dev)[0]
+            ach_p = b_d * dw["envs"] / (ms_p * 1e-3 / max(l_p, 1)) / 1e9
+            extras["dense"]["fp32"] = {"ms_per_step": ms_p / n_d, "value": dw["envs"] * world * n_d / (ms_p * 1e-3),
+                                       "roofline_frac": ach_p / measured_peak_gbs()[0], "kernel": _kernel_name(dw["n_bs"], "fp32")}
         note("dense done")
         denv.close()
         del denv, dpool
