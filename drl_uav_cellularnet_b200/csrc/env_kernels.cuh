@@ -757,7 +757,8 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
     }
     // best server = the FIRST maximum (np.argmax, channel.py:141): the group's maximum by an fmax butterfly, then the
     // lowest BS index that attains it by a min butterfly (cheaper than carrying (value, index) pairs with tie tests)
-    float bestS = fmaxf(fmaxf(S0, S1), fmaxf(S2, S3));
+    const float hi01 = fmaxf(S0, S1), hi23 = fmaxf(S2, S3), mine = fmaxf(hi01, hi23);
+    float bestS = mine;
 #pragma unroll
     for (int o = 1; o < LPU; o <<= 1) bestS = fmaxf(bestS, __shfl_xor_sync(0xffffffffu, bestS, o));
     int best = S0 == bestS ? b0 : (S1 == bestS ? b0 + 1 : (S2 == bestS ? b0 + 2 : (S3 == bestS ? b0 + 3 : 255)));
@@ -766,9 +767,10 @@ __device__ __forceinline__ float ue_channel_quad(const DevCfg &c, const CallArgs
     float second = -3.0e38f;
     if constexpr (GUARD) {
         // FP32_GUARDED: the runner-up (largest SINR of any OTHER BS): its gap to the maximum says whether the argmax can
-        // be trusted
-        second = fmaxf(fmaxf(b0 == best ? -3.0e38f : S0, b0 + 1 == best ? -3.0e38f : S1),
-                       fmaxf(b0 + 2 == best ? -3.0e38f : S2, b0 + 3 == best ? -3.0e38f : S3));
+        // be trusted.  The lane that holds the best server offers the second largest of its four (equal to the largest
+        // if two of them tie), every other lane its largest.
+        const float mine2 = fmaxf(fminf(hi01, hi23), fmaxf(fminf(S0, S1), fminf(S2, S3)));
+        second = (best >> 2) == q ? mine2 : mine;
 #pragma unroll
         for (int o = 1; o < LPU; o <<= 1) second = fmaxf(second, __shfl_xor_sync(0xffffffffu, second, o));
     }
@@ -1103,6 +1105,8 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
         // is: sums are accumulated in fixed point.
         __shared__ int4 wstage_all[NW * 32];
         int4 *wst = wstage_all + warp * 32;
+        __shared__ float wsecond_all[GUARD ? NW * 32 : 1];             // FP32_GUARDED: runner-up SINR per staged UE
+        float *wsec = wsecond_all + (GUARD ? warp * 32 : 0);
         // flat observation index of every UE for the count REDs after barrier 2 (if the env's UEs fit; else HBM is re-read)
         int32_t *lin_arr = a.cells_off >= 0 ? reinterpret_cast<int32_t *>(dyn_smem + a.cells_off) : nullptr;
         // The zero stream (the tile was zeroed by all threads before barrier 1) is issued by the TMA warp only now, after
@@ -1195,11 +1199,11 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 const float curS = full_bs
                     ? ue_channel_quad<NB, DIAG, true, GUARD>(c, a, bx4, by4, e, genv, u0 + slot, cx, cy, (uint32_t)epoch, word, best, bestS, second)
                     : ue_channel_quad<NB, DIAG, false, GUARD>(c, a, bx4, by4, e, genv, u0 + slot, cx, cy, (uint32_t)epoch, word, best, bestS, second);
-                const bool guarded = GUARD && guard_needed(c, mode, best, (int)(word & 31), bestS, second, curS);
                 if (live && q == 0) {
-                    // (best server, its SINR, current-cell SINR, FP32_GUARDED: re-evaluate?) for the decision pass
-                    reinterpret_cast<int2 *>(wst + slot)[0].y = (int)(word | ((uint32_t)best << 23) | (guarded ? HO_PENDING : 0u));
+                    // (best server, its SINR, current-cell SINR, FP32_GUARDED: the runner-up) for the decision pass
+                    reinterpret_cast<int2 *>(wst + slot)[0].y = (int)(word | ((uint32_t)best << 23));
                     reinterpret_cast<int2 *>(wst + slot)[1] = make_int2(__float_as_int(bestS), __float_as_int(curS));
+                    if (GUARD) wsec[slot] = second;
                 }
             }
             __syncwarp();
@@ -1208,13 +1212,14 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
                 const int4 sv = wst[lane];
                 const int cx = sv.x & 0xffff, cy = (int)((uint32_t)sv.x >> 16);
                 uint32_t word = (uint32_t)sv.y & 0x7fffffu;
-                if (GUARD && ((uint32_t)sv.y & HO_PENDING)) {
+                const int best = ((uint32_t)sv.y >> 23) & 31;
+                // the three margin tests once per UE here, not on every lane of the UE's group in pass B
+                if (GUARD && guard_needed(c, mode, best, (int)(word & 31), __int_as_float(sv.z), wsec[lane], __int_as_float(sv.w))) {
                     // FP32_GUARDED: decision deferred to the guard phase; the handover word keeps its pre-step value + a mark
                     const int slot = atomicAdd(&s.guard_n, 1);
                     if (slot < GUARD_LIST) s.guard_ue[slot] = uA;
                     stk(c.ho + iA, word | HO_PENDING, keep);
                 } else {
-                    const int best = ((uint32_t)sv.y >> 23) & 31;
                     int new_out, did_ho;
                     const float srvS = ho_decide<float>(c, mode, best, __int_as_float(sv.z), __int_as_float(sv.w), word, new_out, did_ho);
                     acc_fix += __double2ll_rn((double)srvS * 4294967296.0);
