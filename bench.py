@@ -533,9 +533,10 @@ def main():
                              "between steps; no explicit flush" % (E * 4e-6 * (N_BS + 1) * GRID * GRID)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": n_e2e, "ms_per_step": ms_e2e / n_e2e,
-                    "note": "uavenv_step_host: pinned host actions in (one async copy), kernel, rewards + done flags "
-                            "written by the kernel into the caller's pinned buffers, stream sync -- every step; the "
-                            "observation stays in HBM for the policy network",
+                    "note": "uavenv_step_host: the kernel reads the actions from the caller's pinned host buffer over PCIe "
+                            "and writes rewards + done flags into the caller's pinned buffers (the byte counts are those "
+                            "transfers), one launch + one stream sync every step; the observation stays in HBM for the "
+                            "policy network",
                     "with_sparse_state": {"value": total_envs * n_e2e / (ms_e2e_state * 1e-3), "ms_per_step": ms_e2e_state / n_e2e,
                                           "d2h_bytes_per_step": d2h + E * (N_UE + N_BS) * 4,
                                           "note": "the same step with the state also returned to the host, as obs_idx (the "
