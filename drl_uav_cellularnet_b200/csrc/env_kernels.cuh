@@ -870,6 +870,9 @@ constexpr int NT_SMALL = UAVENV_NT_SMALL;
 #ifndef UAVENV_MINB_SMALL
 #define UAVENV_MINB_SMALL 16
 #endif
+#ifndef UAVENV_QUAD_UNROLL
+#define UAVENV_QUAD_UNROLL 1      /* UE groups of the per-(UE, 4 BS) loop in flight per lane (tuning: 2 needs UAVENV_MINB_WIDE=2) */
+#endif
 constexpr int min_blocks(int nb, bool f64, int nt) { return f64 ? 1 : (nb > 8 ? UAVENV_MINB_WIDE : (nt == NT_SMALL ? UAVENV_MINB_SMALL : UAVENV_MINB)); }
 
 // fp32 mapping for more than 4 BSs: per warp, double-buffered landing area of the next chunk's state (cp.async)
@@ -1186,7 +1189,8 @@ env_kernel(const __grid_constant__ DevCfg c, const __grid_constant__ CallArgs a)
             __syncwarp();
             // ---- (B) NB/4 lanes = one UE, lane = 4 BSs
             const int last_slot = min(31, nUE - 1 - u0);               // shuffles need every lane on a valid UE
-#pragma unroll 1
+            constexpr int QUAD_UNROLL = UAVENV_QUAD_UNROLL;
+#pragma unroll QUAD_UNROLL
             for (int j = 0; j < LPU; j++) {
                 const int slot_raw = j * UPW + lane / LPU;
                 const bool live = slot_raw <= last_slot;
